@@ -1,0 +1,6 @@
+"""B200-native distortion-aware convolution path (sky-dome HDR reconstruction hot path).
+
+Importing this package loads libskydome_b200.so; a missing library is an ImportError (no CPU fallback)."""
+from . import _lib                      # noqa: F401  (fails loudly if the CUDA library is absent)
+from . import distortion_aware_ops     # noqa: F401
+from .distortion_aware_ops import conv2d, deconv2d   # noqa: F401

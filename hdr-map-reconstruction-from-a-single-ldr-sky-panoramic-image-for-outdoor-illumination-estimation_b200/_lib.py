@@ -1,0 +1,64 @@
+"""ctypes binding of libskydome_b200.so (include/skydome_b200.h).  There is no fallback: if the library is missing the
+import raises, and every op requires CUDA tensors."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libskydome_b200.so")
+
+OK = 0
+ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
+EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL = 0, 1, 2
+MATH_TF32, MATH_3XTF32 = 0, 1
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes): every symbol include/skydome_b200.h declares
+SIGNATURES = {
+    "sky_version": (_i, []),
+    "sky_last_error": (ctypes.c_char_p, []),
+    "sky_da_offsets_host": (_i, [_i, _i, _i, _i, _i, _vp]),
+    "sky_da_offsets_device": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sky_da_sample_debug": (_i, [_i, _i, _i, _vp] + [_vp] * 8 + [_vp]),
+    "sky_da_packed_weight_bytes": (_sz, [_i, _i, _i, _i]),
+    "sky_da_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sky_da_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+
+class SkydomeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"skydome_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built (run `python __graft_entry__.py` or "
+            f"`python {os.path.join(HERE, 'build.py')}`).  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == the .so does not export what the header declares
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+LIB = load()
+
+
+def check(rc):
+    if rc != OK:
+        msg = LIB.sky_last_error().decode("utf-8", "replace")
+        if rc == ERR_EVEN_KERNEL:
+            raise AssertionError(msg)                        # reference: assert at distortion_aware_ops.py:188
+        if rc == ERR_UNDEFINED_COORDS:
+            raise Exception("undefined coordinates")         # reference: distortion_aware_ops.py:252
+        if rc == ERR_INVALID:
+            raise ValueError(msg)
+        raise SkydomeError(rc, msg)
+    return rc

@@ -1,0 +1,487 @@
+// Forward distortion-aware convolution (distortion_aware_ops.py:50-123) for sm_100a.
+//
+//   sky_da_pack_weights     kernel [k*k*C, F] -> K-major SWIZZLE_128B tiles of 32 k-values x F_pad filters (TF32, rna)
+//   sky_da_conv2d_fwd       warp-specialised implicit GEMM: producer warps evaluate the sampling geometry, gather the
+//                           four corners with 128-bit loads, blend, and write the A tile in the UMMA swizzled layout;
+//                           one thread streams the weight tiles with bulk async copies; one thread issues
+//                           tcgen05.mma (kind::tf32) into TMEM; the producer warps then drain TMEM (tcgen05.ld), add
+//                           the bias (+ LeakyReLU / residual) and store NHWC.
+//   sky_da_conv2d_fwd_simt  fp32 CUDA-core restatement of the same contract (cross-check, odd shapes)
+//   sky_resize_bilinear_fwd TF2 half-pixel bilinear resize (deconv2d.call :322)
+#include "da_geometry.cuh"
+
+namespace sky {
+
+constexpr int BLOCK_M = 128;        // output pixels per CTA tile (UMMA M)
+constexpr int BLOCK_K = 32;         // fp32/tf32 values per 128-byte swizzled row
+constexpr int UMMA_K = 8;           // k per tcgen05.mma for tf32
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int NUM_THREADS = NUM_PRODUCER_THREADS + 64;   // + MMA warp + weight-loader warp
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int f_pad_of(int F) { return round_up(F < 16 ? 16 : F, 16); }
+
+// -----------------------------------------------------------------------------------------------------------------
+// weight prepack
+// -----------------------------------------------------------------------------------------------------------------
+// packed[kb][plane][n_tile rows][32] : for k-block kb the image is exactly what the MMA expects in shared memory, so a
+// stage is filled by one contiguous bulk copy.  plane 0 = tf32(rna(w)); plane 1 (3xTF32 only) = tf32(rna(w - hi)).
+__global__ void da_pack_weights_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int K, int F, int Fp,
+                                       int KB, int planes)
+{
+    const long total = (long)KB * Fp * BLOCK_K;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % BLOCK_K);
+        const int n = (int)((e / BLOCK_K) % Fp);
+        const int kb = (int)(e / ((long)BLOCK_K * Fp));
+        const int kidx = kb * BLOCK_K + kk;
+        float v = 0.f;
+        if (kidx < K && n < F) v = kernel[(size_t)kidx * F + n];
+        const uint32_t hi = f32_to_tf32_rna(v);
+        const size_t tile_floats = (size_t)Fp * BLOCK_K;
+        const size_t o = (sw128_offset((uint32_t)n, (uint32_t)(kk >> 2)) >> 2) + (kk & 3);
+        packed[((size_t)kb * planes + 0) * tile_floats + o] = __uint_as_float(hi);
+        if (planes == 2) {
+            const float lo = v - __uint_as_float(hi);
+            packed[((size_t)kb * planes + 1) * tile_floats + o] = __uint_as_float(f32_to_tf32_rna(lo));
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// tensor-core forward
+// -----------------------------------------------------------------------------------------------------------------
+struct FwdParams {
+    const float *x;
+    const float *offsets;   // [h][k2][2]
+    const float *packed;
+    const float *bias;
+    const float *residual;
+    float *y;
+    int B, h, w, C, F, Fp, k, k2, K, KB;
+    int in_h, in_w, ph0, pw0;
+    int M;                  // B*h*w
+    int flags;
+    float slope;
+};
+
+template <int STAGES, bool SPLIT3>
+struct FwdSmem {
+    static constexpr int PLANES = SPLIT3 ? 2 : 1;
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;                    // 16 KB per plane
+    static __host__ __device__ int b_bytes(int Fp) { return Fp * BLOCK_K * 4; }
+    static __host__ __device__ int stage_bytes(int Fp) { return PLANES * (A_BYTES + b_bytes(Fp)); }
+    static __host__ __device__ int total_bytes(int Fp)
+    {
+        // stages | coord table (2 x 128 x 32 B) | barriers | tmem slot ; +1024 for manual alignment
+        return STAGES * stage_bytes(Fp) + 2 * BLOCK_M * 32 + (2 * STAGES + 1) * 8 + 16 + 1024;
+    }
+};
+
+// One 16-byte chunk (4 channels) of one A row: 4 corner loads, blend in the reference's add_n order (:112-113).
+__device__ __forceinline__ float4 blend4(const float *__restrict__ x, const CornerRef &cr, int ch)
+{
+    float4 p[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        p[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cr.off[c] >= 0) p[c] = __ldg(reinterpret_cast<const float4 *>(x + cr.off[c] + ch));
+    }
+    float4 r;
+    r.x = cr.w[0] * p[0].x; r.y = cr.w[0] * p[0].y; r.z = cr.w[0] * p[0].z; r.w = cr.w[0] * p[0].w;
+#pragma unroll
+    for (int c = 1; c < 4; ++c) {
+        r.x = fmaf(cr.w[c], p[c].x, r.x);
+        r.y = fmaf(cr.w[c], p[c].y, r.y);
+        r.z = fmaf(cr.w[c], p[c].z, r.z);
+        r.w = fmaf(cr.w[c], p[c].w, r.w);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store_a_chunk(uint8_t *a_tile, int row, int chunk, float4 v, bool split3)
+{
+    uint4 hi;
+    hi.x = f32_to_tf32_rna(v.x); hi.y = f32_to_tf32_rna(v.y); hi.z = f32_to_tf32_rna(v.z); hi.w = f32_to_tf32_rna(v.w);
+    const uint32_t o = sw128_offset((uint32_t)row, (uint32_t)chunk);
+    *reinterpret_cast<uint4 *>(a_tile + o) = hi;
+    if (split3) {
+        uint4 lo;
+        lo.x = f32_to_tf32_rna(v.x - __uint_as_float(hi.x));
+        lo.y = f32_to_tf32_rna(v.y - __uint_as_float(hi.y));
+        lo.z = f32_to_tf32_rna(v.z - __uint_as_float(hi.z));
+        lo.w = f32_to_tf32_rna(v.w - __uint_as_float(hi.w));
+        *reinterpret_cast<uint4 *>(a_tile + BLOCK_M * BLOCK_K * 4 + o) = lo;
+    }
+}
+
+template <int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const FwdParams p)
+{
+    using L = FwdSmem<STAGES, SPLIT3>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = L::stage_bytes(p.Fp);
+    const int b_bytes = L::b_bytes(p.Fp);
+    CornerRef *coord = reinterpret_cast<CornerRef *>(smem + STAGES * stage_bytes);           // [2][BLOCK_M]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * stage_bytes + 2 * BLOCK_M * 32);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tmem_full = smem_u32(bars + 2 * STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BLOCK_M;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.Fp) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, NUM_PRODUCER_THREADS / 32 + 1);   // 4 producer warps + the weight loader
+            mbar_init(empty0 + 8 * s, 1);                              // tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {   // TMEM allocation is warp-wide
+        tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== PRODUCERS: geometry -> gather -> blend -> swizzled A tile ===========================
+        const bool fast = (p.C % BLOCK_K) == 0;
+        const int chunk = tid & 7;            // 16-byte chunk inside the 128-byte row
+        const int row_base = tid >> 3;        // rows row_base + 16*i
+        int kb = 0;
+        if (fast) {
+            const int cpt = p.C / BLOCK_K;    // k-blocks per tap
+            // this thread's own pixel (row = tid) for the per-tap coordinate table
+            const int m = m0 + tid;
+            const bool m_ok = m < p.M;
+            const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
+            for (int t = 0; t < p.k2; ++t) {
+                CornerRef cr;
+                if (m_ok) {
+                    const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
+                    const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
+                    const Sample s = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
+                    cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { cr.off[c] = -1; cr.w[c] = 0.f; }
+                }
+                CornerRef *tab = coord + (t & 1) * BLOCK_M;
+                tab[tid] = cr;
+                named_bar_sync(1, NUM_PRODUCER_THREADS);
+                for (int cc = 0; cc < cpt; ++cc, ++kb) {
+                    const int s = kb % STAGES;
+                    mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                    uint8_t *a_tile = smem + s * stage_bytes;
+                    const int ch = cc * BLOCK_K + chunk * 4;
+#pragma unroll 4
+                    for (int r = 0; r < BLOCK_M / 16; ++r) {
+                        const int row = row_base + 16 * r;
+                        const CornerRef c = tab[row];
+                        store_a_chunk(a_tile, row, chunk, blend4(p.x, c, ch), SPLIT3);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full0 + 8 * s);
+                }
+            }
+        } else {
+            // generic channel counts (3-channel image layers, C not a multiple of 32): geometry per element
+            for (; kb < p.KB; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                uint8_t *a_tile = smem + s * stage_bytes;
+                for (int r = 0; r < BLOCK_M / 16; ++r) {
+                    const int row = row_base + 16 * r;
+                    const int m = m0 + row;
+                    float v[4] = { 0.f, 0.f, 0.f, 0.f };
+                    if (m < p.M) {
+                        const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int kidx = kb * BLOCK_K + chunk * 4 + e;
+                            if (kidx < p.K) {
+                                const int t = kidx / p.C, c = kidx % p.C;
+                                const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
+                                const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
+                                const Sample sm = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
+                                const CornerRef cr = da_corners(sm, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+                                float acc = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float px = cr.off[q] >= 0 ? __ldg(p.x + cr.off[q] + c) : 0.f;
+                                    acc = (q == 0) ? cr.w[0] * px : fmaf(cr.w[q], px, acc);
+                                }
+                                v[e] = acc;
+                            }
+                        }
+                    }
+                    store_a_chunk(a_tile, row, chunk, make_float4(v[0], v[1], v[2], v[3]), SPLIT3);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
+            }
+        }
+
+        // =========================== EPILOGUE: TMEM -> registers -> bias/activation/residual -> NHWC ===========================
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;         // TMEM lane == tile row
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const bool vec_ok = (p.F % 4) == 0;
+        for (int c0 = 0; c0 < p.Fp; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr_row + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (m < p.M) {
+                float o[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int f = c0 + q;
+                    float val = __uint_as_float(r[q]);
+                    if (f < p.F) {
+                        val += __ldg(p.bias + f);
+                        if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
+                        if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.F + f);
+                    }
+                    o[q] = val;
+                }
+                float *dst = p.y + (size_t)m * p.F + c0;
+                if (vec_ok && c0 + 16 <= p.F) {
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(dst + q) = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (c0 + q < p.F) dst[q] = o[q];
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // =========================== MMA ISSUER (one elected lane) ===========================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BLOCK_M, (uint32_t)p.Fp);
+            for (int kb = 0; kb < p.KB; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_hi = a_hi + L::PLANES * L::A_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                    const uint32_t koff = ks * UMMA_K * 4;
+                    const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
+                    const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
+                    umma_tf32(tmem_base, da, db, idesc, (kb | ks) != 0);
+                    if (SPLIT3) {
+                        const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff);
+                        const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + b_bytes + koff);
+                        umma_tf32(tmem_base, da_lo, db, idesc, 1);
+                        umma_tf32(tmem_base, da, db_lo, idesc, 1);
+                    }
+                }
+                umma_commit(empty0 + 8 * s);            // smem stage free once these MMAs have read it
+            }
+            umma_commit(tmem_full);                      // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // =========================== WEIGHT LOADER (one elected lane, bulk async copies) ===========================
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(L::PLANES * b_bytes);
+            for (int kb = 0; kb < p.KB; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                const uint32_t dst = smem_u32(smem + s * stage_bytes + L::PLANES * L::A_BYTES);
+                mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                bulk_g2s(dst, reinterpret_cast<const uint8_t *>(p.packed) + (size_t)kb * bytes, bytes, full0 + 8 * s);
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// CUDA-core restatement
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void da_conv2d_fwd_simt_kernel(const float *__restrict__ x, const float *__restrict__ offsets,
+                                          const float *__restrict__ kernel, const float *__restrict__ bias,
+                                          float *__restrict__ y, int B, int h, int w, int C, int F, int k)
+{
+    const int k2 = k * k;
+    int ph0, pht, pw0, pwt;
+    pad_axis(h, k, &ph0, &pht);
+    pad_axis(w, k, &pw0, &pwt);
+    const long total = (long)B * h * w * F;
+    for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
+        const int f = (int)(o % F);
+        const long m = o / F;
+        const int j = (int)(m % w), i = (int)((m / w) % h), b_img = (int)(m / ((long)w * h));
+        float acc = 0.f;
+        for (int t = 0; t < k2; ++t) {
+            const float yo = offsets[((size_t)i * k2 + t) * 2 + 0], xo = offsets[((size_t)i * k2 + t) * 2 + 1];
+            const Sample s = da_sample(i, j, t / k, t % k, yo, xo, h + pht, w + pwt);
+            const CornerRef cr = da_corners(s, b_img, h, w, C, ph0, pw0);
+            for (int c = 0; c < C; ++c) {
+                float pix = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float px = cr.off[q] >= 0 ? x[cr.off[q] + c] : 0.f;
+                    pix = (q == 0) ? __fmul_rn(cr.w[0], px) : __fadd_rn(pix, __fmul_rn(cr.w[q], px));   // add_n order
+                }
+                acc = fmaf(pix, kernel[((size_t)t * C + c) * F + f], acc);
+            }
+        }
+        y[o] = acc + bias[f];
+    }
+}
+
+// TF2 bilinear resize, half-pixel centres: src = (dst + 0.5) * (in/out) - 0.5 ; lower = max(floor, 0) ;
+// upper = min(ceil, n-1) ; lerp = src - floor(src) ; top/bottom lerp in x, then lerp in y.
+__global__ void resize_bilinear_kernel(const float *__restrict__ x, float *__restrict__ y, int B, int h, int w, int C,
+                                       int oh, int ow)
+{
+    const float sy = __fdiv_rn((float)h, (float)oh), sx = __fdiv_rn((float)w, (float)ow);
+    const long total = (long)B * oh * ow * C;
+    for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(o % C);
+        const int ox = (int)((o / C) % ow), oy = (int)((o / ((long)C * ow)) % oh), b = (int)(o / ((long)C * ow * oh));
+        const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sy), 0.5f);
+        const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sx), 0.5f);
+        const float fly = floorf(fy), flx = floorf(fx);
+        const int ylo = max((int)fly, 0), yhi = min((int)ceilf(fy), h - 1);
+        const int xlo = max((int)flx, 0), xhi = min((int)ceilf(fx), w - 1);
+        const float ly = __fsub_rn(fy, fly), lx = __fsub_rn(fx, flx);
+        const float *img = x + (size_t)b * h * w * C + c;
+        const float tl = img[((size_t)ylo * w + xlo) * C], tr = img[((size_t)ylo * w + xhi) * C];
+        const float bl = img[((size_t)yhi * w + xlo) * C], br = img[((size_t)yhi * w + xhi) * C];
+        const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+        const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+        y[o] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+    }
+}
+
+static int check_conv_args(int B, int h, int w, int C, int F, int k)
+{
+    SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension (B=%d h=%d w=%d C=%d F=%d)", B, h, w, C, F);
+    SKY_REQUIRE(k % 2 == 1, SKY_ERR_EVEN_KERNEL, "kernel_size must be odd number, current kernel size : %d", k);
+    SKY_REQUIRE(k >= 3 && k <= 15, SKY_ERR_UNSUPPORTED, "kernel_size %d outside the supported odd range 3..15", k);
+    SKY_REQUIRE((long)B * h * w * (long)(C > F ? C : F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
+    return SKY_OK;
+}
+
+template <int STAGES, bool SPLIT3>
+static int launch_fwd(const FwdParams &p, cudaStream_t st)
+{
+    using L = FwdSmem<STAGES, SPLIT3>;
+    const int smem = L::total_bytes(p.Fp);
+    static int configured = 0;
+    if (configured < smem) {
+        SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_fwd_tc_kernel<STAGES, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = 227 * 1024;
+    }
+    SKY_REQUIRE(smem <= 227 * 1024, SKY_ERR_UNSUPPORTED, "shared memory %d B exceeds 227 KB (F=%d)", smem, p.F);
+    const int grid = (p.M + BLOCK_M - 1) / BLOCK_M;
+    da_conv2d_fwd_tc_kernel<STAGES, SPLIT3><<<grid, NUM_THREADS, smem, st>>>(p);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+}  // namespace sky
+
+using namespace sky;
+
+extern "C" size_t sky_da_packed_weight_bytes(int C, int F, int k, int math_mode)
+{
+    if (C <= 0 || F <= 0 || k <= 0) return 0;
+    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K, Fp = f_pad_of(F);
+    const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
+    return (size_t)KB * planes * Fp * BLOCK_K * sizeof(float);
+}
+
+extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int F, int k, int math_mode, void *stream)
+{
+    SKY_REQUIRE(kernel && packed, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(C > 0 && F > 0 && k > 0, SKY_ERR_INVALID, "non-positive dimension");
+    SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
+    SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K, Fp = f_pad_of(F);
+    const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
+    const long total = (long)KB * Fp * BLOCK_K;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, K, F, Fp, KB, planes);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const void *packed, const float *bias, float *y,
+                                 const float *residual, int B, int h, int w, int C, int F, int k, int epilogue_flags,
+                                 float slope, int math_mode, void *stream)
+{
+    int rc = check_conv_args(B, h, w, C, F, k);
+    if (rc != SKY_OK) return rc;
+    SKY_REQUIRE(x && offsets && packed && bias && y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
+    SKY_REQUIRE(!(epilogue_flags & SKY_EPI_RESIDUAL) || residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
+    SKY_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
+    FwdParams p;
+    p.x = x; p.offsets = offsets; p.packed = (const float *)packed; p.bias = bias; p.residual = residual; p.y = y;
+    p.B = B; p.h = h; p.w = w; p.C = C; p.F = F; p.Fp = f_pad_of(F); p.k = k; p.k2 = k * k;
+    p.K = k * k * C; p.KB = (p.K + BLOCK_K - 1) / BLOCK_K;
+    int pht, pwt;
+    pad_axis(h, k, &p.ph0, &pht);
+    pad_axis(w, k, &p.pw0, &pwt);
+    p.in_h = h + pht; p.in_w = w + pwt;
+    p.M = B * h * w;
+    p.flags = epilogue_flags; p.slope = slope;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (math_mode == SKY_MATH_TF32) {
+        // 3 stages of 16 KB + Fp*128 B keep two CTAs resident per SM for F <= 128
+        return p.Fp <= 128 ? launch_fwd<3, false>(p, st) : launch_fwd<4, false>(p, st);
+    } else if (math_mode == SKY_MATH_3XTF32) {
+        return p.Fp <= 128 ? launch_fwd<3, true>(p, st) : launch_fwd<2, true>(p, st);
+    }
+    SKY_REQUIRE(false, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+}
+
+extern "C" int sky_da_conv2d_fwd_simt(const float *x, const float *offsets, const float *kernel, const float *bias, float *y,
+                                      int B, int h, int w, int C, int F, int k, void *stream)
+{
+    int rc = check_conv_args(B, h, w, C, F, k);
+    if (rc != SKY_OK) return rc;
+    SKY_REQUIRE(x && offsets && kernel && bias && y, SKY_ERR_INVALID, "NULL pointer");
+    const long total = (long)B * h * w * F;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    da_conv2d_fwd_simt_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, offsets, kernel, bias, y, B, h, w, C, F, k);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_resize_bilinear_fwd(const float *x, float *y, int B, int h, int w, int C, int oh, int ow, void *stream)
+{
+    SKY_REQUIRE(x && y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && oh > 0 && ow > 0, SKY_ERR_INVALID, "non-positive dimension");
+    const long total = (long)B * oh * ow * C;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    resize_bilinear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
