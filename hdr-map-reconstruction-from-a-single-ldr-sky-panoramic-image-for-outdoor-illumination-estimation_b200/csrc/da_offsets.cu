@@ -132,7 +132,9 @@ __global__ void da_offsets_kernel(int h, int w, int k, int dilation, int skydome
         for (int t = 0; t < 2 * k * k; ++t)
             if (isnan(row[t])) rc = SKY_ERR_NAN_OFFSET;
     }
-    if (rc != SKY_OK) atomicMin(status, rc);
+    // "undefined coordinates" is raised inside distortion() and therefore wins over a NaN table
+    if (rc == SKY_ERR_UNDEFINED_COORDS) atomicExch(status, rc);
+    else if (rc != SKY_OK) atomicCAS(status, SKY_OK, rc);
 }
 
 __global__ void da_sample_debug_kernel(int h, int w, int k, const float *__restrict__ offsets, int32_t *y0, int32_t *y1,
