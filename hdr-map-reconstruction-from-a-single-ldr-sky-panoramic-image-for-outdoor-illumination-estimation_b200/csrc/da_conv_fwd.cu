@@ -8,18 +8,12 @@
 //                           the bias (+ LeakyReLU / residual) and store NHWC.
 //   sky_da_conv2d_fwd_simt  fp32 CUDA-core restatement of the same contract (cross-check, odd shapes)
 //   sky_resize_bilinear_fwd TF2 half-pixel bilinear resize (deconv2d.call :322)
-#include "da_geometry.cuh"
+#include "da_conv.cuh"
 
 namespace sky {
 
-constexpr int BLOCK_M = 128;        // output pixels per CTA tile (UMMA M)
-constexpr int BLOCK_K = 32;         // fp32/tf32 values per 128-byte swizzled row
-constexpr int UMMA_K = 8;           // k per tcgen05.mma for tf32
 constexpr int NUM_PRODUCER_THREADS = 128;
 constexpr int NUM_THREADS = NUM_PRODUCER_THREADS + 64;   // + MMA warp + weight-loader warp
-
-__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-__host__ __device__ inline int f_pad_of(int F) { return round_up(F < 16 ? 16 : F, 16); }
 
 // -----------------------------------------------------------------------------------------------------------------
 // weight prepack
@@ -58,6 +52,7 @@ struct FwdParams {
     const float *bias;
     const float *residual;
     float *y;
+    double *stats;
     int B, h, w, C, F, Fp, k, k2, K, KB;
     int in_h, in_w, ph0, pw0;
     int M;                  // B*h*w
@@ -251,6 +246,11 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                         val += __ldg(p.bias + f);
                         if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
                         if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.F + f);
+                        if (p.stats) {   // generic path: plain atomics (the band-staged kernel reduces per tile first)
+                            double *st = p.stats + ((size_t)(m / (p.h * p.w)) * p.F + f) * 2;
+                            atomicAdd(st, (double)val);
+                            atomicAdd(st + 1, (double)val * (double)val);
+                        }
                     }
                     o[q] = val;
                 }
@@ -430,9 +430,28 @@ extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int
     return SKY_OK;
 }
 
-extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const void *packed, const float *bias, float *y,
-                                 const float *residual, int B, int h, int w, int C, int F, int k, int epilogue_flags,
-                                 float slope, int math_mode, void *stream)
+int sky::launch_fwd_direct(const FwdArgs &a)
+{
+    FwdParams p;
+    p.x = a.x; p.offsets = a.offsets; p.packed = a.packed; p.bias = a.bias; p.residual = a.residual; p.y = a.y; p.stats = a.stats;
+    p.B = a.B; p.h = a.h; p.w = a.w; p.C = a.C; p.F = a.F; p.Fp = f_pad_of(a.F); p.k = a.k; p.k2 = a.k * a.k;
+    p.K = a.k * a.k * a.C; p.KB = (p.K + BLOCK_K - 1) / BLOCK_K;
+    int pht, pwt;
+    pad_axis(a.h, a.k, &p.ph0, &pht);
+    pad_axis(a.w, a.k, &p.pw0, &pwt);
+    p.in_h = a.h + pht; p.in_w = a.w + pwt;
+    p.M = a.B * a.h * a.w;
+    p.flags = a.flags; p.slope = a.slope;
+    if (a.math_mode == SKY_MATH_TF32) {
+        // 3 stages of 16 KB + Fp*128 B keep two CTAs resident per SM for F <= 128
+        return p.Fp <= 128 ? launch_fwd<3, false>(p, a.stream) : launch_fwd<4, false>(p, a.stream);
+    }
+    return p.Fp <= 128 ? launch_fwd<3, true>(p, a.stream) : launch_fwd<2, true>(p, a.stream);
+}
+
+extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const float *offsets_host, const void *packed,
+                                 const float *bias, float *y, const float *residual, double *stats, int B, int h, int w,
+                                 int C, int F, int k, int epilogue_flags, float slope, int math_mode, void *stream)
 {
     int rc = check_conv_args(B, h, w, C, F, k);
     if (rc != SKY_OK) return rc;
@@ -440,24 +459,16 @@ extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const voi
     SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
     SKY_REQUIRE(!(epilogue_flags & SKY_EPI_RESIDUAL) || residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
     SKY_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
-    FwdParams p;
-    p.x = x; p.offsets = offsets; p.packed = (const float *)packed; p.bias = bias; p.residual = residual; p.y = y;
-    p.B = B; p.h = h; p.w = w; p.C = C; p.F = F; p.Fp = f_pad_of(F); p.k = k; p.k2 = k * k;
-    p.K = k * k * C; p.KB = (p.K + BLOCK_K - 1) / BLOCK_K;
-    int pht, pwt;
-    pad_axis(h, k, &p.ph0, &pht);
-    pad_axis(w, k, &p.pw0, &pwt);
-    p.in_h = h + pht; p.in_w = w + pwt;
-    p.M = B * h * w;
-    p.flags = epilogue_flags; p.slope = slope;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (math_mode == SKY_MATH_TF32) {
-        // 3 stages of 16 KB + Fp*128 B keep two CTAs resident per SM for F <= 128
-        return p.Fp <= 128 ? launch_fwd<3, false>(p, st) : launch_fwd<4, false>(p, st);
-    } else if (math_mode == SKY_MATH_3XTF32) {
-        return p.Fp <= 128 ? launch_fwd<3, true>(p, st) : launch_fwd<2, true>(p, st);
+    SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+    FwdArgs a;
+    a.x = x; a.offsets = offsets; a.offsets_host = offsets_host; a.packed = (const float *)packed; a.bias = bias;
+    a.residual = residual; a.y = y; a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k;
+    a.flags = epilogue_flags; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
+    if (offsets_host != nullptr && (C % BLOCK_K) == 0 && !(epilogue_flags & SKY_EPI_FORCE_DIRECT)) {
+        rc = launch_fwd_band(a);
+        if (rc != SKY_ERR_UNSUPPORTED) return rc;
     }
-    SKY_REQUIRE(false, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+    return launch_fwd_direct(a);
 }
 
 extern "C" int sky_da_conv2d_fwd_simt(const float *x, const float *offsets, const float *kernel, const float *bias, float *y,

@@ -183,3 +183,24 @@ __device__ __host__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
 #endif  // __CUDACC__
 
 }  // namespace sky
+
+#ifdef __CUDACC__
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+namespace sky {
+// 4-D tiled TMA load (fastest dim first: c, x, y, b) into shared memory; out-of-bounds elements are zero-filled,
+// which is exactly the zero halo of _pad_input (distortion_aware_ops.py:125-150).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap *tmap, int c, int x, int y, int b, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst_smem), "l"(tmap), "r"(c), "r"(x), "r"(y), "r"(b), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// Host: encode a 4-D fp32 NHWC tensor map with box (box_c, box_w, box_h, 1), no swizzle.
+int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, int w, int C, int box_c, int box_w, int box_h);
+}  // namespace sky
+#endif

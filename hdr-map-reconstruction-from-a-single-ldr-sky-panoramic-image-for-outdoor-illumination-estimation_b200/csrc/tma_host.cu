@@ -1,0 +1,38 @@
+// Host-side TMA descriptor encoding.  cuTensorMapEncodeTiled lives in libcuda; it is resolved at run time through the
+// runtime's driver entry-point query so the library links against cudart only.
+#include "sky_common.cuh"
+
+namespace sky {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, int w, int C, int box_c, int box_w, int box_h)
+{
+    EncodeTiledFn enc = get_encoder();
+    SKY_REQUIRE(enc != nullptr, SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B };
+    cuuint64_t strides[3] = { (cuuint64_t)C * 4, (cuuint64_t)w * C * 4, (cuuint64_t)h * w * C * 4 };
+    cuuint32_t box[4] = { (cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKY_REQUIRE(r == CUDA_SUCCESS, SKY_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (B=%d h=%d w=%d C=%d box=%dx%dx%d)", (int)r,
+                B, h, w, C, box_c, box_w, box_h);
+    return SKY_OK;
+}
+
+}  // namespace sky

@@ -98,6 +98,9 @@ CASES = [
     (1, 8, 32, 40, 24, 3),      # C % 32 != 0 and C % 4 == 0
     (1, 8, 32, 32, 256, 3),     # widest N
     (1, 32, 128, 64, 64, 3),    # full-resolution map
+    (2, 64, 256, 32, 32, 3),    # wide map: tiles away from the seam, tiles on it
+    (1, 12, 48, 32, 16, 5),     # k=5, sizes that are not multiples of the tile
+    (5, 4, 16, 64, 32, 3),      # map smaller than a tile (64 pixels per panorama)
 ]
 
 
@@ -117,6 +120,14 @@ def test_conv_forward_vs_oracle(pkg, ops, B, h, w, C, F, k):
         got = layer(xd).cpu().numpy()
         assert np.isfinite(got).all()
         assert rel_l2(got, want) <= tol, (mode, rel_l2(got, want))
+        # the direct-gather kernel (no smem band) must agree with the band-staged one
+        direct = layer(xd, force_direct=True).cpu().numpy()
+        assert rel_l2(direct, want) <= tol, (mode, "direct", rel_l2(direct, want))
+        # fused instance-norm moments: sum and sum of squares of y per (sample, filter)
+        stats = torch.zeros(B, F, 2, dtype=torch.float64, device="cuda")
+        y2 = layer(xd, stats=stats)
+        ref_s = torch.stack([y2.double().sum((1, 2)), (y2.double() ** 2).sum((1, 2))], dim=-1)
+        assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-4), (stats - ref_s).abs().max()
         assert tuple(layer.offset.shape) == (1, h, w, k * k, 2)
         assert tuple(layer.kernel.shape) == (k * k * C, F) and tuple(layer.bias.shape) == (F,)
 
