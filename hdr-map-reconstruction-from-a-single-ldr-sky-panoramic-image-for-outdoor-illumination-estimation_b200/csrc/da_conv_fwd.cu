@@ -20,15 +20,22 @@ constexpr int NUM_THREADS = NUM_PRODUCER_THREADS + 64;   // + MMA warp + weight-
 // -----------------------------------------------------------------------------------------------------------------
 // packed[kb][plane][n_tile rows][32] : for k-block kb the image is exactly what the MMA expects in shared memory, so a
 // stage is filled by one contiguous bulk copy.  plane 0 = tf32(rna(w)); plane 1 (3xTF32 only) = tf32(rna(w - hi)).
+// k-block order: for C % 32 == 0 the tiles are stored chunk-major, kb = cc * k2 + tap (the order the conv kernels walk K:
+// all taps of one 32-channel chunk, then the next chunk), so consecutive taps of a chunk are contiguous; otherwise
+// k-block kb simply covers kernel rows [32 kb, 32 kb + 32).
 __global__ void da_pack_weights_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int K, int F, int Fp,
-                                       int KB, int planes)
+                                       int KB, int planes, int C, int k2)
 {
     const long total = (long)KB * Fp * BLOCK_K;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const int kk = (int)(e % BLOCK_K);
         const int n = (int)((e / BLOCK_K) % Fp);
         const int kb = (int)(e / ((long)BLOCK_K * Fp));
-        const int kidx = kb * BLOCK_K + kk;
+        int kidx = kb * BLOCK_K + kk;
+        if (C % BLOCK_K == 0) {
+            const int cc = kb / k2, t = kb % k2;
+            kidx = t * C + cc * BLOCK_K + kk;
+        }
         float v = 0.f;
         if (kidx < K && n < F) v = kernel[(size_t)kidx * F + n];
         const uint32_t hi = f32_to_tf32_rna(v);
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
 {
     using L = FwdSmem<STAGES, SPLIT3>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
     const int stage_bytes = L::stage_bytes(p.Fp);
     const int b_bytes = L::b_bytes(p.Fp);
     CornerRef *coord = reinterpret_cast<CornerRef *>(smem + STAGES * stage_bytes);           // [2][BLOCK_M]
@@ -157,7 +164,8 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
             const int m = m0 + tid;
             const bool m_ok = m < p.M;
             const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
-            for (int t = 0; t < p.k2; ++t) {
+            for (int kk = 0; kk < cpt * p.k2; ++kk) {     // chunk-major k-block order (matches the packed weights)
+                const int cc = kk / p.k2, t = kk % p.k2;
                 CornerRef cr;
                 if (m_ok) {
                     const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
@@ -168,10 +176,10 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { cr.off[c] = -1; cr.w[c] = 0.f; }
                 }
-                CornerRef *tab = coord + (t & 1) * BLOCK_M;
+                CornerRef *tab = coord + (kk & 1) * BLOCK_M;
                 tab[tid] = cr;
                 named_bar_sync(1, NUM_PRODUCER_THREADS);
-                for (int cc = 0; cc < cpt; ++cc, ++kb) {
+                {
                     const int s = kb % STAGES;
                     mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
                     uint8_t *a_tile = smem + s * stage_bytes;
@@ -185,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8 * s);
+                    ++kb;
                 }
             }
         } else {
@@ -425,7 +434,7 @@ extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int
     const long total = (long)KB * Fp * BLOCK_K;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, K, F, Fp, KB, planes);
+    da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, K, F, Fp, KB, planes, C, k * k);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }

@@ -3,26 +3,45 @@
 // One CTA per SM loops over tiles of TH x TW = 128 output pixels of one panorama.  Per tile and 32-channel chunk the
 // input band the tile can touch (tile + halo derived from the offset table) is brought into shared memory by ONE TMA
 // tensor load whose out-of-bounds zero fill *is* the zero halo of _pad_input (distortion_aware_ops.py:125-150).
-// Warp roles (352 threads):
-//   warps 0-3  producers   per k-block (chunk cc, tap t): exact sampling geometry (da_sample) for the thread's pixel ->
-//                          table in smem; then each thread blends 8 (pixel, 16-byte chunk) items from the band
-//                          (4 x LDS.128 + fma) and writes them TF32-rounded into the SWIZZLE_128B A stage.
-//                          Corners the band does not hold (360-degree wrap at the seam, zenith row) are read from global.
-//   warps 4-7  epilogue    tcgen05.ld the finished accumulator (double-buffered in TMEM), bias / LeakyReLU, stage
-//                          through smem for coalesced stores, residual add, per-(sample, filter) sum / sum-of-squares
-//                          for the instance norm that follows (generator.py:27-33).
-//   warp 8     MMA         one lane issues tcgen05.mma.kind::tf32 (M=128, N=F_pad, K=8) x4 per k-block.
-//   warp 9     weights     one lane streams the packed weight tile of each k-block with a bulk async copy.
-//   warp 10    band        one lane issues the TMA tensor load of each (tile, chunk) band.
+//
+// The sampling offsets depend on (row, tap) only (distortion_aware_ops.py:266-268), so RUN horizontally adjacent
+// output pixels read RUN+1 adjacent input columns from the same two input rows with the same bilinear factors.  A
+// producer thread therefore blends a whole run from 2*(RUN+1) 128-bit shared-memory loads instead of 4*RUN.
+//
+// Warp roles (15 warps):
+//   warps 0-7   producers  two groups of 4 warps that alternate k-blocks (chunk cc, tap t).  Per run: vertical then
+//                          horizontal blend from the band, TF32 rounding, store into the SWIZZLE_128B A stage.  Runs
+//                          flagged irregular (360-degree wrap at the seam, zenith row, band miss) take an exact
+//                          per-pixel path.
+//   warps 8-11  epilogue + geometry.  Geometry, one tile ahead: exact reference geometry (da_sample) for every
+//                          (pixel, tap) of the next tile, reduced per run to {two band row offsets, 4 bilinear
+//                          factors, regular?}.  Epilogue: tcgen05.ld the finished accumulator (double-buffered in
+//                          TMEM), stage through smem, bias / LeakyReLU / residual, coalesced stores, and the
+//                          per-(sample, filter) sum / sum-of-squares for the instance norm that follows
+//                          (generator.py:27-33).
+//   warp 12     MMA        one lane issues tcgen05.mma.kind::tf32 (M=128, N=F_pad, K=8) x4 per k-block.
+//   warp 13     weights    one lane streams the packed weight tile of each k-block with a bulk async copy.
+//   warp 14     band       one lane issues the TMA tensor load of each (tile, chunk) band.
 #include <math.h>
 
 #include "da_conv.cuh"
 
 namespace sky {
 
-constexpr int BAND_THREADS = 352;
-constexpr int WARP_MMA = 8, WARP_WLOAD = 9, WARP_BAND = 10;
-constexpr int EPI_COLS = 32, EPI_STRIDE = 36;   // staging row stride (floats): odd multiple of 16 B -> conflict-free
+constexpr int RUN = 8;                              // output pixels per producer item (TW % 8 == 0)
+constexpr int NRUN = BLOCK_M / RUN;                 // runs per tile
+constexpr int GROUP_WARPS = NRUN * 8 / 32;          // one thread per (run, 16-byte chunk): 4 warps build one k-block
+constexpr int PROD_GROUPS = 2;                      // groups alternate k-blocks, so two A stages are being filled at once
+constexpr int PROD_WARPS = GROUP_WARPS * PROD_GROUPS;
+constexpr int EPI_WARP0 = PROD_WARPS;               // 4 epilogue/geometry warps; EPI_WARP0 % 4 == 0 keeps warp%4 == TMEM lane quadrant
+constexpr int WARP_MMA = PROD_WARPS + 4, WARP_WLOAD = PROD_WARPS + 5, WARP_BAND = PROD_WARPS + 6;
+constexpr int BAND_THREADS = (PROD_WARPS + 7) * 32;
+constexpr int EPI_COLS = 16, EPI_STRIDE = 20;       // staging row stride (floats): odd multiple of 16 B -> conflict-free
+// A pipeline stage holds up to ATOMS k-blocks (two consecutive taps of one 32-channel chunk).  One full/empty barrier
+// round trip costs the single MMA-issuing thread ~160 cycles (try_wait) + ~45 (commit), measured in
+// tools/ubench_sync.cu; a 32-wide k-block only buys 4 x 67 cycles of tensor work, so stages are made two k-blocks deep.
+constexpr int ATOMS = 1;
+static_assert(EPI_WARP0 % 4 == 0, "epilogue warps must align with TMEM lane quadrants");
 
 struct BandParams {
     const float *x, *offsets, *packed, *bias, *residual;
@@ -37,24 +56,24 @@ struct BandParams {
     uint32_t tmem_cols;
 };
 
-struct TabEntry {
-    int off[4];   // >= 0: byte offset of the pixel inside the band buffer; -1: zero; <= -2: global element offset -(off+2)
-    float w[4];
-};
-
+// Run table entry: ints {band-relative byte offset of (row y0, first column), same for row y1, regular?, -},
+// floats {dy1, dy0, dx1, dx0} of the run's first pixel (distortion_aware_ops.py:103-106 factors).
 template <int STAGES, bool SPLIT3>
 struct BandSmem {
     static constexpr int PLANES = SPLIT3 ? 2 : 1;
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
     static __host__ __device__ int b_bytes(int Fp) { return Fp * BLOCK_K * 4; }
-    static __host__ __device__ int stage_bytes(int Fp) { return PLANES * (A_BYTES + b_bytes(Fp)); }
-    static constexpr int TABLE_BYTES = 2 * BLOCK_M * (int)sizeof(TabEntry);
+    static constexpr int A_STAGE = ATOMS * PLANES * A_BYTES;
+    static __host__ __device__ int b_stage(int Fp) { return ATOMS * PLANES * b_bytes(Fp); }
+    static __host__ __device__ int stage_bytes(int Fp) { return STAGES * A_STAGE + STAGES * b_stage(Fp); }   // both rings
+    // run table: double-buffered by tile, [k2][NRUN] x (int4 + float4)
+    static __host__ __device__ int table_bytes(int k2) { return 2 * k2 * NRUN * 32; }
     static constexpr int EPI_BYTES = BLOCK_M * EPI_STRIDE * 4;
-    static constexpr int PART_BYTES = 4 * EPI_COLS * 2 * 4;
-    static __host__ __device__ int num_bars(int NB) { return 2 * STAGES + 2 * NB + 4; }
-    static __host__ __device__ int total_bytes(int Fp, int band_stride, int NB)
+    static constexpr int PART_BYTES = 128 * 8 * 4;
+    static __host__ __device__ int num_bars(int NB) { return 2 * STAGES + 2 * NB + 8; }
+    static __host__ __device__ int total_bytes(int Fp, int band_stride, int NB, int k2)
     {
-        return STAGES * stage_bytes(Fp) + NB * band_stride + TABLE_BYTES + EPI_BYTES + PART_BYTES + num_bars(NB) * 8 + 16 + 1024;
+        return stage_bytes(Fp) + NB * band_stride + table_bytes(k2) + EPI_BYTES + PART_BYTES + num_bars(NB) * 8 + 16 + 1024;
     }
 };
 
@@ -74,11 +93,16 @@ __device__ __forceinline__ void store_a(uint8_t *a_tile, int row, int chunk, flo
     }
 }
 
-__device__ __forceinline__ float4 fetch_corner(int off, const uint8_t *band, int chunk_bytes, const float *x, int ch_glob)
+// Exact per-pixel path for irregular runs: one corner of one pixel, 4 channels.
+__device__ __forceinline__ float4 fetch_exact(int yy_pad, int xx_pad, const BandParams &p, const uint8_t *band, int by0, int bx0,
+                                              int b_img, int chunk, int ch_glob)
 {
-    if (off >= 0) return *reinterpret_cast<const float4 *>(band + off + chunk_bytes);
-    if (off < -1) return __ldg(reinterpret_cast<const float4 *>(x + (size_t)(-(off + 2)) + ch_glob));
-    return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int yy = yy_pad - p.ph0, xx = xx_pad - p.pw0;
+    if (yy < 0 || yy >= p.h || xx < 0 || xx >= p.w) return make_float4(0.f, 0.f, 0.f, 0.f);   // zero halo
+    const int by = yy - by0, bx = xx - bx0;
+    if (by >= 0 && by < p.BH && bx >= 0 && bx < p.BW)
+        return *reinterpret_cast<const float4 *>(band + (by * p.BW + bx) * (BLOCK_K * 4) + chunk * 16);
+    return __ldg(reinterpret_cast<const float4 *>(p.x + ((size_t)(b_img * p.h + yy) * p.w + xx) * p.C + ch_glob));
 }
 
 template <int STAGES, bool SPLIT3>
@@ -87,33 +111,42 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
 {
     using L = BandSmem<STAGES, SPLIT3>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = L::stage_bytes(p.Fp);
+    // round the dynamic smem base up to 1024 B by OFFSET arithmetic (a uintptr_t round trip would demote every access
+    // below to generic LD/ST)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_bytes = L::b_bytes(p.Fp);
-    uint8_t *bands = smem + STAGES * stage_bytes;
-    TabEntry *table = reinterpret_cast<TabEntry *>(bands + p.NB * p.band_stride);
-    float *epi = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(table) + L::TABLE_BYTES);
+    const int b_stage = L::b_stage(p.Fp);
+    uint8_t *b_ring = smem + STAGES * L::A_STAGE;
+    uint8_t *bands = smem + L::stage_bytes(p.Fp);
+    uint8_t *table = bands + p.NB * p.band_stride;
+    const int tab_n = p.k2 * NRUN;                                                // entries per tile buffer
+    int4 *rt_i = reinterpret_cast<int4 *>(table);                                 // [2][k2][NRUN]
+    float4 *rt_w = reinterpret_cast<float4 *>(table + 2 * tab_n * 16);            // [2][k2][NRUN]
+    float *epi = reinterpret_cast<float *>(table + L::table_bytes(p.k2));
     float *part = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(epi) + L::EPI_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(part) + L::PART_BYTES);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + L::num_bars(p.NB));
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES;
     const uint32_t band_full0 = empty0 + 8 * STAGES, band_empty0 = band_full0 + 8 * p.NB;
     const uint32_t tmem_full0 = band_empty0 + 8 * p.NB, tmem_empty0 = tmem_full0 + 16;
+    const uint32_t rt_full0 = tmem_empty0 + 16, rt_empty0 = rt_full0 + 16;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 4 + 1);    // 4 producer warps + the weight loader's expect_tx arrive
-            mbar_init(empty0 + 8 * s, 1);       // tcgen05.commit
+            mbar_init(full0 + 8 * s, GROUP_WARPS + 1);  // the producer group that builds this k-block + the weight loader
+            mbar_init(empty0 + 8 * s, 1);               // tcgen05.commit (producers and the weight loader both wait on it)
         }
         for (int n = 0; n < p.NB; ++n) {
             mbar_init(band_full0 + 8 * n, 1);   // band loader's expect_tx arrive
-            mbar_init(band_empty0 + 8 * n, 4);  // 4 producer warps
+            mbar_init(band_empty0 + 8 * n, PROD_WARPS);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full0 + 8 * a, 1);   // tcgen05.commit
             mbar_init(tmem_empty0 + 8 * a, 4);  // 4 epilogue warps
+            mbar_init(rt_full0 + 8 * a, 4);     // 4 geometry (= epilogue) warps
+            mbar_init(rt_empty0 + 8 * a, PROD_WARPS);
         }
         fence_mbar_init();
     }
@@ -128,65 +161,81 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-    if (warp < 4) {
+    if (warp < PROD_WARPS) {
         // ================================================ PRODUCERS ================================================
-        const int chunk = tid & 7, row_base = tid >> 3;
-        const int pty = tid / p.TW, ptx = tid % p.TW;       // this thread's pixel inside the tile (table duty)
-        uint32_t kbg = 0, bandg = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int group = warp / GROUP_WARPS, gtid = tid - group * (GROUP_WARPS * 32);
+        const int chunk = gtid & 7, run = gtid >> 3;
+        const int rty = (run * RUN) / p.TW, rtx = (run * RUN) % p.TW;   // first pixel of this thread's run inside the tile
+        uint32_t sg = 0, bandg = 0, it = 0;     // sg: global stage counter (same sequence in every role)
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int b_img = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
-            const int i = i0 + pty, j = j0 + ptx;
-            const bool pix_ok = (i < p.h) && (j < p.w);
             const int by0 = i0 + p.hy_lo, bx0 = j0 + p.hx_lo;
+            const int ri = i0 + rty, rj = j0 + rtx;
+            const uint32_t tb = it & 1;
+            mbar_wait(rt_full0 + 8 * tb, (it >> 1) & 1);              // geometry of this tile is in the run table
+            const int4 *ti = rt_i + tb * tab_n + run;
+            const float4 *tw = rt_w + tb * tab_n + run;
             for (int cc = 0; cc < p.CC; ++cc, ++bandg) {
                 const int nb = bandg % p.NB;
                 mbar_wait(band_full0 + 8 * nb, (bandg / p.NB) & 1);
                 const uint8_t *band = bands + nb * p.band_stride;
                 const int ch_glob = cc * BLOCK_K + chunk * 4;
-                for (int t = 0; t < p.k2; ++t, ++kbg) {
-                    // ---- table duty: exact reference geometry for (pixel, tap) ----
-                    TabEntry e;
+                for (int t0 = 0; t0 < p.k2; t0 += ATOMS, ++sg) {
+                    if ((int)(sg % PROD_GROUPS) != group) continue;   // the other group builds this stage
+                    const int natoms = min(ATOMS, p.k2 - t0);
+                    const int s = sg % STAGES;
+                    mbar_wait(empty0 + 8 * s, ((sg / STAGES) & 1) ^ 1);
+                    for (int at = 0; at < natoms; ++at) {
+                        const int t = t0 + at;
+                        const int4 e = ti[t * NRUN];
+                        const float4 f = tw[t * NRUN];
+                        uint8_t *a_tile = smem + s * L::A_STAGE + at * (L::PLANES * L::A_BYTES);
+                        if (p.flags & (1 << 16)) {
+                            // timing experiment: no gather
+                        } else if (e.z) {
+                            // regular run: RUN+1 adjacent columns of two band rows
+                            const uint8_t *top = band + e.x + chunk * 16, *bot = band + e.y + chunk * 16;
+                            float4 v[RUN + 1];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) { e.off[c] = -1; e.w[c] = 0.f; }
-                    if (pix_ok) {
-                        const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
-                        const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
-                        const Sample s = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
-                        const int ys[4] = { s.y0, s.y0, s.y1, s.y1 };
-                        const int xs[4] = { s.x0, s.x1, s.x0, s.x1 };
-                        e.w[0] = s.w0; e.w[1] = s.w1; e.w[2] = s.w2; e.w[3] = s.w3;
+                            for (int c = 0; c <= RUN; ++c) {
+                                const float4 a = *reinterpret_cast<const float4 *>(top + c * (BLOCK_K * 4));
+                                const float4 b = *reinterpret_cast<const float4 *>(bot + c * (BLOCK_K * 4));
+                                v[c].x = fmaf(f.y, b.x, f.x * a.x);
+                                v[c].y = fmaf(f.y, b.y, f.x * a.y);
+                                v[c].z = fmaf(f.y, b.z, f.x * a.z);
+                                v[c].w = fmaf(f.y, b.w, f.x * a.w);
+                            }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int yy = ys[c] - p.ph0, xx = xs[c] - p.pw0;
-                            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
-                                const int by = yy - by0, bx = xx - bx0;
-                                if (by >= 0 && by < p.BH && bx >= 0 && bx < p.BW) e.off[c] = (by * p.BW + bx) * (BLOCK_K * 4);
-                                else e.off[c] = -2 - ((b_img * p.h + yy) * p.w + xx) * p.C;
+                            for (int q = 0; q < RUN; ++q) {
+                                float4 o;
+                                o.x = fmaf(f.w, v[q + 1].x, f.z * v[q].x);
+                                o.y = fmaf(f.w, v[q + 1].y, f.z * v[q].y);
+                                o.z = fmaf(f.w, v[q + 1].z, f.z * v[q].z);
+                                o.w = fmaf(f.w, v[q + 1].w, f.z * v[q].w);
+                                store_a(a_tile, run * RUN + q, chunk, o, SPLIT3);
+                            }
+                        } else {
+                            // irregular run: exact per-pixel geometry, corners from the band, from global, or the zero halo
+                            const float2 yx = (ri < p.h) ? __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)ri * p.k2 + t)
+                                                         : make_float2(0.f, 0.f);
+                            const int ta = t / p.k, tbb = t % p.k;
+                            for (int q = 0; q < RUN; ++q) {
+                                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (ri < p.h && rj + q < p.w) {
+                                    const Sample sm = da_sample(ri, rj + q, ta, tbb, yx.x, yx.y, p.in_h, p.in_w);
+                                    const float4 p0 = fetch_exact(sm.y0, sm.x0, p, band, by0, bx0, b_img, chunk, ch_glob);
+                                    const float4 p1 = fetch_exact(sm.y0, sm.x1, p, band, by0, bx0, b_img, chunk, ch_glob);
+                                    const float4 p2 = fetch_exact(sm.y1, sm.x0, p, band, by0, bx0, b_img, chunk, ch_glob);
+                                    const float4 p3 = fetch_exact(sm.y1, sm.x1, p, band, by0, bx0, b_img, chunk, ch_glob);
+                                    o.x = fmaf(sm.w3, p3.x, fmaf(sm.w2, p2.x, fmaf(sm.w1, p1.x, sm.w0 * p0.x)));
+                                    o.y = fmaf(sm.w3, p3.y, fmaf(sm.w2, p2.y, fmaf(sm.w1, p1.y, sm.w0 * p0.y)));
+                                    o.z = fmaf(sm.w3, p3.z, fmaf(sm.w2, p2.z, fmaf(sm.w1, p1.z, sm.w0 * p0.z)));
+                                    o.w = fmaf(sm.w3, p3.w, fmaf(sm.w2, p2.w, fmaf(sm.w1, p1.w, sm.w0 * p0.w)));
+                                }
+                                store_a(a_tile, run * RUN + q, chunk, o, SPLIT3);
                             }
                         }
-                    }
-                    TabEntry *tab = table + (kbg & 1) * BLOCK_M;
-                    tab[tid] = e;
-                    named_bar_sync(1, 128);
-                    // ---- gather + blend into the A stage ----
-                    const int s = kbg % STAGES;
-                    mbar_wait(empty0 + 8 * s, ((kbg / STAGES) & 1) ^ 1);
-                    uint8_t *a_tile = smem + s * stage_bytes;
-#pragma unroll 4
-                    for (int r = 0; r < BLOCK_M / 16; ++r) {
-                        const int row = row_base + 16 * r;
-                        const TabEntry q = tab[row];
-                        const float4 p0 = fetch_corner(q.off[0], band, chunk * 16, p.x, ch_glob);
-                        const float4 p1 = fetch_corner(q.off[1], band, chunk * 16, p.x, ch_glob);
-                        const float4 p2 = fetch_corner(q.off[2], band, chunk * 16, p.x, ch_glob);
-                        const float4 p3 = fetch_corner(q.off[3], band, chunk * 16, p.x, ch_glob);
-                        float4 v;   // add_n order of distortion_aware_ops.py:112-113
-                        v.x = fmaf(q.w[3], p3.x, fmaf(q.w[2], p2.x, fmaf(q.w[1], p1.x, q.w[0] * p0.x)));
-                        v.y = fmaf(q.w[3], p3.y, fmaf(q.w[2], p2.y, fmaf(q.w[1], p1.y, q.w[0] * p0.y)));
-                        v.z = fmaf(q.w[3], p3.z, fmaf(q.w[2], p2.z, fmaf(q.w[1], p1.z, q.w[0] * p0.z)));
-                        v.w = fmaf(q.w[3], p3.w, fmaf(q.w[2], p2.w, fmaf(q.w[1], p1.w, q.w[0] * p0.w)));
-                        store_a(a_tile, row, chunk, v, SPLIT3);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -195,107 +244,150 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 __syncwarp();
                 if (lane == 0) mbar_arrive(band_empty0 + 8 * nb);   // this warp no longer reads the band buffer
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rt_empty0 + 8 * tb);         // ... nor this tile's run table
         }
-    } else if (warp < 8) {
-        // ================================================ EPILOGUE ================================================
-        const int wq = warp - 4, etid = tid - 128;
+    } else if (warp < EPI_WARP0 + 4) {
+        // ================================================ EPILOGUE + GEOMETRY ================================================
+        const int wq = warp - EPI_WARP0, etid = tid - EPI_WARP0 * 32;
         const bool vec_ok = (p.F % 4) == 0;
+        int log_tw = 0;
+        while ((1 << log_tw) < p.TW) ++log_tw;            // TW is a power of two
+        // geometry duty: thread <-> tile pixel (row-major; TW % RUN == 0 => a run is RUN adjacent lanes)
+        const int gt = etid;
+        const int pty = gt / p.TW, ptx = gt % p.TW;
+        const int grun = gt / RUN, gq = gt % RUN;
+        const uint32_t run_mask = ((1u << RUN) - 1u) << (lane & ~(RUN - 1));
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        // geometry runs one tile ahead of the epilogue: table(tile_0) first, then per tile: table(next), epilogue(this)
+        for (int tile = blockIdx.x - (int)gridDim.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int gtile = tile + (int)gridDim.x;
+            const uint32_t git = (tile < 0) ? 0u : it + 1;
+            if (gtile < p.ntiles) {
+                const int rem = gtile % tiles_per_img;
+                const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
+                const int by0 = i0 + p.hy_lo, bx0 = j0 + p.hx_lo;
+                const int i = i0 + pty, j = j0 + ptx;
+                const bool pix_ok = (i < p.h) && (j < p.w);
+                const uint32_t tb = git & 1;
+                mbar_wait_sleep(rt_empty0 + 8 * tb, ((git >> 1) & 1) ^ 1);
+                int4 *ti = rt_i + tb * tab_n + grun;
+                float4 *tw = rt_w + tb * tab_n + grun;
+                int t = 0;
+                for (int a = 0; a < p.k; ++a)
+                    for (int b = 0; b < p.k; ++b, ++t) {
+                        Sample s;
+                        s.y0 = s.y1 = s.x0 = s.x1 = 0; s.dy1 = s.dy0 = s.dx1 = s.dx0 = 0.f;
+                        if (pix_ok) {
+                            const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
+                            s = da_sample(i, j, a, b, yx.x, yx.y, p.in_h, p.in_w);
+                        }
+                        // the run's first pixel defines the run; every in-image pixel must agree with it
+                        const int src = lane & ~(RUN - 1);
+                        const int fy0 = __shfl_sync(0xffffffffu, s.y0, src), fy1 = __shfl_sync(0xffffffffu, s.y1, src);
+                        const int fx0 = __shfl_sync(0xffffffffu, s.x0, src);
+                        const bool f_ok = __shfl_sync(0xffffffffu, (int)pix_ok, src) != 0;
+                        bool agree = !pix_ok || (f_ok && s.y0 == fy0 && s.y1 == fy1 && s.x0 == fx0 + gq && s.x1 == s.x0 + 1);
+                        const uint32_t votes = __ballot_sync(0xffffffffu, agree);
+                        if (gq == 0) {
+                            int4 e = make_int4(0, 0, 0, 0);
+                            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (pix_ok) {
+                                const int r0 = s.y0 - p.ph0 - by0, r1 = s.y1 - p.ph0 - by0, c0 = s.x0 - p.pw0 - bx0;
+                                const bool inside = r0 >= 0 && r0 < p.BH && r1 >= 0 && r1 < p.BH && c0 >= 0 && c0 + RUN < p.BW;
+                                // columns left of the image (x < 0 in the unpadded frame) are zero-filled by TMA only if they are
+                                // not wrapped pixels: a wrapped index lands inside the image far away, so `inside` already fails
+                                const bool regular = inside && ((votes & run_mask) == run_mask);
+                                e = make_int4((r0 * p.BW + c0) * (BLOCK_K * 4), (r1 * p.BW + c0) * (BLOCK_K * 4), regular ? 1 : 0, 0);
+                                f = make_float4(s.dy1, s.dy0, s.dx1, s.dx0);
+                            } else {
+                                e.z = 1;   // run entirely outside the panorama (tile overhang): rows are never stored; read anything
+                            }
+                            ti[t * NRUN] = e;
+                            tw[t * NRUN] = f;
+                        }
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rt_full0 + 8 * tb);
+
+            }
+            if (tile < 0) { it = (uint32_t)-1; continue; }     // prologue pass: only the first table
             const int b_img = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
             const uint32_t acc = it & 1;
-            mbar_wait(tmem_full0 + 8 * acc, (it >> 1) & 1);
+            mbar_wait_sleep(tmem_full0 + 8 * acc, (it >> 1) & 1);   // a whole tile away: back off, leave issue slots to producers
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.Fp + ((uint32_t)(wq * 32) << 16);
-            for (int c0 = 0; c0 < p.Fp; c0 += EPI_COLS) {
-                const int ncols = min(EPI_COLS, p.Fp - c0);   // 32 or 16
-                uint32_t r[32];
-                if (ncols == 32) tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                else {
-                    uint32_t r16[16];
-                    tmem_ld_32x16(taddr + (uint32_t)c0, r16);
+            for (int c0 = 0; c0 < ((p.flags & (1 << 19)) ? 0 : p.Fp); c0 += EPI_COLS) {   // bit 19: timing experiment, no epilogue
+                const int ncols = EPI_COLS;                   // F_pad is a multiple of 16
+                {   // phase 1: the row owner (TMEM lane) parks the raw accumulator row in the staging tile
+                    static_assert(EPI_COLS == 16, "phase 1 moves 16 columns per pass");
+                    uint32_t r[16];
+                    tmem_ld_32x16(taddr + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    uint4 *dst = reinterpret_cast<uint4 *>(epi + (wq * 32 + lane) * EPI_STRIDE);
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) { r[q] = r16[q]; r[q + 16] = 0u; }
-                }
-                tmem_ld_wait();
-                {   // phase 1: row-owner applies bias / activation and parks the row in the staging tile
-                    float *dst = epi + (wq * 32 + lane) * EPI_STRIDE;
-#pragma unroll
-                    for (int q = 0; q < 32; q += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int f = c0 + q + u;
-                            float val = __uint_as_float(r[q + u]);
-                            if (f < p.F) {
-                                val += __ldg(p.bias + f);
-                                if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
-                            } else val = 0.f;
-                            o[u] = val;
-                        }
-                        *reinterpret_cast<float4 *>(dst + q) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                 }
                 named_bar_sync(2, 128);
-                {   // phase 2: coalesced stores (8 threads cover 128 contiguous bytes of one pixel), residual add
-                    const int c4n = ncols / 4;
-                    for (int idx = etid; idx < BLOCK_M * c4n; idx += 128) {
-                        const int row = idx / c4n, c4 = idx % c4n;
-                        const int ii = i0 + row / p.TW, jj = j0 + row % p.TW;
-                        const int f = c0 + 4 * c4;
-                        if (ii < p.h && jj < p.w && f < p.F) {
-                            float *sp = epi + row * EPI_STRIDE + 4 * c4;
-                            float4 v = *reinterpret_cast<float4 *>(sp);
+                {   // phase 2: each thread owns 4 fixed columns -> bias / activation / residual, coalesced 128-byte stores,
+                    //          and the per-filter moments of what was stored
+                    const int lg = (ncols == 32) ? 3 : 2;             // log2(float4 columns per row)
+                    const int c4 = etid & ((1 << lg) - 1), row0 = etid >> lg, rstep = 128 >> lg;
+                    const int f = c0 + 4 * c4;
+                    float bv[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (f + u < p.F) bv[u] = __ldg(p.bias + f + u);
+                    float s1[4] = { 0.f, 0.f, 0.f, 0.f }, s2[4] = { 0.f, 0.f, 0.f, 0.f };
+                    if (f < p.F) {
+                        for (int row = row0; row < BLOCK_M; row += rstep) {
+                            const int ii = i0 + (row >> log_tw), jj = j0 + (row & (p.TW - 1));
+                            if (ii >= p.h || jj >= p.w) continue;
+                            const float4 raw = *reinterpret_cast<const float4 *>(epi + row * EPI_STRIDE + 4 * c4);
+                            float v[4] = { raw.x + bv[0], raw.y + bv[1], raw.z + bv[2], raw.w + bv[3] };
+                            if (p.flags & SKY_EPI_LEAKY_RELU) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * p.slope;
+                            }
                             const size_t go = ((size_t)(b_img * p.h + ii) * p.w + jj) * p.F + f;
                             if (vec_ok) {
                                 if (p.flags & SKY_EPI_RESIDUAL) {
                                     const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + go));
-                                    v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-                                    *reinterpret_cast<float4 *>(sp) = v;
+                                    v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
                                 }
-                                *reinterpret_cast<float4 *>(p.y + go) = v;
+                                *reinterpret_cast<float4 *>(p.y + go) = make_float4(v[0], v[1], v[2], v[3]);
                             } else {
-                                float vv[4] = { v.x, v.y, v.z, v.w };
                                 for (int u = 0; u < 4; ++u)
                                     if (f + u < p.F) {
-                                        if (p.flags & SKY_EPI_RESIDUAL) vv[u] += __ldg(p.residual + go + u);
-                                        p.y[go + u] = vv[u];
-                                    }
-                                *reinterpret_cast<float4 *>(sp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                                        if (p.flags & SKY_EPI_RESIDUAL) v[u] += __ldg(p.residual + go + u);
+                                        p.y[go + u] = v[u];
+                                    } else v[u] = 0.f;
                             }
-                        }
-                    }
-                }
-                if (p.stats) {   // phase 3: per-filter sum / sum of squares over the tile's valid pixels
-                    named_bar_sync(2, 128);
-                    const int c = etid & 31, g = etid >> 5;
-                    float s1 = 0.f, s2 = 0.f;
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = g * 32 + rr;
-                        const int ii = i0 + row / p.TW, jj = j0 + row % p.TW;
-                        if (ii < p.h && jj < p.w) {
-                            const float v = epi[row * EPI_STRIDE + c];
-                            s1 += v;
-                            s2 = fmaf(v, v, s2);
-                        }
-                    }
-                    part[(g * EPI_COLS + c) * 2 + 0] = s1;
-                    part[(g * EPI_COLS + c) * 2 + 1] = s2;
-                    named_bar_sync(2, 128);
-                    if (g == 0 && c < ncols && c0 + c < p.F) {
-                        double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-                        for (int gg = 0; gg < 4; ++gg) {
-                            d1 += (double)part[(gg * EPI_COLS + c) * 2 + 0];
-                            d2 += (double)part[(gg * EPI_COLS + c) * 2 + 1];
+                            for (int u = 0; u < 4; ++u) { s1[u] += v[u]; s2[u] = fmaf(v[u], v[u], s2[u]); }
                         }
-                        double *st = p.stats + ((size_t)b_img * p.F + c0 + c) * 2;
-                        atomicAdd(st, d1);
-                        atomicAdd(st + 1, d2);
+                    }
+                    if (p.stats) {
+                        // threads with the same c4 (stride 1<<lg in etid) hold partial sums of the same 4 filters
+                        float *pp = part + etid * 8;     // [128][8] floats
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { pp[u] = s1[u]; pp[4 + u] = s2[u]; }
+                        named_bar_sync(2, 128);
+                        if (etid < ncols && c0 + etid < p.F) {
+                            const int cc4 = etid >> 2, u = etid & 3;
+                            double d1 = 0.0, d2 = 0.0;
+                            for (int k = cc4; k < 128; k += (1 << lg)) {
+                                d1 += (double)part[k * 8 + u];
+                                d2 += (double)part[k * 8 + 4 + u];
+                            }
+                            double *st = p.stats + ((size_t)b_img * p.F + c0 + etid) * 2;
+                            atomicAdd(st, d1);
+                            atomicAdd(st + 1, d2);
+                        }
                     }
                 }
-                named_bar_sync(2, 128);   // staging tile is rewritten by the next column chunk
+                named_bar_sync(2, 128);   // staging tile (and the partial sums) are rewritten by the next column chunk
             }
             tc_fence_before();
             __syncwarp();
@@ -305,31 +397,39 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
         // ================================================ MMA ISSUER ================================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BLOCK_M, (uint32_t)p.Fp);
-            uint32_t kbg = 0, it = 0;
+            uint32_t sg = 0, it = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1;
                 mbar_wait(tmem_empty0 + 8 * acc, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Fp;
-                for (int kb = 0; kb < p.KB; ++kb, ++kbg) {
-                    const int s = kbg % STAGES;
-                    mbar_wait(full0 + 8 * s, (kbg / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
-                    const uint32_t b_hi = a_hi + L::PLANES * L::A_BYTES;
+                uint32_t first = 0;
+                for (int cc = 0; cc < p.CC; ++cc)
+                    for (int t0 = 0; t0 < p.k2; t0 += ATOMS, ++sg) {
+                        const int natoms = min(ATOMS, p.k2 - t0);
+                        const int s = sg % STAGES;
+                        mbar_wait(full0 + 8 * s, (sg / STAGES) & 1);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + s * L::A_STAGE);
+                        const uint32_t b0 = smem_u32(b_ring + s * b_stage);
+                        for (int at = 0; at < natoms; ++at) {
+                            const uint32_t a_hi = a0 + at * (L::PLANES * L::A_BYTES);
+                            const uint32_t b_hi = b0 + at * (L::PLANES * b_bytes);
 #pragma unroll
-                    for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-                        const uint32_t koff = ks * UMMA_K * 4;
-                        const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
-                        const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
-                        umma_tf32(d_tmem, da, db, idesc, (kb | ks) != 0);
-                        if (SPLIT3) {
-                            umma_tf32(d_tmem, umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff), db, idesc, 1);
-                            umma_tf32(d_tmem, da, umma_desc_kmajor_sw128(b_hi + b_bytes + koff), idesc, 1);
+                            for (int ks = 0; ks < ((p.flags & (1 << 20)) ? 0 : BLOCK_K / UMMA_K); ++ks) {   // bit 20: timing experiment, no MMA
+                                const uint32_t koff = ks * UMMA_K * 4;
+                                const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
+                                const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
+                                umma_tf32(d_tmem, da, db, idesc, first);
+                                first = 1;
+                                if (SPLIT3) {
+                                    umma_tf32(d_tmem, umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff), db, idesc, 1);
+                                    umma_tf32(d_tmem, da, umma_desc_kmajor_sw128(b_hi + b_bytes + koff), idesc, 1);
+                                }
+                            }
                         }
+                        umma_commit(empty0 + 8 * s);
                     }
-                    umma_commit(empty0 + 8 * s);
-                }
                 umma_commit(tmem_full0 + 8 * acc);
             }
         }
@@ -337,18 +437,21 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
     } else if (warp == WARP_WLOAD) {
         // ================================================ WEIGHT LOADER ================================================
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(L::PLANES * b_bytes);
-            uint32_t kbg = 0;
+            const uint32_t atom_bytes = (uint32_t)(L::PLANES * b_bytes);
+            uint32_t sg = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
                 for (int cc = 0; cc < p.CC; ++cc)
-                    for (int t = 0; t < p.k2; ++t, ++kbg) {
-                        const int s = kbg % STAGES;
-                        mbar_wait(empty0 + 8 * s, ((kbg / STAGES) & 1) ^ 1);
-                        const uint32_t dst = smem_u32(smem + s * stage_bytes + L::PLANES * L::A_BYTES);
+                    for (int t0 = 0; t0 < p.k2; t0 += ATOMS, ++sg) {
+                        const int natoms = min(ATOMS, p.k2 - t0);
+                        const int s = sg % STAGES;
+                        mbar_wait(empty0 + 8 * s, ((sg / STAGES) & 1) ^ 1);
+                        if (p.flags & (1 << 17)) { mbar_arrive(full0 + 8 * s); continue; }   // timing experiment: no weight load
+                        const uint32_t bytes = atom_bytes * natoms;
                         mbar_arrive_expect_tx(full0 + 8 * s, bytes);
-                        // packed tiles are stored in the kernel variable's row order: k-block = tap * CC + chunk
-                        const size_t kb_nat = (size_t)t * p.CC + cc;
-                        bulk_g2s(dst, reinterpret_cast<const uint8_t *>(p.packed) + kb_nat * bytes, bytes, full0 + 8 * s);
+                        // packed tiles are chunk-major (k-block = cc * k2 + tap): the taps of a stage are contiguous
+                        const size_t kb0 = (size_t)cc * p.k2 + t0;
+                        bulk_g2s(smem_u32(b_ring + s * b_stage), reinterpret_cast<const uint8_t *>(p.packed) + kb0 * atom_bytes, bytes,
+                                 full0 + 8 * s);
                     }
         }
         __syncwarp();
@@ -361,7 +464,8 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
                 for (int cc = 0; cc < p.CC; ++cc, ++bandg) {
                     const int nb = bandg % p.NB;
-                    mbar_wait(band_empty0 + 8 * nb, ((bandg / p.NB) & 1) ^ 1);
+                    mbar_wait_sleep(band_empty0 + 8 * nb, ((bandg / p.NB) & 1) ^ 1);
+                    if (p.flags & (1 << 18)) { mbar_arrive(band_full0 + 8 * nb); continue; }   // timing experiment: no band load
                     mbar_arrive_expect_tx(band_full0 + 8 * nb, (uint32_t)p.band_bytes);
                     tma_load_4d(smem_u32(bands + nb * p.band_stride), &tmap, cc * BLOCK_K, j0 + p.hx_lo, i0 + p.hy_lo, b_img,
                                 band_full0 + 8 * nb);
@@ -411,17 +515,18 @@ template <int STAGES, bool SPLIT3>
 static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span)
 {
     using L = BandSmem<STAGES, SPLIT3>;
-    static const int cand[8][2] = { { 8, 16 }, { 4, 32 }, { 16, 8 }, { 2, 64 }, { 1, 128 }, { 32, 4 }, { 64, 2 }, { 128, 1 } };
+    static const int cand[8][2] = { { 8, 16 }, { 4, 32 }, { 16, 8 }, { 2, 64 }, { 1, 128 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
     long best_cost = -1;
     for (int nb_try = (p.CC > 1 ? 2 : 1); nb_try >= 1 && best_cost < 0; --nb_try)
         for (int c = 0; c < 8; ++c) {
             const int TH = cand[c][0], TW = cand[c][1];
+            if (TH == 0 || TW % RUN != 0) continue;
             if ((TH > 2 * a.h && TH > 1) || (TW > 2 * a.w && TW > 1)) continue;
             const int BH = TH + hy_span, BW = TW + hx_span;
             if (BW > 256 || BH > 256) continue;
             const int band_bytes = BH * BW * BLOCK_K * 4;
             const int band_stride = round_up(band_bytes, 1024);
-            if (L::total_bytes(p.Fp, band_stride, nb_try) > 227 * 1024) continue;
+            if (L::total_bytes(p.Fp, band_stride, nb_try, p.k2) > 227 * 1024) continue;
             const int tiles_y = (a.h + TH - 1) / TH, tiles_x = (a.w + TW - 1) / TW;
             const long cost = (long)tiles_y * tiles_x * BH * BW;
             if (best_cost < 0 || cost < best_cost) {
@@ -437,7 +542,7 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
     int rc = encode_nhwc_tensor_map(&tmap, a.x, a.B, a.h, a.w, a.C, BLOCK_K, p.BW, p.BH);
     if (rc != SKY_OK) return rc;
 
-    const int smem = L::total_bytes(p.Fp, p.band_stride, p.NB);
+    const int smem = L::total_bytes(p.Fp, p.band_stride, p.NB, p.k2);
     static bool configured = false;
     if (!configured) {
         SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_fwd_band_kernel<STAGES, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -475,8 +580,8 @@ int launch_fwd_band(const FwdArgs &a)
     p.hy_lo = hy_lo; p.hx_lo = hx_lo;
     const int hy_span = hy_hi - hy_lo, hx_span = hx_hi - hx_lo;
     if (a.math_mode == SKY_MATH_TF32)
-        return p.Fp <= 128 ? launch_band<3, false>(p, a, hy_span, hx_span) : launch_band<2, false>(p, a, hy_span, hx_span);
-    return p.Fp <= 128 ? launch_band<2, true>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
+        return p.Fp <= 128 ? launch_band<4, false>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
+    return p.Fp <= 32 ? launch_band<2, true>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
 }
 
 }  // namespace sky

@@ -12,6 +12,8 @@ namespace sky {
 struct Sample {
     int y0, y1, x0, x1;    // corner coordinates in the reference's PADDED frame (:82-91)
     float w0, w1, w2, w3;  // bilinear weights (:103-106); corners (y0,x0) (y0,x1) (y1,x0) (y1,x1)
+    float dy1, dy0, dx1, dx0;  // the factors: w0 = dy1*dx1, w1 = dy1*dx0, w2 = dy0*dx1, w3 = dy0*dx0
+    bool wrapped;          // any 360-degree wrap applied to x (:76-77, :90-91)
 };
 
 // (i, j): output pixel; (a, b): tap row / column (tap = a*k + b, :152-168); in_h/in_w: padded map size.
@@ -32,6 +34,7 @@ __device__ __forceinline__ Sample da_sample(int i, int j, int a, int b, float y_
     if (x1 < 0) x1 += in_w;
     if (x0 > in_w - 1) x0 -= in_w;                 // :91
     if (x1 > in_w - 1) x1 -= in_w;
+    const bool wrapped = (x0 != x0_w) || (x1 != x1_w);
     const float dy1 = __fsub_rn((float)y1, y), dy0 = __fsub_rn(y, (float)y0);      // :103-106
     const float dx1 = __fsub_rn((float)x1_w, x), dx0 = __fsub_rn(x, (float)x0_w);
     Sample s;
@@ -40,6 +43,8 @@ __device__ __forceinline__ Sample da_sample(int i, int j, int a, int b, float y_
     s.w1 = __fmul_rn(dy1, dx0);
     s.w2 = __fmul_rn(dy0, dx1);
     s.w3 = __fmul_rn(dy0, dx0);
+    s.dy1 = dy1; s.dy0 = dy0; s.dx1 = dx1; s.dx0 = dx0;
+    s.wrapped = wrapped;
     return s;
 }
 

@@ -71,6 +71,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is still pending; test_wait never does)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) { }
@@ -90,6 +103,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// named barrier that also OR-reduces a predicate over the participating threads
+__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, uint32_t pred)
+{
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(pred), "r"(id), "r"(nthreads)
+        : "memory");
+    return r != 0;
+}
+// wait with back-off, for roles whose barrier is far away (keeps issue slots free for the producer warps)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------------------------------
