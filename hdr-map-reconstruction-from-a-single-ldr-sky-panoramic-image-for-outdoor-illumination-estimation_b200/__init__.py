@@ -4,3 +4,5 @@ Importing this package loads libskydome_b200.so; a missing library is an ImportE
 from . import _lib                      # noqa: F401  (fails loudly if the CUDA library is absent)
 from . import distortion_aware_ops     # noqa: F401
 from .distortion_aware_ops import conv2d, deconv2d   # noqa: F401
+from . import generator                 # noqa: F401
+from .generator import resBlock, resLayer, InstanceNormalization   # noqa: F401

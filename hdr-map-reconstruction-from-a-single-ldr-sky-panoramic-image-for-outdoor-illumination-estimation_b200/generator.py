@@ -1,0 +1,142 @@
+"""Host-side mirror of the residual trunk of the reference's generator.py: the same class names and constructor
+signatures (``resBlock(filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1)``,
+``resLayer(filters, filter_in, k_h, k_w, strides=1, dilation_rate=1)``) wired the way the commented lines
+generator.py:14,18 wire them: distortion-aware convolutions inside every res-block.
+
+    resBlock.call  (generator.py:26-35):  x + IN(conv2(leaky_relu_0.1(IN(conv1(x)))))
+
+Launches per res-block: conv1 (+ fused IN moments) -> IN apply + LeakyReLU -> conv2 (+ moments) -> IN apply + residual.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import LIB, check
+from .distortion_aware_ops import _require_cuda, _stream, conv2d as da_conv2d
+
+
+class InstanceNormalization:
+    """tfa.layers.InstanceNormalization() defaults: axis=-1, epsilon=1e-3, center/scale with beta=0, gamma=1."""
+
+    def __init__(self, epsilon=1e-3, device="cuda"):
+        self.epsilon = float(epsilon)
+        self.device = torch.device(device)
+        self.gamma = None
+        self.beta = None
+
+    def build(self, input_shape):
+        c = int(input_shape[-1])
+        self.gamma = torch.ones(c, dtype=torch.float32, device=self.device)
+        self.beta = torch.zeros(c, dtype=torch.float32, device=self.device)
+
+    @property
+    def trainable_variables(self):
+        return [self.gamma, self.beta]
+
+    def apply(self, x, stats, leaky_slope=None, residual=None):
+        """Normalise `x` with the fp64 moments `stats` [B, C, 2] that the producing conv accumulated."""
+        if self.gamma is None:
+            self.build(tuple(x.shape))
+        x = _require_cuda(x, "inputs")
+        B, h, w, C = x.shape
+        y = torch.empty_like(x)
+        flags = _lib.EPI_NONE
+        if leaky_slope is not None:
+            flags |= _lib.EPI_LEAKY_RELU
+        if residual is not None:
+            residual = _require_cuda(residual, "residual")
+            flags |= _lib.EPI_RESIDUAL
+        check(LIB.sky_instnorm_apply(x.data_ptr(), stats.data_ptr(), self.gamma.data_ptr(), self.beta.data_ptr(),
+                                     None if residual is None else residual.data_ptr(), y.data_ptr(), B, h, w, C,
+                                     self.epsilon, flags, float(leaky_slope or 0.0), _stream()))
+        return y
+
+
+class resBlock:
+    def __init__(self, filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1, *, math_mode=None, device="cuda"):
+        if k_h != k_w:
+            raise ValueError("the distortion-aware conv takes one kernel_size (generator.py:14)")
+        self.conv1 = da_conv2d(filter_out, kernel_size=k_h, strides=strides, dilation_rate=dilation_rate,
+                               math_mode=math_mode, device=device)            # generator.py:14
+        self.norm1 = InstanceNormalization(device=device)                       # :15
+        self.conv2 = da_conv2d(filter_out, kernel_size=k_h, strides=strides, dilation_rate=dilation_rate,
+                               math_mode=math_mode, device=device)            # :18
+        self.norm2 = InstanceNormalization(device=device)                       # :19
+        if filter_in != filter_out:                                             # :21-24 (never taken: the trunk is 128 -> 128)
+            raise NotImplementedError("1x1 projection shortcut (generator.py:24) is outside the hot path: every "
+                                      "res-block of the reference model has filter_in == filter_out == 128")
+        self._stats = None
+
+    def _moments(self, B, C, device):
+        if self._stats is None or self._stats.shape[1] != B or self._stats.shape[2] != C:
+            self._stats = torch.zeros(2, B, C, 2, dtype=torch.float64, device=device)
+        else:
+            self._stats.zero_()
+        return self._stats[0], self._stats[1]
+
+    @property
+    def trainable_variables(self):
+        return (self.conv1.trainable_variables + self.norm1.trainable_variables + self.conv2.trainable_variables
+                + self.norm2.trainable_variables)
+
+    def build(self, input_shape):
+        for conv, norm in ((self.conv1, self.norm1), (self.conv2, self.norm2)):
+            if not conv.built:
+                conv.build(tuple(input_shape))
+            shape = tuple(input_shape[:3]) + (conv.filters,)
+            if norm.gamma is None:
+                norm.build(shape)
+            input_shape = shape
+
+    def set_weights(self, w):
+        """w: dict conv{1,2}_kernel / conv{1,2}_bias / norm{1,2}_gamma / norm{1,2}_beta (numpy or torch), the reference's
+        variable names under each res-block."""
+        for i, (conv, norm) in enumerate(((self.conv1, self.norm1), (self.conv2, self.norm2)), start=1):
+            conv.kernel.copy_(torch.as_tensor(w[f"conv{i}_kernel"]))
+            conv.bias.copy_(torch.as_tensor(w[f"conv{i}_bias"]))
+            norm.gamma.copy_(torch.as_tensor(w[f"norm{i}_gamma"]))
+            norm.beta.copy_(torch.as_tensor(w[f"norm{i}_beta"]))
+
+    def call(self, x):
+        x = _require_cuda(x, "inputs")
+        if not self.conv1.built:
+            self.conv1.build(tuple(x.shape))
+        B = x.shape[0]
+        s1, s2 = self._moments(B, self.conv1.filters, x.device)
+        conv1 = self.conv1.call(x, stats=s1)                                    # :28
+        actv1 = self.norm1.apply(conv1, s1, leaky_slope=0.1)                    # :29-30
+        if not self.conv2.built:
+            self.conv2.build(tuple(actv1.shape))
+        conv2 = self.conv2.call(actv1, stats=s2)                                # :32
+        return self.norm2.apply(conv2, s2, residual=x)                          # :33-35
+
+    __call__ = call
+
+
+class resLayer:
+    def __init__(self, filters, filter_in, k_h, k_w, strides=1, dilation_rate=1, *, math_mode=None, device="cuda"):
+        self.sequence = list()
+        for f_in, f_out in zip([filter_in] + list(filters), filters):           # generator.py:43-44
+            self.sequence.append(resBlock(f_in, f_out, k_h=k_h, k_w=k_w, strides=strides, dilation_rate=dilation_rate,
+                                          math_mode=math_mode, device=device))
+
+    @property
+    def trainable_variables(self):
+        return [v for unit in self.sequence for v in unit.trainable_variables]
+
+    def build(self, input_shape):
+        for unit in self.sequence:
+            unit.build(input_shape)
+            input_shape = tuple(input_shape[:3]) + (unit.conv2.filters,)
+
+    def set_weights(self, blocks):
+        for unit, w in zip(self.sequence, blocks):
+            unit.set_weights(w)
+
+    def call(self, x):
+        for unit in self.sequence:                                              # :46-49
+            x = unit(x)
+        return x
+
+    __call__ = call
