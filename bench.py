@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native distortion-aware convolution path.
+
+Workload (config.workload): forward pass of the generator's residual trunk with the distortion-aware convolutions of
+generator.py:14,18 wired in — 6 res-blocks = 12 DA convs (128->128, k=3) + 12 instance norms (+LeakyReLU / residual) —
+on the trunk feature map of a batch of 32 synthetic 32x128 sky-dome panoramas per GPU ([32, 8, 32, 128] NHWC fp32).
+This is the slice of BASELINE.json config 1 ("generator inference, batch 32, 32x128") that runs through the hot path
+built so far; the encoder/decoder around it are next.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU under torchrun)
+    python bench.py --impl reference [--steps K] [--warmup W]      reference arm: the oracle's CPU restatement of the
+                                                                   same path on the host cores (TensorFlow itself is
+                                                                   not installable here)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BLOCKS, C, K_SIZE = 6, 128, 3
+METRIC, UNIT = "panoramas/sec (32x128, inference: DA residual trunk forward)", "panoramas/s"
+
+
+def make_weights(seed=0):
+    """numpy-seeded weights with the reference's initialiser distributions (glorot_uniform, zero bias, gamma 1, beta 0)."""
+    rng = np.random.default_rng(seed)
+    lim = (6.0 / (K_SIZE * K_SIZE * C + C)) ** 0.5
+    blocks = []
+    for _ in range(N_BLOCKS):
+        w = {}
+        for i in (1, 2):
+            w[f"conv{i}_kernel"] = rng.uniform(-lim, lim, (K_SIZE * K_SIZE * C, C)).astype(np.float32)
+            w[f"conv{i}_bias"] = np.zeros(C, np.float32)
+            w[f"norm{i}_gamma"] = np.ones(C, np.float32)
+            w[f"norm{i}_beta"] = np.zeros(C, np.float32)
+        blocks.append(w)
+    return blocks
+
+
+def make_input(batch, h, w, seed):
+    # trunk input = output of leaky_relu(IN(conv3_d(.))) (generator.py:104-106): unit-variance, LeakyReLU-shaped
+    x = np.random.default_rng(seed).standard_normal((batch, h, w, C)).astype(np.float32)
+    return np.where(x > 0, x, 0.1 * x).astype(np.float32)
+
+
+def workload_name(batch, H, W):
+    return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3, TF32) + 12 instance norms, "
+            f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:       # noqa: BLE001  (nvidia-smi missing: report empty clocks rather than fail the bench)
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """Reference arm: the path's CPU restatement (oracle port; TF cannot be installed) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import model_oracle as M
+    torch.set_num_threads(os.cpu_count())
+    sample = min(args.batch, 8)                     # bounded sample of the B=32 batch per step
+    h, w = args.height // 4, args.width // 4
+    blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
+    x = torch.from_numpy(make_input(sample, h, w, seed=1))
+    for _ in range(max(1, min(args.warmup, 2))):
+        M.res_layer(x, blocks, K_SIZE)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        M.res_layer(x, blocks, K_SIZE)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.batch, args.height, args.width),
+                       "note": "reference dataflow (materialised pad/gather/blend/matmul) restated on torch-CPU; not TensorFlow"},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{sample} of {args.batch} panoramas per step, {args.steps} steps"},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = load_package()
+
+    B, H, W = args.batch, args.height, args.width
+    h, w = H // 4, W // 4
+    trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
+    trunk.build((B, h, w, C))
+    trunk.set_weights(make_weights())
+    x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
+    y_host = torch.empty_like(x_host).pin_memory()
+    x = x_host.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
+
+    # ---- the step: captured once into a CUDA graph (24 kernel launches + 12 memsets) ----
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            y = trunk(x)                         # eager warm-up (packs weights, sizes scratch)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            y = trunk(x)
+    torch.cuda.synchronize()
+    launches_per_step = 4 * N_BLOCKS             # per res-block: 2 conv + 2 instance-norm kernels (ours)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                        # L2 flush between iterations, outside the timed events
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    def step_device():
+        graph.replay()
+
+    def step_e2e():
+        x.copy_(x_host, non_blocking=True)       # H2D of the step's input from pinned memory
+        graph.replay()
+        y_host.copy_(y, non_blocking=True)       # D2H of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(step_device, args.steps)
+    barrier()
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- dominant kernel: the band-staged DA conv, timed per launch with CUDA events on its stream ----
+    conv_ms = []
+    blk = trunk.sequence[0]
+    stats = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
+    for rep in range(12 + 3):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        blk.conv1.call(x, stats=stats)
+        e.record()
+        torch.cuda.synchronize()
+        if rep >= 3:
+            conv_ms.append(s.elapsed_time(e))
+    conv_t = float(np.mean(conv_ms))
+
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)           # max over ranks
+    t_dev, t_e2e = (float(v) / args.steps for v in tot.tolist())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else None
+        bf16_peak = peaks["bf16_tflops"] if peaks else 1590.0
+        flops = 2.0 * (B * h * w) * (K_SIZE * K_SIZE * C) * C
+        achieved = flops / (conv_t * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": round(world * B / (t_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
+            "config": {"workload": workload_name(B, H, W), "global_batch": world * B, "parallelism": f"batch shards x{world}, no collective",
+                       "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": True},
+            "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": round(t_e2e, 4)},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"kernel": "da_conv2d_fwd_band_kernel (128->128, k=3, M=%d)" % (B * h * w), "bound": "tensor",
+                         "achieved": round(achieved, 2), "peak": round(bf16_peak / 2, 1), "unit": "TFLOP/s",
+                         "frac": round(achieved / (bf16_peak / 2), 4), "traffic": traffic,
+                         "peak_note": ("TF32 operands: peak = 1/2 x measured bf16 burst (%s)" % ("of measured" if peaks else "of fallback")),
+                         "frac_of_bf16_peak": round(achieved / bf16_peak, 4), "ms_per_launch": round(conv_t, 5),
+                         "flops_per_launch": flops},
+            "clocks": clocks,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(B, h, w)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(B, h, w):
+    """The oracle (a port of the reference dataflow) timed on the host cores, on a bounded sample."""
+    import torch
+    from oracle import model_oracle as M
+    torch.set_num_threads(os.cpu_count())
+    sample = min(B, 8)
+    blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
+    x = torch.from_numpy(make_input(sample, h, w, seed=1))
+    M.res_layer(x, blocks, K_SIZE)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 40):
+        M.res_layer(x, blocks, K_SIZE)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(sample / dt, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sample} of {B} panoramas per step, {reps} steps, torch-CPU fp32 restatement of the reference dataflow"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="panoramas per GPU per step")
+    ap.add_argument("--height", type=int, default=32)
+    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
