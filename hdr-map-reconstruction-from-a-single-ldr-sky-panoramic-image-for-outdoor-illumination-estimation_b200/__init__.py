@@ -6,3 +6,4 @@ from . import distortion_aware_ops     # noqa: F401
 from .distortion_aware_ops import conv2d, deconv2d   # noqa: F401
 from . import generator                 # noqa: F401
 from .generator import resBlock, resLayer, InstanceNormalization   # noqa: F401
+from . import sharding                  # noqa: F401

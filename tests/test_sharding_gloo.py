@@ -1,0 +1,54 @@
+"""World-size-2 gloo test (CPU) of the batch-sharding host logic used by bench.py --gpus N."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG_NAME, ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, global_batch, ret):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = importlib.import_module(PKG_NAME).sharding
+    lo, hi = sh.shard_bounds(global_batch, rank, world)
+    full = torch.arange(global_batch * 6, dtype=torch.float32).reshape(global_batch, 2, 3)
+    local = full[lo:hi] * 2.0                       # stand-in for the per-sample forward
+    got = sh.gather_shards(local, global_batch)
+    ok = torch.equal(got, full * 2.0)
+    mx = sh.max_over_ranks([1.0 + rank, 5.0 - rank])
+    ret[rank] = (lo, hi, bool(ok), mx)
+    dist.destroy_process_group()
+
+
+def test_shards_cover_batch_and_timings_take_the_max():
+    for global_batch in (32, 33, 1):
+        world, port = 2, _free_port()
+        with mp.Manager() as m:
+            ret = m.dict()
+            mp.spawn(_worker, args=(world, port, global_batch, ret), nprocs=world, join=True)
+            ret = dict(ret)
+        assert ret[0][0] == 0 and ret[0][1] == ret[1][0] and ret[1][1] == global_batch
+        assert ret[0][2] and ret[1][2]
+        assert ret[0][3] == ret[1][3] == [2.0, 5.0]
+
+
+def test_shard_bounds_edge_cases(pkg):
+    sb = pkg.sharding.shard_bounds
+    assert [sb(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [sb(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]      # empty shards
+    assert sb(0, 0, 1) == (0, 0)
