@@ -26,6 +26,8 @@ SIGNATURES = {
     "sky_da_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
+    "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
