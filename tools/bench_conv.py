@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--math", default="tf32")
     ap.add_argument("--layers", default="all")
+    ap.add_argument("--bwd", action="store_true", help="also time dgrad and wgrad")
     ap.add_argument("--trunk-scale", action="store_true", help="run C128 layers at H/4 x W/4 (their site in the model)")
     args = ap.parse_args()
     pkg = load_package()
@@ -61,6 +62,16 @@ def main():
                                   tflops=round(flops / ms / 1e9, 2), gbs=round(bytes_ / ms / 1e6, 1),
                                   frac_tf32_peak=round(flops / ms / 1e9 / (peaks["bf16_tflops"] / 2), 4),
                                   frac_hbm=round(bytes_ / ms / 1e6 / peaks["hbm_gbs"], 4))), flush=True)
+            if args.bwd and C % 32 == 0 and F % 32 == 0:
+                dy = torch.randn(B, h, w, F, device="cuda")
+                bw = pkg.distortion_aware_ops.conv2d_backward
+                for name, fn in (("da_conv2d_bwd_data", lambda: bw(layer, x, dy, need_dw=False)),
+                                 ("da_conv2d_bwd_filter", lambda: bw(layer, x, dy, need_dx=False))):
+                    ms = time_op(fn, args.reps, flush)
+                    print(json.dumps(dict(op=name, math="tf32", B=B, h=h, w=w, C=C, F=F, k=k, ms=round(ms, 4),
+                                          tflops=round(flops / ms / 1e9, 2),
+                                          frac_tf32_peak=round(flops / ms / 1e9 / (peaks["bf16_tflops"] / 2), 4))), flush=True)
+                del dy
             del x, layer
 
 
