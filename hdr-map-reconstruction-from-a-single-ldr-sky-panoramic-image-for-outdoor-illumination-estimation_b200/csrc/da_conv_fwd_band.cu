@@ -8,31 +8,33 @@
 // output pixels read RUN+1 adjacent input columns from the same two input rows with the same bilinear factors.  A
 // producer thread therefore blends a whole run from 2*(RUN+1) 128-bit shared-memory loads instead of 4*RUN.
 //
-// Warp roles (15 warps):
-//   warps 0-7   producers  two groups of 4 warps that alternate k-blocks (chunk cc, tap t).  Per run: vertical then
+// Warp roles (23 warps):
+//   warps 0-15  producers  split into groups that alternate k-blocks (chunk cc, tap t).  Per run: vertical then
 //                          horizontal blend from the band, TF32 rounding, store into the SWIZZLE_128B A stage.  Runs
 //                          flagged irregular (360-degree wrap at the seam, zenith row, band miss) take an exact
 //                          per-pixel path.
-//   warps 8-11  epilogue + geometry.  Geometry, one tile ahead: exact reference geometry (da_sample) for every
+//   warps 16-19 epilogue + geometry.  Geometry, one tile ahead: exact reference geometry (da_sample) for every
 //                          (pixel, tap) of the next tile, reduced per run to {two band row offsets, 4 bilinear
 //                          factors, regular?}.  Epilogue: tcgen05.ld the finished accumulator (double-buffered in
 //                          TMEM), stage through smem, bias / LeakyReLU / residual, coalesced stores, and the
 //                          per-(sample, filter) sum / sum-of-squares for the instance norm that follows
 //                          (generator.py:27-33).
-//   warp 12     MMA        one lane issues tcgen05.mma.kind::tf32 (M=128, N=F_pad, K=8) x4 per k-block.
-//   warp 13     weights    one lane streams the packed weight tile of each k-block with a bulk async copy.
-//   warp 14     band       one lane issues the TMA tensor load of each (tile, chunk) band.
+//   warp 20     MMA        one lane issues tcgen05.mma.kind::tf32 (M=128, N=F_pad, K=8) x4 per k-block.
+//   warp 21     weights    one lane streams the packed weight tile of each k-block with a bulk async copy.
+//   warp 22     band       one lane issues the TMA tensor load of each (tile, chunk) band.
 #include <math.h>
 
 #include "da_conv.cuh"
 
 namespace sky {
 
-constexpr int RUN = 8;                              // output pixels per producer item (TW % 8 == 0)
-constexpr int NRUN = BLOCK_M / RUN;                 // runs per tile
-constexpr int GROUP_WARPS = NRUN * 8 / 32;          // one thread per (run, 16-byte chunk): 4 warps build one k-block
-constexpr int PROD_GROUPS = 2;                      // groups alternate k-blocks, so two A stages are being filled at once
-constexpr int PROD_WARPS = GROUP_WARPS * PROD_GROUPS;
+constexpr int RUN = 4;                              // output pixels per producer item (TW % 8 == 0)
+constexpr int NRUN = BLOCK_M / RUN;                 // run slots per tile (table stride)
+constexpr int PROD_WARPS = 16;                      // producer warps, four per SM sub-partition
+// The producer warps are split at run time into `ngroups` groups that alternate k-blocks (so that many A stages are
+// being filled at once): 2 groups x 8 warps for 128-pixel tiles, 4 groups x 4 warps for 64-pixel tiles (one thread per
+// (run, 16-byte chunk) item either way).  64-pixel tiles fill only half of the UMMA M = 128 rows; they are chosen when
+// the problem has too few 128-pixel tiles to occupy the SMs (the trunk of 32x128 panoramas at B = 32 has 64).
 constexpr int EPI_WARP0 = PROD_WARPS;               // 4 epilogue/geometry warps; EPI_WARP0 % 4 == 0 keeps warp%4 == TMEM lane quadrant
 constexpr int WARP_MMA = PROD_WARPS + 4, WARP_WLOAD = PROD_WARPS + 5, WARP_BAND = PROD_WARPS + 6;
 constexpr int BAND_THREADS = (PROD_WARPS + 7) * 32;
@@ -50,14 +52,16 @@ struct BandParams {
     int B, h, w, C, F, Fp, k, k2, CC, KB;
     int in_h, in_w, ph0, pw0;
     int TH, TW, tiles_x, tiles_y, ntiles;
+    int tile_px, ngroups, group_threads;   // tile_px = TH*TW (64 or 128); producer grouping
     int hy_lo, hx_lo, BH, BW, band_bytes, band_stride, NB;
     int flags;
     float slope;
     uint32_t tmem_cols;
 };
 
-// Run table entry: ints {band-relative byte offset of (row y0, first column), same for row y1, regular?, -},
-// floats {dy1, dy0, dx1, dx0} of the run's first pixel (distortion_aware_ops.py:103-106 factors).
+// Run table entry: one uint32 {bits 0-14: band offset of (row y0, first column) in 16-byte units, bit 15: regular?,
+// bits 16-31: same offset for row y1} and floats {dy1, dy0, dx1, dx0} of the run's first pixel
+// (the factors of distortion_aware_ops.py:103-106).
 template <int STAGES, bool SPLIT3>
 struct BandSmem {
     static constexpr int PLANES = SPLIT3 ? 2 : 1;
@@ -66,8 +70,8 @@ struct BandSmem {
     static constexpr int A_STAGE = ATOMS * PLANES * A_BYTES;
     static __host__ __device__ int b_stage(int Fp) { return ATOMS * PLANES * b_bytes(Fp); }
     static __host__ __device__ int stage_bytes(int Fp) { return STAGES * A_STAGE + STAGES * b_stage(Fp); }   // both rings
-    // run table: double-buffered by tile, [k2][NRUN] x (int4 + float4)
-    static __host__ __device__ int table_bytes(int k2) { return 2 * k2 * NRUN * 32; }
+    // run table: double-buffered by tile, [k2][NRUN] x (packed uint32 offsets + float4 factors)
+    static __host__ __device__ int table_bytes(int k2) { return 2 * k2 * NRUN * 20; }
     static constexpr int EPI_BYTES = BLOCK_M * EPI_STRIDE * 4;
     static constexpr int PART_BYTES = 128 * 8 * 4;
     static __host__ __device__ int num_bars(int NB) { return 2 * STAGES + 2 * NB + 8; }
@@ -120,8 +124,8 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
     uint8_t *bands = smem + L::stage_bytes(p.Fp);
     uint8_t *table = bands + p.NB * p.band_stride;
     const int tab_n = p.k2 * NRUN;                                                // entries per tile buffer
-    int4 *rt_i = reinterpret_cast<int4 *>(table);                                 // [2][k2][NRUN]
-    float4 *rt_w = reinterpret_cast<float4 *>(table + 2 * tab_n * 16);            // [2][k2][NRUN]
+    float4 *rt_w = reinterpret_cast<float4 *>(table);                             // [2][k2][NRUN]
+    uint32_t *rt_i = reinterpret_cast<uint32_t *>(table + 2 * tab_n * 16);        // [2][k2][NRUN]
     float *epi = reinterpret_cast<float *>(table + L::table_bytes(p.k2));
     float *part = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(epi) + L::EPI_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(part) + L::PART_BYTES);
@@ -135,7 +139,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, GROUP_WARPS + 1);  // the producer group that builds this k-block + the weight loader
+            mbar_init(full0 + 8 * s, p.group_threads / 32 + 1);   // the producer group that builds this k-block + the weight loader
             mbar_init(empty0 + 8 * s, 1);               // tcgen05.commit (producers and the weight loader both wait on it)
         }
         for (int n = 0; n < p.NB; ++n) {
@@ -163,8 +167,8 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
 
     if (warp < PROD_WARPS) {
         // ================================================ PRODUCERS ================================================
-        const int group = warp / GROUP_WARPS, gtid = tid - group * (GROUP_WARPS * 32);
-        const int chunk = gtid & 7, run = gtid >> 3;
+        const int group = tid / p.group_threads, gtid = tid % p.group_threads;
+        const int chunk = gtid & 7, run = gtid >> 3;           // run < tile_px / RUN by construction of the grouping
         const int rty = (run * RUN) / p.TW, rtx = (run * RUN) % p.TW;   // first pixel of this thread's run inside the tile
         uint32_t sg = 0, bandg = 0, it = 0;     // sg: global stage counter (same sequence in every role)
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -174,7 +178,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
             const int ri = i0 + rty, rj = j0 + rtx;
             const uint32_t tb = it & 1;
             mbar_wait(rt_full0 + 8 * tb, (it >> 1) & 1);              // geometry of this tile is in the run table
-            const int4 *ti = rt_i + tb * tab_n + run;
+            const uint32_t *ti = rt_i + tb * tab_n + run;
             const float4 *tw = rt_w + tb * tab_n + run;
             for (int cc = 0; cc < p.CC; ++cc, ++bandg) {
                 const int nb = bandg % p.NB;
@@ -182,13 +186,14 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 const uint8_t *band = bands + nb * p.band_stride;
                 const int ch_glob = cc * BLOCK_K + chunk * 4;
                 for (int t0 = 0; t0 < p.k2; t0 += ATOMS, ++sg) {
-                    if ((int)(sg % PROD_GROUPS) != group) continue;   // the other group builds this stage
+                    if ((int)(sg % p.ngroups) != group) continue;   // another group builds this stage
                     const int natoms = min(ATOMS, p.k2 - t0);
                     const int s = sg % STAGES;
                     mbar_wait(empty0 + 8 * s, ((sg / STAGES) & 1) ^ 1);
                     for (int at = 0; at < natoms; ++at) {
                         const int t = t0 + at;
-                        const int4 e = ti[t * NRUN];
+                        const uint32_t ew = ti[t * NRUN];
+                        const int4 e = make_int4((int)(ew & 0x7FFFu) << 4, (int)(ew >> 16) << 4, (int)((ew >> 15) & 1u), 0);
                         const float4 f = tw[t * NRUN];
                         uint8_t *a_tile = smem + s * L::A_STAGE + at * (L::PLANES * L::A_BYTES);
                         if (p.flags & (1 << 16)) {
@@ -268,10 +273,10 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
                 const int by0 = i0 + p.hy_lo, bx0 = j0 + p.hx_lo;
                 const int i = i0 + pty, j = j0 + ptx;
-                const bool pix_ok = (i < p.h) && (j < p.w);
+                const bool pix_ok = (gt < p.tile_px) && (i < p.h) && (j < p.w);
                 const uint32_t tb = git & 1;
                 mbar_wait_sleep(rt_empty0 + 8 * tb, ((git >> 1) & 1) ^ 1);
-                int4 *ti = rt_i + tb * tab_n + grun;
+                uint32_t *ti = rt_i + tb * tab_n + grun;
                 float4 *tw = rt_w + tb * tab_n + grun;
                 int t = 0;
                 for (int a = 0; a < p.k; ++a)
@@ -298,12 +303,14 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                 // columns left of the image (x < 0 in the unpadded frame) are zero-filled by TMA only if they are
                                 // not wrapped pixels: a wrapped index lands inside the image far away, so `inside` already fails
                                 const bool regular = inside && ((votes & run_mask) == run_mask);
-                                e = make_int4((r0 * p.BW + c0) * (BLOCK_K * 4), (r1 * p.BW + c0) * (BLOCK_K * 4), regular ? 1 : 0, 0);
+                                // irregular runs never use the offsets: keep them in range of the packed fields
+                                e = regular ? make_int4((r0 * p.BW + c0) * (BLOCK_K * 4), (r1 * p.BW + c0) * (BLOCK_K * 4), 1, 0)
+                                            : make_int4(0, 0, 0, 0);
                                 f = make_float4(s.dy1, s.dy0, s.dx1, s.dx0);
                             } else {
                                 e.z = 1;   // run entirely outside the panorama (tile overhang): rows are never stored; read anything
                             }
-                            ti[t * NRUN] = e;
+                            ti[t * NRUN] = ((uint32_t)e.x >> 4) | ((uint32_t)e.z << 15) | (((uint32_t)e.y >> 4) << 16);
                             tw[t * NRUN] = f;
                         }
                     }
@@ -343,7 +350,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     if (f < p.F) {
                         for (int row = row0; row < BLOCK_M; row += rstep) {
                             const int ii = i0 + (row >> log_tw), jj = j0 + (row & (p.TW - 1));
-                            if (ii >= p.h || jj >= p.w) continue;
+                            if (row >= p.tile_px || ii >= p.h || jj >= p.w) continue;
                             const float4 raw = *reinterpret_cast<const float4 *>(epi + row * EPI_STRIDE + 4 * c4);
                             float v[4] = { raw.x + bv[0], raw.y + bv[1], raw.z + bv[2], raw.w + bv[3] };
                             if (p.flags & SKY_EPI_LEAKY_RELU) {
@@ -515,28 +522,56 @@ template <int STAGES, bool SPLIT3>
 static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span)
 {
     using L = BandSmem<STAGES, SPLIT3>;
-    static const int cand[8][2] = { { 8, 16 }, { 4, 32 }, { 16, 8 }, { 2, 64 }, { 1, 128 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-    long best_cost = -1;
-    for (int nb_try = (p.CC > 1 ? 2 : 1); nb_try >= 1 && best_cost < 0; --nb_try)
-        for (int c = 0; c < 8; ++c) {
-            const int TH = cand[c][0], TW = cand[c][1];
-            if (TH == 0 || TW % RUN != 0) continue;
-            if ((TH > 2 * a.h && TH > 1) || (TW > 2 * a.w && TW > 1)) continue;
-            const int BH = TH + hy_span, BW = TW + hx_span;
-            if (BW > 256 || BH > 256) continue;
-            const int band_bytes = BH * BW * BLOCK_K * 4;
-            const int band_stride = round_up(band_bytes, 1024);
-            if (L::total_bytes(p.Fp, band_stride, nb_try, p.k2) > 227 * 1024) continue;
-            const int tiles_y = (a.h + TH - 1) / TH, tiles_x = (a.w + TW - 1) / TW;
-            const long cost = (long)tiles_y * tiles_x * BH * BW;
-            if (best_cost < 0 || cost < best_cost) {
-                best_cost = cost;
-                p.TH = TH; p.TW = TW; p.BH = BH; p.BW = BW; p.band_bytes = band_bytes; p.band_stride = band_stride;
-                p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.NB = nb_try;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SKY_CHECK_CUDA(cudaGetDevice(&dev));
+        SKY_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // 128-pixel tiles, unless that leaves more than a quarter of the SMs without a tile: then 64-pixel tiles
+    static const int cand128[5][2] = { { 8, 16 }, { 4, 32 }, { 16, 8 }, { 2, 64 }, { 1, 128 } };
+    static const int cand64[4][2] = { { 8, 8 }, { 4, 16 }, { 2, 32 }, { 1, 64 } };
+    BandParams best[2];
+    long cost_of[2] = { -1, -1 };
+    // A stage must belong to ONE producer group (STAGES % ngroups == 0): a group waits on its stage's empty barrier by
+    // parity, which is only unambiguous when its consecutive uses of that stage are consecutive phases.
+    for (int v = 0; v < ((STAGES % 4 == 0) ? 2 : 1); ++v) {
+        const int px = v == 0 ? 128 : 64, ncand = v == 0 ? 5 : 4;
+        for (int nb_try = (p.CC > 1 ? 2 : 1); nb_try >= 1 && cost_of[v] < 0; --nb_try)
+            for (int c = 0; c < ncand; ++c) {
+                const int TH = v == 0 ? cand128[c][0] : cand64[c][0], TW = v == 0 ? cand128[c][1] : cand64[c][1];
+                if ((TH > 2 * a.h && TH > 1) || (TW > 2 * a.w && TW > 8)) continue;
+                const int BH = TH + hy_span, BW = TW + hx_span;
+                if (BW > 256 || BH > 256 || BW < RUN + 1) continue;
+                const int band_bytes = BH * BW * BLOCK_K * 4;
+                const int band_stride = round_up(band_bytes, 1024);
+                if (L::total_bytes(p.Fp, band_stride, nb_try, p.k2) > 227 * 1024) continue;
+                const int tiles_y = (a.h + TH - 1) / TH, tiles_x = (a.w + TW - 1) / TW;
+                const long cost = (long)tiles_y * tiles_x * BH * BW;
+                if (cost_of[v] < 0 || cost < cost_of[v]) {
+                    cost_of[v] = cost;
+                    best[v] = p;
+                    best[v].TH = TH; best[v].TW = TW; best[v].BH = BH; best[v].BW = BW; best[v].band_bytes = band_bytes;
+                    best[v].band_stride = band_stride; best[v].tiles_x = tiles_x; best[v].tiles_y = tiles_y; best[v].NB = nb_try;
+                    best[v].tile_px = px;
+                }
             }
-        }
+    }
+    long best_cost = -1;
+    if (cost_of[0] >= 0) {
+        const long tiles128 = (long)best[0].tiles_x * best[0].tiles_y * a.B;
+        const bool few = tiles128 * 4 < (long)num_sms * 3;
+        const int pick = (few && cost_of[1] >= 0) ? 1 : 0;
+        p = best[pick];
+        best_cost = cost_of[pick];
+    } else if (cost_of[1] >= 0) {
+        p = best[1];
+        best_cost = cost_of[1];
+    }
     if (best_cost < 0) return SKY_ERR_UNSUPPORTED;
     p.ntiles = p.tiles_x * p.tiles_y * a.B;
+    p.ngroups = p.tile_px == 128 ? 2 : 4;
+    p.group_threads = PROD_WARPS * 32 / p.ngroups;      // == (tile_px / RUN) * 8: one thread per (run, chunk)
 
     CUtensorMap tmap;
     int rc = encode_nhwc_tensor_map(&tmap, a.x, a.B, a.h, a.w, a.C, BLOCK_K, p.BW, p.BH);
@@ -547,12 +582,6 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
     if (!configured) {
         SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_fwd_band_kernel<STAGES, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        SKY_CHECK_CUDA(cudaGetDevice(&dev));
-        SKY_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
     da_conv2d_fwd_band_kernel<STAGES, SPLIT3><<<grid, BAND_THREADS, smem, a.stream>>>(p, tmap);
