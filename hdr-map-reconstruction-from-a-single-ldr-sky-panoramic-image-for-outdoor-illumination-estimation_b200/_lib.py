@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libskydome_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
-EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_FORCE_DIRECT = 0, 1, 2, 256
+EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 256
 MATH_TF32, MATH_3XTF32 = 0, 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -25,6 +25,7 @@ SIGNATURES = {
     "sky_da_packed_weight_bytes": (_sz, [_i, _i, _i, _i]),
     "sky_da_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "sky_conv2d_fwd": (_i, [_vp] * 6 + [_i] * 8 + [_f, _i, _vp]),
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),

@@ -24,6 +24,7 @@ struct FwdArgs {
     int flags;
     float slope;
     int math_mode;
+    int plain_stride;           // 0: distortion-aware sampling; 1 or 2: plain SAME conv with that stride (direct kernel only)
     cudaStream_t stream;
 };
 

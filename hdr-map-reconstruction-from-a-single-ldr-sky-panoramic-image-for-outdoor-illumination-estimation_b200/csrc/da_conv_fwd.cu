@@ -62,7 +62,9 @@ struct FwdParams {
     double *stats;
     int B, h, w, C, F, Fp, k, k2, K, KB;
     int in_h, in_w, ph0, pw0;
-    int M;                  // B*h*w
+    int M;                  // B*oh*ow
+    int oh, ow;             // output map (== h, w for the distortion-aware layers)
+    int plain, stride;      // plain != 0: identity sampler (tf.nn.conv2d SAME), taps at (i*stride + a - ph0, j*stride + b - pw0)
     int flags;
     float slope;
 };
@@ -117,6 +119,25 @@ __device__ __forceinline__ void store_a_chunk(uint8_t *a_tile, int row, int chun
     }
 }
 
+// Sampling of one (pixel, tap): the reference's distortion-aware geometry, or the identity sampler of a plain conv.
+__device__ __forceinline__ CornerRef sample_corners(const FwdParams &p, int b_img, int i, int j, int t)
+{
+    if (p.plain) {
+        CornerRef r;
+        const int yy = i * p.stride + t / p.k - p.ph0, xx = j * p.stride + t % p.k - p.pw0;
+        const bool ok = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+        r.off[0] = ok ? ((b_img * p.h + yy) * p.w + xx) * p.C : -1;
+        r.w[0] = 1.f;
+        r.off[1] = r.off[2] = r.off[3] = -1;
+        r.w[1] = r.w[2] = r.w[3] = 0.f;
+        return r;
+    }
+    const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
+    const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
+    const Sample s = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
+    return da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+}
+
 template <int STAGES, bool SPLIT3>
 __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const FwdParams p)
 {
@@ -163,15 +184,12 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
             // this thread's own pixel (row = tid) for the per-tap coordinate table
             const int m = m0 + tid;
             const bool m_ok = m < p.M;
-            const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
+            const int j = m % p.ow, i = (m / p.ow) % p.oh, b_img = m / (p.ow * p.oh);
             for (int kk = 0; kk < cpt * p.k2; ++kk) {     // chunk-major k-block order (matches the packed weights)
                 const int cc = kk / p.k2, t = kk % p.k2;
                 CornerRef cr;
                 if (m_ok) {
-                    const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
-                    const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
-                    const Sample s = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
-                    cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+                    cr = sample_corners(p, b_img, i, j, t);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { cr.off[c] = -1; cr.w[c] = 0.f; }
@@ -207,16 +225,13 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     const int m = m0 + row;
                     float v[4] = { 0.f, 0.f, 0.f, 0.f };
                     if (m < p.M) {
-                        const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
+                        const int j = m % p.ow, i = (m / p.ow) % p.oh, b_img = m / (p.ow * p.oh);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int kidx = kb * BLOCK_K + chunk * 4 + e;
                             if (kidx < p.K) {
                                 const int t = kidx / p.C, c = kidx % p.C;
-                                const float yo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 0);
-                                const float xo = __ldg(p.offsets + ((size_t)i * p.k2 + t) * 2 + 1);
-                                const Sample sm = da_sample(i, j, t / p.k, t % p.k, yo, xo, p.in_h, p.in_w);
-                                const CornerRef cr = da_corners(sm, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+                                const CornerRef cr = sample_corners(p, b_img, i, j, t);
                                 float acc = 0.f;
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
@@ -255,8 +270,10 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                         val += __ldg(p.bias + f);
                         if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
                         if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.F + f);
+                        if (p.flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
+                        if (p.flags & SKY_EPI_LOG_DECOMPRESS) val = (expf(val * 2.3978953f) - 1.f) / 10.f;   // log(11) as fp32
                         if (p.stats) {   // generic path: plain atomics (the band-staged kernel reduces per tile first)
-                            double *st = p.stats + ((size_t)(m / (p.h * p.w)) * p.F + f) * 2;
+                            double *st = p.stats + ((size_t)(m / (p.oh * p.ow)) * p.F + f) * 2;
                             atomicAdd(st, (double)val);
                             atomicAdd(st + 1, (double)val * (double)val);
                         }
@@ -449,7 +466,15 @@ int sky::launch_fwd_direct(const FwdArgs &a)
     pad_axis(a.h, a.k, &p.ph0, &pht);
     pad_axis(a.w, a.k, &p.pw0, &pwt);
     p.in_h = a.h + pht; p.in_w = a.w + pwt;
-    p.M = a.B * a.h * a.w;
+    p.oh = a.h; p.ow = a.w; p.plain = 0; p.stride = 1;
+    if (a.plain_stride > 0) {
+        // tf.nn.conv2d SAME: out = ceil(n/s), total pad = max((out-1)*s + k - n, 0), the smaller half in front
+        p.plain = 1; p.stride = a.plain_stride;
+        p.oh = (a.h + p.stride - 1) / p.stride; p.ow = (a.w + p.stride - 1) / p.stride;
+        int th = (p.oh - 1) * p.stride + a.k - a.h, tw = (p.ow - 1) * p.stride + a.k - a.w;
+        p.ph0 = (th > 0 ? th : 0) / 2; p.pw0 = (tw > 0 ? tw : 0) / 2;
+    }
+    p.M = a.B * p.oh * p.ow;
     p.flags = a.flags; p.slope = a.slope;
     if (a.math_mode == SKY_MATH_TF32) {
         // 3 stages of 16 KB + Fp*128 B keep two CTAs resident per SM for F <= 128
@@ -473,10 +498,32 @@ extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const flo
     a.x = x; a.offsets = offsets; a.offsets_host = offsets_host; a.packed = (const float *)packed; a.bias = bias;
     a.residual = residual; a.y = y; a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k;
     a.flags = epilogue_flags; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
+    a.plain_stride = 0;
     if (offsets_host != nullptr && (C % BLOCK_K) == 0 && !(epilogue_flags & SKY_EPI_FORCE_DIRECT)) {
         rc = launch_fwd_band(a);
         if (rc != SKY_ERR_UNSUPPORTED) return rc;
     }
+    return launch_fwd_direct(a);
+}
+
+extern "C" int sky_conv2d_fwd(const float *x, const void *packed, const float *bias, float *y, const float *residual, double *stats,
+                              int B, int h, int w, int C, int F, int k, int stride, int epilogue_flags, float slope,
+                              int math_mode, void *stream)
+{
+    SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension");
+    SKY_REQUIRE(k >= 1 && k <= 15, SKY_ERR_UNSUPPORTED, "kernel size %d outside 1..15", k);
+    SKY_REQUIRE(stride == 1 || stride == 2, SKY_ERR_UNSUPPORTED, "stride %d not supported (the path uses 1 and 2)", stride);
+    SKY_REQUIRE(x && packed && bias && y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
+    SKY_REQUIRE(!(epilogue_flags & SKY_EPI_RESIDUAL) || residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
+    SKY_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
+    SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+    SKY_REQUIRE((long)B * h * w * (long)(C > F ? C : F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
+    FwdArgs a;
+    a.x = x; a.offsets = nullptr; a.offsets_host = nullptr; a.packed = (const float *)packed; a.bias = bias;
+    a.residual = residual; a.y = y; a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k;
+    a.flags = epilogue_flags; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
+    a.plain_stride = stride;
     return launch_fwd_direct(a);
 }
 

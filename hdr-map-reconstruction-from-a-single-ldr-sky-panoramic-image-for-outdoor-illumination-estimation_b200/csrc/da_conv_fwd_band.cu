@@ -358,18 +358,29 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                 for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * p.slope;
                             }
                             const size_t go = ((size_t)(b_img * p.h + ii) * p.w + jj) * p.F + f;
-                            if (vec_ok) {
-                                if (p.flags & SKY_EPI_RESIDUAL) {
+                            if (p.flags & SKY_EPI_RESIDUAL) {
+                                if (vec_ok) {
                                     const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + go));
                                     v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+                                } else {
+                                    for (int u = 0; u < 4; ++u)
+                                        if (f + u < p.F) v[u] += __ldg(p.residual + go + u);
                                 }
+                            }
+                            if (p.flags & SKY_EPI_RELU) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 0.f);
+                            }
+                            if (p.flags & SKY_EPI_LOG_DECOMPRESS) {   // tf_utils.hdr_logDecompression, log(11) as fp32
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) v[u] = (expf(v[u] * 2.3978953f) - 1.f) / 10.f;
+                            }
+                            if (vec_ok) {
                                 *reinterpret_cast<float4 *>(p.y + go) = make_float4(v[0], v[1], v[2], v[3]);
                             } else {
                                 for (int u = 0; u < 4; ++u)
-                                    if (f + u < p.F) {
-                                        if (p.flags & SKY_EPI_RESIDUAL) v[u] += __ldg(p.residual + go + u);
-                                        p.y[go + u] = v[u];
-                                    } else v[u] = 0.f;
+                                    if (f + u < p.F) p.y[go + u] = v[u];
+                                    else v[u] = 0.f;
                             }
 #pragma unroll
                             for (int u = 0; u < 4; ++u) { s1[u] += v[u]; s2[u] = fmaf(v[u], v[u], s2[u]); }

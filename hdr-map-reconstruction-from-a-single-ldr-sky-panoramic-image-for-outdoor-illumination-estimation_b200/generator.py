@@ -13,6 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import LIB, check
+from . import ops
 from .distortion_aware_ops import _require_cuda, _stream, conv2d as da_conv2d
 
 
@@ -140,3 +141,103 @@ class resLayer:
         return x
 
     __call__ = call
+
+
+class _NormAct:
+    """conv -> InstanceNormalization -> leaky_relu(0.1), the pattern of generator.py:94-106 and :112-121, with the moments
+    accumulated by the conv epilogue."""
+
+    def __init__(self, conv, device):
+        self.conv = conv
+        self.norm = InstanceNormalization(device=device)
+        self._stats = None
+
+    def __call__(self, x):
+        B = x.shape[0]
+        F = self.conv.output_channels
+        if self._stats is None or self._stats.shape[0] != B:
+            self._stats = torch.zeros(B, F, 2, dtype=torch.float64, device=x.device)
+        else:
+            self._stats.zero_()
+        y = self.conv(x, stats=self._stats)
+        return self.norm.apply(y, self._stats, leaky_slope=0.1)
+
+
+class model:
+    """generator.model (generator.py:51-175): encoder -> residual trunk -> sky decoder.  The sun branch
+    (sun_decode / sun_rad_estimation / blending, :127-175) depends on sunpose_net, Grad-CAM and sunRadNet, which are not
+    part of this round."""
+
+    def __init__(self, batch_size=32, im_height=32, im_width=128, da_kernel_size=3, dilation_rate=1, *, math_mode=None,
+                 device="cuda"):
+        self.fc_dim = int(im_height * im_width)
+        self.im_height, self.im_width = im_height, im_width
+        kw = dict(math_mode=math_mode, device=device)
+        # sky encode (generator.py:60-67)
+        self.conv1_d = ops.conv2d(output_channels=32, k_h=7, k_w=7, strides=1, **kw)
+        self.conv2_d = ops.conv2d(output_channels=64, k_h=3, k_w=3, strides=2, **kw)
+        self.conv3_d = ops.conv2d(output_channels=128, k_h=3, k_w=3, strides=2, **kw)
+        self._enc = [_NormAct(c, device) for c in (self.conv1_d, self.conv2_d, self.conv3_d)]
+        self.norm1_d, self.norm2_d, self.norm3_d = (e.norm for e in self._enc)
+        self.res = resLayer((128,) * 6, 128, k_h=da_kernel_size, k_w=da_kernel_size, strides=1, dilation_rate=dilation_rate, **kw)
+        # sky_decode (generator.py:69-76)
+        self.conv3_f = ops.deconv2d(output_channels=64, output_imshape=[int(im_height / 2), int(im_width / 2)], k_h=3, k_w=3,
+                                    method='resize', **kw)
+        self.conv2_f = ops.deconv2d(output_channels=32, output_imshape=[int(im_height), int(im_width)], k_h=3, k_w=3,
+                                    method='resize', **kw)
+        self._dec = [_NormAct(c, device) for c in (self.conv3_f, self.conv2_f)]
+        self.norm3_f, self.norm2_f = (d.norm for d in self._dec)
+        self.conv1_f = ops.conv2d(output_channels=3, k_h=7, k_w=7, strides=1, **kw)
+
+    def encode(self, x, training="training"):
+        for stage in self._enc:                       # generator.py:94-106
+            x = stage(x)
+        return self.res(x)                            # :108
+
+    def sky_decode(self, x, _input, training="training", log_decompress=False):
+        for stage in self._dec:                       # generator.py:112-118
+            x = stage(x)
+        # :120-124  leaky_relu(conv1_f) + input -> relu, all in the conv epilogue; optionally followed by
+        # tf_utils.hdr_logDecompression (inference.py:86)
+        return self.conv1_f(x, leaky_slope=0.1, residual=_input, relu=True, log_decompress=log_decompress)
+
+    def sky_inference(self, ldr):
+        """inference.py:84-86: hdr_logDecompression(sky_decode(encode(ldr), ldr)) — the linear-radiance sky prediction."""
+        return self.sky_decode(self.encode(ldr), ldr, log_decompress=True)
+
+    def sun_decode(self, *a, **k):
+        raise NotImplementedError("sun branch (generator.py:127-156) is not built in this round")
+
+    def sun_rad_estimation(self, *a, **k):
+        raise NotImplementedError("sun radiance estimation (generator.py:158-169) is not built in this round")
+
+    def build(self, batch_size=None):
+        """Create every variable by tracing shapes (the reference builds lazily on the first call)."""
+        B = batch_size or 1
+        H, W = self.im_height, self.im_width
+        shapes = [(B, H, W, 3), (B, H, W, 32), (B, H // 2, W // 2, 64)]
+        for st, shp in zip(self._enc, shapes):
+            st.conv.build(shp)
+            st.norm.build(shp[:3] + (st.conv.output_channels,))
+        self.res.build((B, H // 4, W // 4, 128))
+        for st, shp in zip(self._dec, [(B, H // 4, W // 4, 128), (B, H // 2, W // 2, 64)]):
+            st.conv.build(shp)
+            st.norm.build(shp[:3] + (st.conv.output_channels,))
+        self.conv1_f.build((B, H, W, 32))
+
+    def set_weights(self, w):
+        """w: dict keyed by the reference's attribute names: conv1_d/conv2_d/conv3_d/conv3_f/conv2_f/conv1_f ->
+        (kernel [k,k,C,F], bias), norm*_d / norm*_f -> (gamma, beta), res -> list of res-block dicts."""
+        for name in ("conv1_d", "conv2_d", "conv3_d", "conv1_f"):
+            layer = getattr(self, name)
+            layer.w.copy_(torch.as_tensor(w[name][0]))
+            layer.biases.copy_(torch.as_tensor(w[name][1]))
+        for name in ("conv3_f", "conv2_f"):
+            layer = getattr(self, name)
+            layer.kernel.copy_(torch.as_tensor(w[name][0]))
+            layer.biases.copy_(torch.as_tensor(w[name][1]))
+        for name in ("norm1_d", "norm2_d", "norm3_d", "norm3_f", "norm2_f"):
+            norm = getattr(self, name)
+            norm.gamma.copy_(torch.as_tensor(w[name][0]))
+            norm.beta.copy_(torch.as_tensor(w[name][1]))
+        self.res.set_weights(w["res"])

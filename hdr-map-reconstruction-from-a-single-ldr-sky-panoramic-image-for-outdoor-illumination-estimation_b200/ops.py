@@ -1,0 +1,174 @@
+"""Host-side mirror of the plain layers of the reference's ops.py that the generator instantiates:
+
+    ops.conv2d(output_channels, strides, k_h, k_w, padding="SAME")            ops.py:4-42   (tf.nn.conv2d + bias_add)
+    ops.deconv2d(output_channels, output_imshape, k_h, k_w, method='resize')  ops.py:44-126 (tf.image.resize BILINEAR,
+                                                                               then a stride-1 SAME conv; only the
+                                                                               'resize' method is used by generator.py)
+
+Variables keep the reference's names and shapes: ``w`` / ``kernel`` [k_h, k_w, C, F], ``biases`` [F].  Stride-1 odd-k
+layers with C % 32 == 0 run through the distortion-aware entry point with an all-zero offset table (the sampler then
+degenerates to the integer taps of a SAME conv and the band-staged tcgen05 kernel applies); everything else takes the
+identity-sampler mode of the direct kernel (sky_conv2d_fwd).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LIB, check
+from .distortion_aware_ops import _MATH, DEFAULT_MATH_MODE, _initializer, _ptr, _require_cuda, _stream, resize_bilinear
+
+
+def _epilogue_flags(leaky_slope, residual, relu, log_decompress):
+    flags = _lib.EPI_NONE
+    if leaky_slope is not None:
+        flags |= _lib.EPI_LEAKY_RELU
+    if residual is not None:
+        flags |= _lib.EPI_RESIDUAL
+    if relu:
+        flags |= _lib.EPI_RELU
+    if log_decompress:
+        flags |= _lib.EPI_LOG_DECOMPRESS
+    return flags
+
+
+class _PlainConvCore:
+    """Shared by conv2d and deconv2d: weight packing and the two launch routes."""
+
+    def __init__(self, output_channels, k_h, k_w, strides, kernel_initializer, bias_initializer, math_mode, device):
+        if k_h != k_w:
+            raise ValueError("only square kernels are used by the reference model")
+        self.output_channels = output_channels
+        self.k_h, self.k_w = k_h, k_w
+        self.stride = int(strides)
+        self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
+        self.math_mode = math_mode or DEFAULT_MATH_MODE
+        self.device = torch.device(device)
+        self.built = False
+        self._packed = None
+        self._packed_key = None
+        self._zero_tab = None
+
+    def _build_weights(self, channels_in):
+        k, F = self.k_h, self.output_channels
+        fan_in, fan_out = k * k * channels_in, k * k * F          # Keras 4-D glorot: receptive field x channels
+        w = _initializer(self.kernel_initializer, (k, k, channels_in, F), fan_in, fan_out, self.device)
+        b = _initializer(self.bias_initializer, (F,), fan_in, fan_out, self.device)
+        self._channels_in = channels_in
+        self.built = True
+        return w, b
+
+    def _weight(self):
+        raise NotImplementedError
+
+    def _bias(self):
+        raise NotImplementedError
+
+    def _packed_weights(self):
+        wt = self._weight()
+        mode = _MATH[self.math_mode]
+        key = (wt.data_ptr(), wt._version, mode)
+        if self._packed_key != key:
+            k, C, F = self.k_h, self._channels_in, self.output_channels
+            nbytes = LIB.sky_da_packed_weight_bytes(C, F, k, mode)
+            if self._packed is None or self._packed.numel() != nbytes:
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(LIB.sky_da_pack_weights(wt.data_ptr(), self._packed.data_ptr(), C, F, k, mode, _stream()))
+            self._packed_key = key
+        return self._packed
+
+    def _conv(self, x, leaky_slope=None, residual=None, relu=False, log_decompress=False, stats=None):
+        B, h, w, C = x.shape
+        k, F, s = self.k_h, self.output_channels, self.stride
+        if C != self._channels_in:
+            raise ValueError("channel count differs from the shape the layer was built for")
+        oh, ow = -(-h // s), -(-w // s)
+        y = torch.empty((B, oh, ow, F), dtype=torch.float32, device=x.device)
+        if residual is not None:
+            residual = _require_cuda(residual, "residual")
+        flags = _epilogue_flags(leaky_slope, residual, relu, log_decompress)
+        slope = float(leaky_slope or 0.0)
+        mode = _MATH[self.math_mode]
+        if s == 1 and k % 2 == 1 and k >= 3 and C % 32 == 0:
+            if self._zero_tab is None or self._zero_tab[0].shape[0] != h:
+                host = np.zeros((h, k * k, 2), np.float32)
+                self._zero_tab = (torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device), host)
+            dev, host = self._zero_tab
+            check(LIB.sky_da_conv2d_fwd(x.data_ptr(), dev.data_ptr(), host.ctypes.data, self._packed_weights().data_ptr(),
+                                        self._bias().data_ptr(), y.data_ptr(), _ptr(residual), _ptr(stats), B, h, w, C, F, k,
+                                        flags, slope, mode, _stream()))
+        else:
+            check(LIB.sky_conv2d_fwd(x.data_ptr(), self._packed_weights().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
+                                     _ptr(residual), _ptr(stats), B, h, w, C, F, k, s, flags, slope, mode, _stream()))
+        return y
+
+
+class conv2d(_PlainConvCore):
+    def __init__(self, output_channels="output_channels", strides="strides", k_h="k_h", k_w="k_w", padding="SAME",
+                 kernel_initializer='glorot_uniform', bias_initializer='zeros', *, math_mode=None, device="cuda"):
+        if padding != "SAME":
+            raise ValueError("the generator only uses SAME padding (ops.py:10)")
+        super().__init__(output_channels, k_h, k_w, strides, kernel_initializer, bias_initializer, math_mode, device)
+        self.strides = [1, strides, strides, 1]                 # ops.py:17
+        self.padding = padding
+        self.w = None
+        self.biases = None
+
+    def build(self, input_shape):
+        self.w, self.biases = self._build_weights(int(input_shape[-1]))      # ops.py:30-38
+
+    def _weight(self):
+        return self.w
+
+    def _bias(self):
+        return self.biases
+
+    @property
+    def trainable_variables(self):
+        return [self.w, self.biases]
+
+    def call(self, input, **epilogue):
+        x = _require_cuda(input, "input")
+        if not self.built:
+            self.build(tuple(x.shape))
+        return self._conv(x, **epilogue)                                      # ops.py:41-42
+
+    __call__ = call
+
+
+class deconv2d(_PlainConvCore):
+    def __init__(self, output_channels="output_channels", output_imshape=[], k_h="k_h", k_w="k_w", strides=1,
+                 padding="SAME", method='resize', kernel_initializer='glorot_uniform', bias_initializer='zeros', *,
+                 math_mode=None, device="cuda"):
+        if method != 'resize':
+            raise NotImplementedError("generator.py only instantiates ops.deconv2d(method='resize') (generator.py:70-83)")
+        super().__init__(output_channels, k_h, k_w, 1, kernel_initializer, bias_initializer, math_mode, device)
+        self.output_imshape = [int(v) for v in output_imshape]
+        self.method = method
+        self.kernel = None
+        self.biases = None
+
+    def build(self, input_shape):
+        self.kernel, self.biases = self._build_weights(int(input_shape[-1]))  # ops.py:98-110
+
+    def _weight(self):
+        return self.kernel
+
+    def _bias(self):
+        return self.biases
+
+    @property
+    def trainable_variables(self):
+        return [self.kernel, self.biases]
+
+    def call(self, input, **epilogue):
+        x = _require_cuda(input, "input")
+        if not self.built:
+            self.build(tuple(x.shape))
+        im_resized = resize_bilinear(x, self.output_imshape[0], self.output_imshape[1])   # ops.py:122
+        return self._conv(im_resized, **epilogue)                                          # ops.py:124
+
+    __call__ = call

@@ -44,6 +44,80 @@ def res_layer(x, blocks, k=3, dilation=1, acc_dtype=torch.float32):
     return x
 
 
+def conv2d_same(x, w4, b, stride=1, acc_dtype=torch.float32):
+    """tf.nn.conv2d(x, w, strides, 'SAME') + bias_add (ops.py:41-42) on NHWC input, HWIO kernel.  TensorFlow SAME padding:
+    out = ceil(n/s), total = max((out-1)*s + k - n, 0), floor(total/2) in front, the rest behind."""
+    x, w4, b = O._as_t(x).to(acc_dtype), O._as_t(w4).to(acc_dtype), O._as_t(b).to(acc_dtype)
+    k = w4.shape[0]
+    B, h, w, C = x.shape
+    pads = []
+    for n in (h, w):
+        out = -(-n // stride)
+        total = max((out - 1) * stride + k - n, 0)
+        pads.append((total // 2, total - total // 2))
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+    y = torch.nn.functional.conv2d(xp, w4.permute(3, 2, 0, 1), bias=b, stride=stride)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def hdr_log_decompression(x, valid_dr=10.0):
+    """tf_utils.hdr_logDecompression (tf_utils.py:273-280)."""
+    den = torch.log(torch.tensor(1.0 + valid_dr, dtype=x.dtype))
+    return (torch.exp(x * den) - 1.0) / valid_dr
+
+
+def sky_branch(ldr, w, k=3, acc_dtype=torch.float32, decompress=True):
+    """inference.py:84-86 with the distortion-aware trunk: encode (generator.py:92-108) -> sky_decode (:110-125) ->
+    hdr_logDecompression.  w: the dict layout of <package>.generator.model.set_weights."""
+    dt = acc_dtype
+    x = O._as_t(ldr).to(dt)
+    inp = x
+
+    def norm_act(y, name):
+        g, b = (O._as_t(v).to(dt) for v in w[name])
+        return leaky_relu(instance_norm(y, g, b), 0.1)
+
+    x = norm_act(conv2d_same(x, *w["conv1_d"], stride=1, acc_dtype=dt), "norm1_d")
+    x = norm_act(conv2d_same(x, *w["conv2_d"], stride=2, acc_dtype=dt), "norm2_d")
+    x = norm_act(conv2d_same(x, *w["conv3_d"], stride=2, acc_dtype=dt), "norm3_d")
+    blocks = [{kk: O._as_t(v) for kk, v in blk.items()} for blk in w["res"]]
+    x = res_layer(x, blocks, k, acc_dtype=dt)
+    H, W = inp.shape[1], inp.shape[2]
+    x = O.resize_bilinear(x, H // 2, W // 2)                                   # ops.py:122
+    x = norm_act(conv2d_same(x, *w["conv3_f"], acc_dtype=dt), "norm3_f")
+    x = O.resize_bilinear(x, H, W)
+    x = norm_act(conv2d_same(x, *w["conv2_f"], acc_dtype=dt), "norm2_f")
+    sky = leaky_relu(conv2d_same(x, *w["conv1_f"], acc_dtype=dt), 0.1)        # generator.py:120-121
+    sky = torch.relu(inp + sky)                                                # :123-124
+    return hdr_log_decompression(sky) if decompress else sky
+
+
+def random_generator_weights(seed, k=3, affine_noise=True):
+    """numpy-seeded weights for the sky branch with the reference's initialiser distributions (Keras glorot_uniform on
+    the 4-D kernels), biases / gamma / beta optionally perturbed so they are exercised."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = {}
+
+    def conv(name, kk, cin, cout):
+        lim = (6.0 / (kk * kk * cin + kk * kk * cout)) ** 0.5
+        w[name] = (rng.uniform(-lim, lim, (kk, kk, cin, cout)).astype(np.float32),
+                   (0.05 * rng.standard_normal(cout) * affine_noise).astype(np.float32))
+
+    def norm(name, c):
+        w[name] = ((1 + 0.1 * rng.standard_normal(c) * affine_noise).astype(np.float32),
+                   (0.1 * rng.standard_normal(c) * affine_noise).astype(np.float32))
+
+    conv("conv1_d", 7, 3, 32); norm("norm1_d", 32)
+    conv("conv2_d", 3, 32, 64); norm("norm2_d", 64)
+    conv("conv3_d", 3, 64, 128); norm("norm3_d", 128)
+    w["res"] = [{kk: v.numpy() for kk, v in blk.items()} for blk in random_trunk_weights(6, 128, k, seed + 1, affine_noise)]
+    conv("conv3_f", 3, 128, 64); norm("norm3_f", 64)
+    conv("conv2_f", 3, 64, 32); norm("norm2_f", 32)
+    conv("conv1_f", 7, 32, 3)
+    return w
+
+
 def random_trunk_weights(n_blocks, C, k, seed, affine_noise=True):
     """numpy-seeded weights with the reference's initialiser distributions (glorot_uniform kernels, zero bias, gamma=1,
     beta=0), optionally perturbed so bias / gamma / beta are exercised."""
