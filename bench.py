@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native distortion-aware convolution path.
 
-Workload (config.workload): forward pass of the generator's residual trunk with the distortion-aware convolutions of
-generator.py:14,18 wired in — 6 res-blocks = 12 DA convs (128->128, k=3) + 12 instance norms (+LeakyReLU / residual) —
-on the trunk feature map of a batch of 32 synthetic 32x128 sky-dome panoramas per GPU ([32, 8, 32, 128] NHWC fp32).
-This is the slice of BASELINE.json config 1 ("generator inference, batch 32, 32x128") that runs through the hot path
-built so far; the encoder/decoder around it are next.
+Workload (config.workload): BASELINE.json config 1, "generator inference, random-init weights, synthetic 32x128 LDR
+sky-dome panoramas, batch 32", restricted to the sky branch that is built so far (inference.py:84-86): encoder ->
+six res-blocks with the distortion-aware convolutions of generator.py:14,18 -> sky decoder -> hdr_logDecompression.
+The sun branch (sunpose_net, Grad-CAM, sunRadNet, sun_decode, blending) is not built yet.
+`--workload trunk` times the DA residual trunk alone.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU under torchrun)
     python bench.py --impl reference [--steps K] [--warmup W]      reference arm: the oracle's CPU restatement of the
@@ -29,7 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_BLOCKS, C, K_SIZE = 6, 128, 3
-METRIC, UNIT = "panoramas/sec (32x128, inference: DA residual trunk forward)", "panoramas/s"
+UNIT = "panoramas/s"
+METRICS = {"sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
+           "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)"}
 
 
 def make_weights(seed=0):
@@ -54,9 +56,48 @@ def make_input(batch, h, w, seed):
     return np.where(x > 0, x, 0.1 * x).astype(np.float32)
 
 
-def workload_name(batch, H, W):
-    return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3, TF32) + 12 instance norms, "
-            f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
+def workload_name(batch, H, W, workload="sky"):
+    if workload == "trunk":
+        return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3, TF32) + 12 instance norms, "
+                f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
+    return (f"generator_sky_inference (inference.py:84-86): LDR [{batch},{H},{W},3] -> encode (7x7/32, 3x3s2/64, 3x3s2/128, IN, lrelu) "
+            f"-> 6 resBlocks with distortion-aware convs (generator.py:14,18) -> sky_decode (2 resize-deconv, 7x7/3, +LDR, relu) "
+            f"-> hdr_logDecompression; random-init weights, B={batch}/GPU")
+
+
+def make_generator_weights(seed=0):
+    """Sky-branch weights with the reference's initialiser distributions (Keras glorot_uniform, zero bias, gamma 1, beta 0)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+
+    def conv(name, kk, cin, cout):
+        lim = (6.0 / (kk * kk * cin + kk * kk * cout)) ** 0.5
+        w[name] = (rng.uniform(-lim, lim, (kk, kk, cin, cout)).astype(np.float32), np.zeros(cout, np.float32))
+
+    conv("conv1_d", 7, 3, 32); conv("conv2_d", 3, 32, 64); conv("conv3_d", 3, 64, 128)
+    conv("conv3_f", 3, 128, 64); conv("conv2_f", 3, 64, 32); conv("conv1_f", 7, 32, 3)
+    for name, c in (("norm1_d", 32), ("norm2_d", 64), ("norm3_d", 128), ("norm3_f", 64), ("norm2_f", 32)):
+        w[name] = (np.ones(c, np.float32), np.zeros(c, np.float32))
+    w["res"] = make_weights(seed + 1)
+    return w
+
+
+def make_ldr(batch, H, W, seed):
+    """LDR = round(255 u) / 255, u ~ U[0,1)  (mimics train.py:84-92)."""
+    return (np.round(255 * np.random.default_rng(seed).uniform(0, 1, (batch, H, W, 3))) / 255).astype(np.float32)
+
+
+def oracle_step_fn(args, sample):
+    """CPU restatement of the selected workload on `sample` panoramas (returns a zero-argument callable)."""
+    import torch
+    from oracle import model_oracle as M
+    if args.workload == "trunk":
+        blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
+        x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
+        return lambda: M.res_layer(x, blocks, K_SIZE)
+    w = make_generator_weights()
+    ldr = make_ldr(sample, args.height, args.width, seed=1)
+    return lambda: M.sky_branch(ldr, w, K_SIZE)
 
 
 class ClockSampler(threading.Thread):
@@ -99,20 +140,19 @@ def run_reference(args):
     from oracle import model_oracle as M
     torch.set_num_threads(os.cpu_count())
     sample = min(args.batch, 8)                     # bounded sample of the B=32 batch per step
-    h, w = args.height // 4, args.width // 4
-    blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
-    x = torch.from_numpy(make_input(sample, h, w, seed=1))
+    step = oracle_step_fn(args, sample)
     for _ in range(max(1, min(args.warmup, 2))):
-        M.res_layer(x, blocks, K_SIZE)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        M.res_layer(x, blocks, K_SIZE)
+        step()
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt
+    METRIC = METRICS[args.workload]
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch, args.height, args.width),
+            "config": {"workload": workload_name(args.batch, args.height, args.width, args.workload),
                        "note": "reference dataflow (materialised pad/gather/blend/matmul) restated on torch-CPU; not TensorFlow"},
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"{sample} of {args.batch} panoramas per step, {args.steps} steps"},
@@ -136,25 +176,37 @@ def run_ours(args):
 
     B, H, W = args.batch, args.height, args.width
     h, w = H // 4, W // 4
-    trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
-    trunk.build((B, h, w, C))
-    trunk.set_weights(make_weights())
-    x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
-    y_host = torch.empty_like(x_host).pin_memory()
+    METRIC = METRICS[args.workload]
+    if args.workload == "trunk":
+        trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
+        trunk.build((B, h, w, C))
+        trunk.set_weights(make_weights())
+        forward = trunk
+        x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
+        launches_per_step = 4 * N_BLOCKS         # per res-block: 2 conv + 2 instance-norm kernels (ours)
+    else:
+        gen = pkg.model(batch_size=B, im_height=H, im_width=W, da_kernel_size=K_SIZE, math_mode=args.math)
+        gen.build(B)
+        gen.set_weights(make_generator_weights())
+        trunk = gen.res
+        forward = gen.sky_inference
+        x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
+        # encoder 3 conv + 3 IN; trunk 12 conv + 12 IN; decoder 2 resize + 3 conv + 2 IN
+        launches_per_step = 6 + 4 * N_BLOCKS + 7
     x = x_host.cuda()
+    y_host = torch.empty_like(forward(x).cpu()).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
 
     # ---- the step: captured once into a CUDA graph (24 kernel launches + 12 memsets) ----
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
         for _ in range(2):
-            y = trunk(x)                         # eager warm-up (packs weights, sizes scratch)
+            y = forward(x)                       # eager warm-up (packs weights, sizes scratch)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
-            y = trunk(x)
+            y = forward(x)
     torch.cuda.synchronize()
-    launches_per_step = 4 * N_BLOCKS             # per res-block: 2 conv + 2 instance-norm kernels (ours)
 
     def barrier():
         if world > 1:
@@ -200,11 +252,12 @@ def run_ours(args):
     conv_ms = []
     blk = trunk.sequence[0]
     stats = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
+    xt = torch.from_numpy(make_input(B, h, w, seed=7)).cuda()          # a trunk-shaped activation
     for rep in range(12 + 3):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        blk.conv1.call(x, stats=stats)
+        blk.conv1.call(xt, stats=stats)
         e.record()
         torch.cuda.synchronize()
         if rep >= 3:
@@ -230,7 +283,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(world * B / (t_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
-            "config": {"workload": workload_name(B, H, W), "global_batch": world * B, "parallelism": f"batch shards x{world}, no collective",
+            "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B, "parallelism": f"batch shards x{world}, no collective",
                        "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": True},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": round(t_e2e, 4)},
@@ -244,24 +297,23 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline(B, h, w)
+            line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(B, h, w):
+def cpu_baseline(args):
     """The oracle (a port of the reference dataflow) timed on the host cores, on a bounded sample."""
     import torch
-    from oracle import model_oracle as M
     torch.set_num_threads(os.cpu_count())
+    B = args.batch
     sample = min(B, 8)
-    blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
-    x = torch.from_numpy(make_input(sample, h, w, seed=1))
-    M.res_layer(x, blocks, K_SIZE)
+    step = oracle_step_fn(args, sample)
+    step()
     reps, t0 = 0, time.perf_counter()
     while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 40):
-        M.res_layer(x, blocks, K_SIZE)
+        step()
         reps += 1
     dt = (time.perf_counter() - t0) / reps
     return {"value": round(sample / dt, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -278,6 +330,8 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
+    ap.add_argument("--workload", default="sky", choices=["sky", "trunk"],
+                    help="sky: generator inference, sky branch (default); trunk: the DA residual trunk alone")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

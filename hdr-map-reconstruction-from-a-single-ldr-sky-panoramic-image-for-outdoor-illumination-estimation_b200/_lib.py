@@ -26,6 +26,7 @@ SIGNATURES = {
     "sky_da_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "sky_conv2d_fwd": (_i, [_vp] * 6 + [_i] * 8 + [_f, _i, _vp]),
+    "sky_conv2d_smallc_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_f, _vp]),
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),

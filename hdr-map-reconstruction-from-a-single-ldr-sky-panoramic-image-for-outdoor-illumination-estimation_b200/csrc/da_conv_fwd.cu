@@ -378,15 +378,17 @@ __global__ void da_conv2d_fwd_simt_kernel(const float *__restrict__ x, const flo
 }
 
 // TF2 bilinear resize, half-pixel centres: src = (dst + 0.5) * (in/out) - 0.5 ; lower = max(floor, 0) ;
-// upper = min(ceil, n-1) ; lerp = src - floor(src) ; top/bottom lerp in x, then lerp in y.
+// upper = min(ceil, n-1) ; lerp = src - floor(src) ; top/bottom lerp in x, then lerp in y.  VEC channels per thread.
+template <int VEC>
 __global__ void resize_bilinear_kernel(const float *__restrict__ x, float *__restrict__ y, int B, int h, int w, int C,
                                        int oh, int ow)
 {
     const float sy = __fdiv_rn((float)h, (float)oh), sx = __fdiv_rn((float)w, (float)ow);
-    const long total = (long)B * oh * ow * C;
+    const int cv = C / VEC;
+    const long total = (long)B * oh * ow * cv;
     for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(o % C);
-        const int ox = (int)((o / C) % ow), oy = (int)((o / ((long)C * ow)) % oh), b = (int)(o / ((long)C * ow * oh));
+        const int c = (int)(o % cv) * VEC;
+        const int ox = (int)((o / cv) % ow), oy = (int)((o / ((long)cv * ow)) % oh), b = (int)(o / ((long)cv * ow * oh));
         const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)oy, 0.5f), sy), 0.5f);
         const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)ox, 0.5f), sx), 0.5f);
         const float fly = floorf(fy), flx = floorf(fx);
@@ -394,11 +396,26 @@ __global__ void resize_bilinear_kernel(const float *__restrict__ x, float *__res
         const int xlo = max((int)flx, 0), xhi = min((int)ceilf(fx), w - 1);
         const float ly = __fsub_rn(fy, fly), lx = __fsub_rn(fx, flx);
         const float *img = x + (size_t)b * h * w * C + c;
-        const float tl = img[((size_t)ylo * w + xlo) * C], tr = img[((size_t)ylo * w + xhi) * C];
-        const float bl = img[((size_t)yhi * w + xlo) * C], br = img[((size_t)yhi * w + xhi) * C];
-        const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
-        const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
-        y[o] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+        const float *ptl = img + ((size_t)ylo * w + xlo) * C, *ptr = img + ((size_t)ylo * w + xhi) * C;
+        const float *pbl = img + ((size_t)yhi * w + xlo) * C, *pbr = img + ((size_t)yhi * w + xhi) * C;
+        float tl[VEC], tr[VEC], bl[VEC], br[VEC], out[VEC];
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(tl) = __ldg(reinterpret_cast<const float4 *>(ptl));
+            *reinterpret_cast<float4 *>(tr) = __ldg(reinterpret_cast<const float4 *>(ptr));
+            *reinterpret_cast<float4 *>(bl) = __ldg(reinterpret_cast<const float4 *>(pbl));
+            *reinterpret_cast<float4 *>(br) = __ldg(reinterpret_cast<const float4 *>(pbr));
+        } else {
+            tl[0] = ptl[0]; tr[0] = ptr[0]; bl[0] = pbl[0]; br[0] = pbr[0];
+        }
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            const float top = __fadd_rn(tl[u], __fmul_rn(__fsub_rn(tr[u], tl[u]), lx));
+            const float bot = __fadd_rn(bl[u], __fmul_rn(__fsub_rn(br[u], bl[u]), lx));
+            out[u] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+        }
+        float *dst = y + (((size_t)b * oh + oy) * ow + ox) * C + c;
+        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<float4 *>(out);
+        else dst[0] = out[0];
     }
 }
 
@@ -545,10 +562,12 @@ extern "C" int sky_resize_bilinear_fwd(const float *x, float *y, int B, int h, i
 {
     SKY_REQUIRE(x && y, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && oh > 0 && ow > 0, SKY_ERR_INVALID, "non-positive dimension");
-    const long total = (long)B * oh * ow * C;
+    const bool vec = (C % 4 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)y & 15) == 0);
+    const long total = (long)B * oh * ow * (vec ? C / 4 : C);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    resize_bilinear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
+    if (vec) resize_bilinear_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
+    else resize_bilinear_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }

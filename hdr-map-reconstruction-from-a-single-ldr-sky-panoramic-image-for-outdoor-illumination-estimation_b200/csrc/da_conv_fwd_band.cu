@@ -60,7 +60,8 @@ struct BandParams {
 };
 
 // Run table entry: one uint32 {bits 0-14: band offset of (row y0, first column) in 16-byte units, bit 15: regular?,
-// bits 16-31: same offset for row y1} and floats {dy1, dy0, dx1, dx0} of the run's first pixel
+// bits 16-30: same offset for row y1, bit 31: integer taps (weights exactly (1,0,0,0): a plain conv run through the
+// zero offset table, or an on-grid tap such as the centre row of the reference's table) -> straight copy} and floats {dy1, dy0, dx1, dx0} of the run's first pixel
 // (the factors of distortion_aware_ops.py:103-106).
 template <int STAGES, bool SPLIT3>
 struct BandSmem {
@@ -193,11 +194,18 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     for (int at = 0; at < natoms; ++at) {
                         const int t = t0 + at;
                         const uint32_t ew = ti[t * NRUN];
-                        const int4 e = make_int4((int)(ew & 0x7FFFu) << 4, (int)(ew >> 16) << 4, (int)((ew >> 15) & 1u), 0);
+                        const int4 e = make_int4((int)(ew & 0x7FFFu) << 4, (int)((ew >> 16) & 0x7FFFu) << 4, (int)((ew >> 15) & 1u),
+                                                 (int)(ew >> 31));
                         const float4 f = tw[t * NRUN];
                         uint8_t *a_tile = smem + s * L::A_STAGE + at * (L::PLANES * L::A_BYTES);
                         if (p.flags & (1 << 16)) {
                             // timing experiment: no gather
+                        } else if (e.z && e.w) {
+                            // regular run with integer taps: the A rows are the band pixels themselves
+                            const uint8_t *top = band + e.x + chunk * 16;
+#pragma unroll
+                            for (int q = 0; q < RUN; ++q)
+                                store_a(a_tile, run * RUN + q, chunk, *reinterpret_cast<const float4 *>(top + q * (BLOCK_K * 4)), SPLIT3);
                         } else if (e.z) {
                             // regular run: RUN+1 adjacent columns of two band rows
                             const uint8_t *top = band + e.x + chunk * 16, *bot = band + e.y + chunk * 16;
@@ -304,13 +312,15 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                 // not wrapped pixels: a wrapped index lands inside the image far away, so `inside` already fails
                                 const bool regular = inside && ((votes & run_mask) == run_mask);
                                 // irregular runs never use the offsets: keep them in range of the packed fields
-                                e = regular ? make_int4((r0 * p.BW + c0) * (BLOCK_K * 4), (r1 * p.BW + c0) * (BLOCK_K * 4), 1, 0)
+                                const bool integer_taps = s.dy1 == 1.f && s.dy0 == 0.f && s.dx1 == 1.f && s.dx0 == 0.f;
+                                e = regular ? make_int4((r0 * p.BW + c0) * (BLOCK_K * 4), (r1 * p.BW + c0) * (BLOCK_K * 4), 1,
+                                                        integer_taps ? 1 : 0)
                                             : make_int4(0, 0, 0, 0);
                                 f = make_float4(s.dy1, s.dy0, s.dx1, s.dx0);
                             } else {
                                 e.z = 1;   // run entirely outside the panorama (tile overhang): rows are never stored; read anything
                             }
-                            ti[t * NRUN] = ((uint32_t)e.x >> 4) | ((uint32_t)e.z << 15) | (((uint32_t)e.y >> 4) << 16);
+                            ti[t * NRUN] = ((uint32_t)e.x >> 4) | ((uint32_t)e.z << 15) | (((uint32_t)e.y >> 4) << 16) | ((uint32_t)e.w << 31);
                             tw[t * NRUN] = f;
                         }
                     }

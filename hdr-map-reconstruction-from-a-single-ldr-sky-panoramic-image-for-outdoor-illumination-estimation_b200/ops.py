@@ -92,7 +92,11 @@ class _PlainConvCore:
         flags = _epilogue_flags(leaky_slope, residual, relu, log_decompress)
         slope = float(leaky_slope or 0.0)
         mode = _MATH[self.math_mode]
-        if s == 1 and k % 2 == 1 and k >= 3 and C % 32 == 0:
+        if (s == 1 and k % 2 == 1 and k <= 11 and C <= 4 and F <= 32 and residual is None and not relu and not log_decompress):
+            # image-like input (conv1_d): fp32 CUDA-core kernel, the unpacked variable is read directly
+            check(LIB.sky_conv2d_smallc_fwd(x.data_ptr(), self._weight().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
+                                            _ptr(stats), B, h, w, C, F, k, flags, slope, _stream()))
+        elif s == 1 and k % 2 == 1 and k >= 3 and C % 32 == 0:
             if self._zero_tab is None or self._zero_tab[0].shape[0] != h:
                 host = np.zeros((h, k * k, 2), np.float32)
                 self._zero_tab = (torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device), host)
