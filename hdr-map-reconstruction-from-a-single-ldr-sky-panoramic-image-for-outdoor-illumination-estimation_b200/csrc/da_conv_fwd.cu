@@ -541,6 +541,10 @@ extern "C" int sky_conv2d_fwd(const float *x, const void *packed, const float *b
     a.residual = residual; a.y = y; a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k;
     a.flags = epilogue_flags; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
     a.plain_stride = stride;
+    if ((C % BLOCK_K) == 0 && !(epilogue_flags & SKY_EPI_FORCE_DIRECT)) {
+        int rc = launch_fwd_band(a);        // identity sampler in the band-staged kernel (any stride the band fits)
+        if (rc != SKY_ERR_UNSUPPORTED) return rc;
+    }
     return launch_fwd_direct(a);
 }
 

@@ -53,6 +53,8 @@ struct BandParams {
     int in_h, in_w, ph0, pw0;
     int TH, TW, tiles_x, tiles_y, ntiles;
     int tile_px, ngroups, group_threads;   // tile_px = TH*TW (64 or 128); producer grouping
+    int plain, stride, oh, ow;             // plain != 0: identity sampler of a SAME conv (ops.py:41), taps at
+                                           // (i*stride + a - ph0, j*stride + b - pw0); oh, ow: output map (== h, w otherwise)
     int hy_lo, hx_lo, BH, BW, band_bytes, band_stride, NB;
     int flags;
     float slope;
@@ -175,7 +177,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
             const int b_img = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
-            const int by0 = i0 + p.hy_lo, bx0 = j0 + p.hx_lo;
+            const int by0 = i0 * p.stride + p.hy_lo, bx0 = j0 * p.stride + p.hx_lo;
             const int ri = i0 + rty, rj = j0 + rtx;
             const uint32_t tb = it & 1;
             mbar_wait(rt_full0 + 8 * tb, (it >> 1) & 1);              // geometry of this tile is in the run table
@@ -205,7 +207,8 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                             const uint8_t *top = band + e.x + chunk * 16;
 #pragma unroll
                             for (int q = 0; q < RUN; ++q)
-                                store_a(a_tile, run * RUN + q, chunk, *reinterpret_cast<const float4 *>(top + q * (BLOCK_K * 4)), SPLIT3);
+                                store_a(a_tile, run * RUN + q, chunk,
+                                        *reinterpret_cast<const float4 *>(top + q * p.stride * (BLOCK_K * 4)), SPLIT3);
                         } else if (e.z) {
                             // regular run: RUN+1 adjacent columns of two band rows
                             const uint8_t *top = band + e.x + chunk * 16, *bot = band + e.y + chunk * 16;
@@ -279,9 +282,9 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
             if (gtile < p.ntiles) {
                 const int rem = gtile % tiles_per_img;
                 const int i0 = (rem / p.tiles_x) * p.TH, j0 = (rem % p.tiles_x) * p.TW;
-                const int by0 = i0 + p.hy_lo, bx0 = j0 + p.hx_lo;
+                const int by0 = i0 * p.stride + p.hy_lo, bx0 = j0 * p.stride + p.hx_lo;
                 const int i = i0 + pty, j = j0 + ptx;
-                const bool pix_ok = (gt < p.tile_px) && (i < p.h) && (j < p.w);
+                const bool pix_ok = (gt < p.tile_px) && (i < p.oh) && (j < p.ow);
                 const uint32_t tb = git & 1;
                 mbar_wait_sleep(rt_empty0 + 8 * tb, ((git >> 1) & 1) ^ 1);
                 uint32_t *ti = rt_i + tb * tab_n + grun;
@@ -291,6 +294,19 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     for (int b = 0; b < p.k; ++b, ++t) {
                         Sample s;
                         s.y0 = s.y1 = s.x0 = s.x1 = 0; s.dy1 = s.dy0 = s.dx1 = s.dx0 = 0.f;
+                        if (p.plain) {
+                            // identity sampler: the tap itself, in the same "padded frame" convention (+ph0, +pw0) as da_sample
+                            if (gq == 0 && pix_ok) {
+                                const int r0 = pty * p.stride + a, c0 = ptx * p.stride + b;       // band-relative
+                                ti[t * NRUN] = ((uint32_t)((r0 * p.BW + c0) * (BLOCK_K * 4)) >> 4) | (1u << 15) |
+                                               (((uint32_t)((r0 * p.BW + c0) * (BLOCK_K * 4)) >> 4) << 16) | (1u << 31);
+                                tw[t * NRUN] = make_float4(1.f, 0.f, 1.f, 0.f);
+                            } else if (gq == 0) {
+                                ti[t * NRUN] = (1u << 15);
+                                tw[t * NRUN] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            continue;
+                        }
                         if (pix_ok) {
                             const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
                             s = da_sample(i, j, a, b, yx.x, yx.y, p.in_h, p.in_w);
@@ -360,14 +376,14 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     if (f < p.F) {
                         for (int row = row0; row < BLOCK_M; row += rstep) {
                             const int ii = i0 + (row >> log_tw), jj = j0 + (row & (p.TW - 1));
-                            if (row >= p.tile_px || ii >= p.h || jj >= p.w) continue;
+                            if (row >= p.tile_px || ii >= p.oh || jj >= p.ow) continue;
                             const float4 raw = *reinterpret_cast<const float4 *>(epi + row * EPI_STRIDE + 4 * c4);
                             float v[4] = { raw.x + bv[0], raw.y + bv[1], raw.z + bv[2], raw.w + bv[3] };
                             if (p.flags & SKY_EPI_LEAKY_RELU) {
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) v[u] = v[u] > 0.f ? v[u] : v[u] * p.slope;
                             }
-                            const size_t go = ((size_t)(b_img * p.h + ii) * p.w + jj) * p.F + f;
+                            const size_t go = ((size_t)(b_img * p.oh + ii) * p.ow + jj) * p.F + f;
                             if (p.flags & SKY_EPI_RESIDUAL) {
                                 if (vec_ok) {
                                     const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + go));
@@ -495,7 +511,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     mbar_wait_sleep(band_empty0 + 8 * nb, ((bandg / p.NB) & 1) ^ 1);
                     if (p.flags & (1 << 18)) { mbar_arrive(band_full0 + 8 * nb); continue; }   // timing experiment: no band load
                     mbar_arrive_expect_tx(band_full0 + 8 * nb, (uint32_t)p.band_bytes);
-                    tma_load_4d(smem_u32(bands + nb * p.band_stride), &tmap, cc * BLOCK_K, j0 + p.hx_lo, i0 + p.hy_lo, b_img,
+                    tma_load_4d(smem_u32(bands + nb * p.band_stride), &tmap, cc * BLOCK_K, j0 * p.stride + p.hx_lo, i0 * p.stride + p.hy_lo, b_img,
                                 band_full0 + 8 * nb);
                 }
             }
@@ -561,13 +577,13 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
         for (int nb_try = (p.CC > 1 ? 2 : 1); nb_try >= 1 && cost_of[v] < 0; --nb_try)
             for (int c = 0; c < ncand; ++c) {
                 const int TH = v == 0 ? cand128[c][0] : cand64[c][0], TW = v == 0 ? cand128[c][1] : cand64[c][1];
-                if ((TH > 2 * a.h && TH > 1) || (TW > 2 * a.w && TW > 8)) continue;
-                const int BH = TH + hy_span, BW = TW + hx_span;
+                if ((TH > 2 * p.oh && TH > 1) || (TW > 2 * p.ow && TW > 8)) continue;
+                const int BH = (TH - 1) * p.stride + 1 + hy_span, BW = (TW - 1) * p.stride + 1 + hx_span;
                 if (BW > 256 || BH > 256 || BW < RUN + 1) continue;
                 const int band_bytes = BH * BW * BLOCK_K * 4;
                 const int band_stride = round_up(band_bytes, 1024);
                 if (L::total_bytes(p.Fp, band_stride, nb_try, p.k2) > 227 * 1024) continue;
-                const int tiles_y = (a.h + TH - 1) / TH, tiles_x = (a.w + TW - 1) / TW;
+                const int tiles_y = (p.oh + TH - 1) / TH, tiles_x = (p.ow + TW - 1) / TW;
                 const long cost = (long)tiles_y * tiles_x * BH * BW;
                 if (cost_of[v] < 0 || cost < cost_of[v]) {
                     cost_of[v] = cost;
@@ -612,7 +628,7 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
 
 int launch_fwd_band(const FwdArgs &a)
 {
-    if (a.C % BLOCK_K != 0 || a.offsets_host == nullptr) return SKY_ERR_UNSUPPORTED;
+    if (a.C % BLOCK_K != 0 || (a.offsets_host == nullptr && a.plain_stride == 0)) return SKY_ERR_UNSUPPORTED;
     BandParams p;
     p.x = a.x; p.offsets = a.offsets; p.packed = a.packed; p.bias = a.bias; p.residual = a.residual; p.y = a.y; p.stats = a.stats;
     p.B = a.B; p.h = a.h; p.w = a.w; p.C = a.C; p.F = a.F; p.Fp = f_pad_of(a.F); p.k = a.k; p.k2 = a.k * a.k;
@@ -626,7 +642,17 @@ int launch_fwd_band(const FwdArgs &a)
     while ((int)p.tmem_cols < 2 * p.Fp) p.tmem_cols <<= 1;
     if (p.tmem_cols > 512) return SKY_ERR_UNSUPPORTED;
     int hy_lo, hy_hi, hx_lo, hx_hi;
-    compute_halo(a.offsets_host, a.h, a.w, a.k, &hy_lo, &hy_hi, &hx_lo, &hx_hi);
+    p.plain = 0; p.stride = 1; p.oh = a.h; p.ow = a.w;
+    if (a.plain_stride > 0) {
+        // tf.nn.conv2d SAME: out = ceil(n/s), total pad = max((out-1)*s + k - n, 0), the smaller half in front
+        p.plain = 1; p.stride = a.plain_stride;
+        p.oh = (a.h + p.stride - 1) / p.stride; p.ow = (a.w + p.stride - 1) / p.stride;
+        const int th = (p.oh - 1) * p.stride + a.k - a.h, tw = (p.ow - 1) * p.stride + a.k - a.w;
+        p.ph0 = (th > 0 ? th : 0) / 2; p.pw0 = (tw > 0 ? tw : 0) / 2;
+        hy_lo = -p.ph0; hx_lo = -p.pw0; hy_hi = hy_lo + a.k - 1; hx_hi = hx_lo + a.k - 1;
+    } else {
+        compute_halo(a.offsets_host, a.h, a.w, a.k, &hy_lo, &hy_hi, &hx_lo, &hx_hi);
+    }
     p.hy_lo = hy_lo; p.hx_lo = hx_lo;
     const int hy_span = hy_hi - hy_lo, hx_span = hx_hi - hx_lo;
     if (a.math_mode == SKY_MATH_TF32)

@@ -5,10 +5,9 @@
                                                                                then a stride-1 SAME conv; only the
                                                                                'resize' method is used by generator.py)
 
-Variables keep the reference's names and shapes: ``w`` / ``kernel`` [k_h, k_w, C, F], ``biases`` [F].  Stride-1 odd-k
-layers with C % 32 == 0 run through the distortion-aware entry point with an all-zero offset table (the sampler then
-degenerates to the integer taps of a SAME conv and the band-staged tcgen05 kernel applies); everything else takes the
-identity-sampler mode of the direct kernel (sky_conv2d_fwd).
+Variables keep the reference's names and shapes: ``w`` / ``kernel`` [k_h, k_w, C, F], ``biases`` [F].  Layers with
+C % 32 == 0 run the identity-sampler mode of the band-staged tcgen05 kernel (stride 1 or 2), image-like inputs (C <= 4)
+the fp32 small-C kernel, anything else the direct-gather kernel (all behind sky_conv2d_fwd / sky_conv2d_smallc_fwd).
 """
 from __future__ import annotations
 
@@ -96,14 +95,6 @@ class _PlainConvCore:
             # image-like input (conv1_d): fp32 CUDA-core kernel, the unpacked variable is read directly
             check(LIB.sky_conv2d_smallc_fwd(x.data_ptr(), self._weight().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
                                             _ptr(stats), B, h, w, C, F, k, flags, slope, _stream()))
-        elif s == 1 and k % 2 == 1 and k >= 3 and C % 32 == 0:
-            if self._zero_tab is None or self._zero_tab[0].shape[0] != h:
-                host = np.zeros((h, k * k, 2), np.float32)
-                self._zero_tab = (torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device), host)
-            dev, host = self._zero_tab
-            check(LIB.sky_da_conv2d_fwd(x.data_ptr(), dev.data_ptr(), host.ctypes.data, self._packed_weights().data_ptr(),
-                                        self._bias().data_ptr(), y.data_ptr(), _ptr(residual), _ptr(stats), B, h, w, C, F, k,
-                                        flags, slope, mode, _stream()))
         else:
             check(LIB.sky_conv2d_fwd(x.data_ptr(), self._packed_weights().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
                                      _ptr(residual), _ptr(stats), B, h, w, C, F, k, s, flags, slope, mode, _stream()))
