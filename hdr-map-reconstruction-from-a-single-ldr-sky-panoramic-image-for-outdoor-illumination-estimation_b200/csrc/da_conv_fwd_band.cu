@@ -289,6 +289,15 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 mbar_wait_sleep(rt_empty0 + 8 * tb, ((git >> 1) & 1) ^ 1);
                 uint32_t *ti = rt_i + tb * tab_n + grun;
                 float4 *tw = rt_w + tb * tab_n + grun;
+                // 3x3 layers: fetch the row's nine offsets up front (independent loads) instead of one dependent
+                // global round trip per tap — this is on the critical path of a CTA's first tile
+                float2 pre[9];
+                const bool prefetched = (p.k2 == 9) && !p.plain;
+                if (prefetched) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q)
+                        pre[q] = pix_ok ? __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * 9 + q) : make_float2(0.f, 0.f);
+                }
                 int t = 0;
                 for (int a = 0; a < p.k; ++a)
                     for (int b = 0; b < p.k; ++b, ++t) {
@@ -308,7 +317,15 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                             continue;
                         }
                         if (pix_ok) {
-                            const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
+                            float2 yx;
+                            if (prefetched) {
+                                yx = pre[0];
+#pragma unroll
+                                for (int q = 1; q < 9; ++q)
+                                    if (q == t) yx = pre[q];
+                            } else {
+                                yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
+                            }
                             s = da_sample(i, j, a, b, yx.x, yx.y, p.in_h, p.in_w);
                         }
                         // the run's first pixel defines the run; every in-image pixel must agree with it
