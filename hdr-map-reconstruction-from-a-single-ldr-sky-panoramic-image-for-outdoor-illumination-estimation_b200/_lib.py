@@ -31,6 +31,7 @@ SIGNATURES = {
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
+    "sky_debug_band_trace": (_i, [_vp]),
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

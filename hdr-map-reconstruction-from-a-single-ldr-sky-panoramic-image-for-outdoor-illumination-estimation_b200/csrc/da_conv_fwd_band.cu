@@ -45,6 +45,18 @@ constexpr int EPI_COLS = 16, EPI_STRIDE = 20;       // staging row stride (float
 constexpr int ATOMS = 1;
 static_assert(EPI_WARP0 % 4 == 0, "epilogue warps must align with TMEM lane quadrants");
 
+// Optional timeline probe (tools/trace_band.py): block 0 stamps %globaltimer at a few pipeline events when bit 21 of the
+// flags word is set.  Never set in production.
+__device__ unsigned long long g_band_trace[16];
+__device__ __forceinline__ void trace_stamp(const int flags, int slot)
+{
+    if ((flags & (1 << 21)) && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_band_trace[slot] = t;
+    }
+}
+
 struct BandParams {
     const float *x, *offsets, *packed, *bias, *residual;
     float *y;
@@ -139,6 +151,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
     const uint32_t rt_full0 = tmem_empty0 + 16, rt_empty0 = rt_full0 + 16;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) trace_stamp(p.flags, 0);     // kernel start
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -167,6 +180,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
+    if (tid == 0) trace_stamp(p.flags, 1);     // prologue done (barriers, TMEM)
 
     if (warp < PROD_WARPS) {
         // ================================================ PRODUCERS ================================================
@@ -181,11 +195,13 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
             const int ri = i0 + rty, rj = j0 + rtx;
             const uint32_t tb = it & 1;
             mbar_wait(rt_full0 + 8 * tb, (it >> 1) & 1);              // geometry of this tile is in the run table
+            if (tid == 0 && it == 0) trace_stamp(p.flags, 2);       // first run table ready
             const uint32_t *ti = rt_i + tb * tab_n + run;
             const float4 *tw = rt_w + tb * tab_n + run;
             for (int cc = 0; cc < p.CC; ++cc, ++bandg) {
                 const int nb = bandg % p.NB;
                 mbar_wait(band_full0 + 8 * nb, (bandg / p.NB) & 1);
+                if (tid == 0 && bandg == 0) trace_stamp(p.flags, 3);   // first band landed
                 const uint8_t *band = bands + nb * p.band_stride;
                 const int ch_glob = cc * BLOCK_K + chunk * 4;
                 for (int t0 = 0; t0 < p.k2; t0 += ATOMS, ++sg) {
@@ -193,6 +209,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     const int natoms = min(ATOMS, p.k2 - t0);
                     const int s = sg % STAGES;
                     mbar_wait(empty0 + 8 * s, ((sg / STAGES) & 1) ^ 1);
+                    if (tid == 0 && it == 0 && sg >= 16 && sg < 32) trace_stamp(p.flags, 8 + ((sg - 16) / 4) * 2);   // group 0: stage free
                     for (int at = 0; at < natoms; ++at) {
                         const int t = t0 + at;
                         const uint32_t ew = ti[t * NRUN];
@@ -233,8 +250,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                             }
                         } else {
                             // irregular run: exact per-pixel geometry, corners from the band, from global, or the zero halo
-                            const float2 yx = (ri < p.h) ? __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)ri * p.k2 + t)
-                                                         : make_float2(0.f, 0.f);
+                            const float2 yx = make_float2(f.x, f.y);     // the tap's offsets, left in the table by the geometry warps
                             const int ta = t / p.k, tbb = t % p.k;
                             for (int q = 0; q < RUN; ++q) {
                                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -256,11 +272,13 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8 * s);
+                    if (tid == 0 && it == 0 && sg >= 16 && sg < 32) trace_stamp(p.flags, 9 + ((sg - 16) / 4) * 2);   // group 0: stage filled
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(band_empty0 + 8 * nb);   // this warp no longer reads the band buffer
             }
             __syncwarp();
+            if (tid == 0 && it == 0) trace_stamp(p.flags, 4);       // producers done with the first tile
             if (lane == 0) mbar_arrive(rt_empty0 + 8 * tb);         // ... nor this tile's run table
         }
     } else if (warp < EPI_WARP0 + 4) {
@@ -350,6 +368,18 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                                         integer_taps ? 1 : 0)
                                             : make_int4(0, 0, 0, 0);
                                 f = make_float4(s.dy1, s.dy0, s.dx1, s.dx0);
+                                if (!regular) {   // the exact per-pixel path needs the tap's offsets, not the factors
+                                    float2 yx;
+                                    if (prefetched) {
+                                        yx = pre[0];
+#pragma unroll
+                                        for (int q = 1; q < 9; ++q)
+                                            if (q == t) yx = pre[q];
+                                    } else {
+                                        yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
+                                    }
+                                    f = make_float4(yx.x, yx.y, 0.f, 0.f);
+                                }
                             } else {
                                 e.z = 1;   // run entirely outside the panorama (tile overhang): rows are never stored; read anything
                             }
@@ -367,6 +397,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
             const uint32_t acc = it & 1;
             mbar_wait_sleep(tmem_full0 + 8 * acc, (it >> 1) & 1);   // a whole tile away: back off, leave issue slots to producers
             tc_fence_after();
+            if (etid == 0 && it == 0) trace_stamp(p.flags, 5);      // first accumulator complete
             const uint32_t taddr = tmem_base + acc * (uint32_t)p.Fp + ((uint32_t)(wq * 32) << 16);
             for (int c0 = 0; c0 < ((p.flags & (1 << 19)) ? 0 : p.Fp); c0 += EPI_COLS) {   // bit 19: timing experiment, no epilogue
                 const int ncols = EPI_COLS;                   // F_pad is a multiple of 16
@@ -430,21 +461,23 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                         }
                     }
                     if (p.stats) {
-                        // threads with the same c4 (stride 1<<lg in etid) hold partial sums of the same 4 filters
-                        float *pp = part + etid * 8;     // [128][8] floats
+                        // lanes with equal (lane & (c4n-1)) hold partial sums of the same 4 filters: butterfly over the
+                        // remaining lane bits, then one fp64 atomic per (warp, filter)
+                        for (int o = (1 << lg); o < 32; o <<= 1) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { pp[u] = s1[u]; pp[4 + u] = s2[u]; }
-                        named_bar_sync(2, 128);
-                        if (etid < ncols && c0 + etid < p.F) {
-                            const int cc4 = etid >> 2, u = etid & 3;
-                            double d1 = 0.0, d2 = 0.0;
-                            for (int k = cc4; k < 128; k += (1 << lg)) {
-                                d1 += (double)part[k * 8 + u];
-                                d2 += (double)part[k * 8 + 4 + u];
+                            for (int u = 0; u < 4; ++u) {
+                                s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+                                s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
                             }
-                            double *st = p.stats + ((size_t)b_img * p.F + c0 + etid) * 2;
-                            atomicAdd(st, d1);
-                            atomicAdd(st + 1, d2);
+                        }
+                        if (lane < (1 << lg) && f < p.F) {
+                            double *st = p.stats + ((size_t)b_img * p.F + f) * 2;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (f + u < p.F) {
+                                    atomicAdd(st + 2 * u, (double)s1[u]);
+                                    atomicAdd(st + 2 * u + 1, (double)s2[u]);
+                                }
                         }
                     }
                 }
@@ -452,6 +485,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
             }
             tc_fence_before();
             __syncwarp();
+            if (etid == 0 && it == 0) trace_stamp(p.flags, 6);      // first epilogue done
             if (lane == 0) mbar_arrive(tmem_empty0 + 8 * acc);
         }
     } else if (warp == WARP_MMA) {
@@ -499,6 +533,13 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
         // ================================================ WEIGHT LOADER ================================================
         if (lane == 0) {
             const uint32_t atom_bytes = (uint32_t)(L::PLANES * b_bytes);
+            // The ring only lets STAGES weight tiles be in flight, so every tile's first touch would pay the full
+            // DRAM latency in turn: ask L2 for the whole packed kernel up front (all CTAs want the same bytes).
+            for (int kb = 0; kb < p.KB; ++kb)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint8_t *>(p.packed) +
+                                                                              (size_t)kb * atom_bytes),
+                             "r"(atom_bytes)
+                             : "memory");
             uint32_t sg = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
                 for (int cc = 0; cc < p.CC; ++cc)
@@ -541,31 +582,52 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    if (tid == 0) trace_stamp(p.flags, 7);     // kernel end
 }
 
-// Halo of input pixels (relative to an output pixel) that the regular taps can touch, from the host copy of the offset
-// table.  Zenith-row taps whose x offset is about -2w (the reference's double 360-degree wrap) are left to the global
-// fallback.  The estimate only affects speed: the kernel re-checks every corner against the band it actually holds.
+}  // namespace sky
+extern "C" int sky_debug_band_trace(unsigned long long *host_out16)
+{
+    SKY_CHECK_CUDA(cudaMemcpyFromSymbol(host_out16, sky::g_band_trace, sizeof(unsigned long long) * 16));
+    return SKY_OK;
+}
+namespace sky {
+
+// Halo of input pixels (relative to an output pixel) that the taps touch, from the host copy of the offset table.
+// Every (row, tap) is evaluated with the reference's own arithmetic (same steps as da_sample) at the middle column, so
+// the zenith-row taps — whose x offset of about -2w comes back as a small positive shift after the reference's two
+// 360-degree wraps — are covered too.  Shifts beyond +-(2k+6) columns are left to the exact fallback path.  The estimate
+// only affects speed: the kernel re-checks every corner against the band it actually holds.
 static void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi)
 {
     int ph0, pht, pw0, pwt;
     pad_axis(h, k, &ph0, &pht);
     pad_axis(w, k, &pw0, &pwt);
-    const int in_h = h + pht;
+    const int in_h = h + pht, in_w = w + pwt;
+    // The zenith row's shifted taps widen the band by ~5 columns for every tile; that only pays off when the zenith row
+    // is a sizeable share of the map (h <= 16).  On tall maps those few runs take the exact fallback path instead.
+    const int cap = h <= 16 ? 2 * k + 6 : k + 1;
+    const int j = w / 2;
     int ylo = 0, yhi = 0, xlo = 0, xhi = 0;
     for (int i = 0; i < h; ++i)
         for (int t = 0; t < k * k; ++t) {
             const float yo = off[((size_t)i * k * k + t) * 2 + 0], xo = off[((size_t)i * k * k + t) * 2 + 1];
-            if (!(fabsf(xo) <= 2.f * k + 2.f) || !(fabsf(yo) <= 2.f * k + 2.f)) continue;
+            if (!(yo == yo) || !(xo == xo)) continue;
             const int a = t / k, b = t % k;
-            float y = (float)(i + a) + yo;
+            float y = (float)(i + a) + yo, x = (float)(j + b) + xo;
             y = fminf(fmaxf(y, 0.f), (float)(in_h - 1));
+            if (x < 0.f) x = x + (float)in_w;
+            if (x > (float)(in_w - 1)) x = x - (float)in_w;
             int y0 = (int)floorf(y), y1 = y0 + 1;
             y0 = y0 < 0 ? 0 : (y0 > in_h - 1 ? in_h - 1 : y0);
             y1 = y1 < 0 ? 0 : (y1 > in_h - 1 ? in_h - 1 : y1);
+            // the second (integer) wrap of the reference shifts a still-negative x by in_w once more
+            if (x < 0.f) x = x + (float)in_w;
             const int ry0 = y0 - ph0 - i, ry1 = y1 - ph0 - i;
-            const float xr = (float)b + xo;
-            const int rx0 = (int)floorf(xr - 2e-3f) - pw0, rx1 = (int)floorf(xr + 2e-3f) + 1 - pw0;
+            const float xr = x - (float)(j + pw0);                         // column shift relative to the output pixel
+            // +-2e-3: the fractional part of x depends on j through fp32 rounding only
+            const int rx0 = (int)floorf(xr - 2e-3f), rx1 = (int)floorf(xr + 2e-3f) + 1;
+            if (rx0 < -cap || rx1 > cap) continue;                          // far away (or wrapped): exact fallback path
             ylo = ry0 < ylo ? ry0 : ylo; yhi = ry1 > yhi ? ry1 : yhi;
             xlo = rx0 < xlo ? rx0 : xlo; xhi = rx1 > xhi ? rx1 : xhi;
         }
