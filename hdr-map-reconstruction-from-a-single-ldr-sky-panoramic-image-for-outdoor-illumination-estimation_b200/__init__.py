@@ -9,3 +9,4 @@ from .generator import resBlock, resLayer, InstanceNormalization   # noqa: F401
 from . import sharding                  # noqa: F401
 from . import ops                        # noqa: F401
 from .generator import model             # noqa: F401
+from . import trunk_train              # noqa: F401

@@ -28,9 +28,12 @@ SIGNATURES = {
     "sky_conv2d_fwd": (_i, [_vp] * 6 + [_i] * 8 + [_f, _i, _vp]),
     "sky_conv2d_smallc_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_f, _vp]),
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
+    "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
+    "sky_instnorm_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp]),
+    "sky_mse_loss": (_i, [_vp] * 4 + [ctypes.c_long, _vp]),
+    "sky_rmsprop_step": (_i, [_vp] * 3 + [ctypes.c_long, _f, _f, _f, _f, _vp]),
     "sky_debug_band_trace": (_i, [_vp]),
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }

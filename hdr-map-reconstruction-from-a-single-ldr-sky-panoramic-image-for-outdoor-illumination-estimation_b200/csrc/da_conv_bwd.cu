@@ -322,7 +322,7 @@ static int fill_bwd_params(BwdParams &p, const float *x, const float *offsets, c
 using namespace sky;
 
 extern "C" int sky_da_conv2d_bwd_data(const float *dy, const float *offsets, const float *kernel, float *dx, int B, int h, int w,
-                                      int C, int F, int k, void *stream)
+                                      int C, int F, int k, int accumulate, void *stream)
 {
     BwdParams p;
     int rc = fill_bwd_params(p, nullptr, offsets, kernel, dy, B, h, w, C, F, k);
@@ -330,7 +330,7 @@ extern "C" int sky_da_conv2d_bwd_data(const float *dy, const float *offsets, con
     SKY_REQUIRE(dy && offsets && kernel && dx, SKY_ERR_INVALID, "NULL pointer");
     p.dx = dx;
     cudaStream_t st = (cudaStream_t)stream;
-    SKY_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)p.M * C * sizeof(float), st));
+    if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)p.M * C * sizeof(float), st));
     const int smem = p.FC * 16384 + 2 * p.FC * 4096 + 64 + 1024;
     static bool configured = false;
     if (!configured) {
