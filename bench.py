@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 
 N_BLOCKS, C, K_SIZE = 6, 128, 3
 UNIT = "panoramas/s"
-METRICS = {"sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
+METRICS = {"trunk_train": "panoramas/sec (32x128, data-parallel train step of the DA residual trunk: fwd + L2 loss + bwd + 1 NCCL all-reduce + RMSprop)",
+           "sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
            "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)"}
 
 
@@ -57,6 +58,10 @@ def make_input(batch, h, w, seed):
 
 
 def workload_name(batch, H, W, workload="sky"):
+    if workload == "trunk_train":
+        return (f"res_trunk_train_step: 6 resBlocks with distortion-aware convs, forward + synthetic L2 objective + backward "
+                f"(IN/LeakyReLU bwd, DA dgrad/wgrad/dbias) + one all-reduce of the flat gradient buffer (7.1 MB) + fused Keras RMSprop, "
+                f"B={batch}/GPU on the {H // 4}x{W // 4}x{C} trunk map of {H}x{W} panoramas")
     if workload == "trunk":
         return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3, TF32) + 12 instance norms, "
                 f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
@@ -91,6 +96,21 @@ def oracle_step_fn(args, sample):
     """CPU restatement of the selected workload on `sample` panoramas (returns a zero-argument callable)."""
     import torch
     from oracle import model_oracle as M
+    if args.workload == "trunk_train":
+        blocks = [{k: torch.from_numpy(v).requires_grad_(True) for k, v in b.items()} for b in make_weights()]
+        x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
+        tgt = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=2))
+        params = [v for blk in blocks for v in blk.values()]
+        ms = [torch.zeros_like(v) for v in params]
+
+        def step():
+            loss = ((M.res_layer(x, blocks, K_SIZE) - tgt) ** 2).mean()
+            grads = torch.autograd.grad(loss, params)
+            with torch.no_grad():
+                for v, g, m in zip(params, grads, ms):
+                    m.mul_(0.9).add_(0.1 * g * g)
+                    v.sub_(1e-4 * g / (m.sqrt() + 1e-7))
+        return step
     if args.workload == "trunk":
         blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
         x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
@@ -177,7 +197,23 @@ def run_ours(args):
     B, H, W = args.batch, args.height, args.width
     h, w = H // 4, W // 4
     METRIC = METRICS[args.workload]
-    if args.workload == "trunk":
+    trainer = None
+    if args.workload == "trunk_train":
+        trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
+        trunk.build((B, h, w, C))
+        trunk.set_weights(make_weights())
+        trainer = pkg.trunk_train.TrunkTrainer(trunk, (B, h, w, C), lr=1e-4)
+        target = torch.from_numpy(make_input(B, h, w, seed=100 + rank)).cuda()
+        loss_buf = trainer._loss
+
+        def forward(inp):
+            trainer.train_step(inp, target)
+            return loss_buf
+        x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()
+        # per res-block: fwd 2 conv + 2 IN; bwd 2 x (IN reduce + IN apply) + 2 dgrad + 2 wgrad + 2 dbias + 2 pack (re-pack after the
+        # update); + loss + rmsprop
+        launches_per_step = N_BLOCKS * (4 + 4 + 6 + 2) + 2
+    elif args.workload == "trunk":
         trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
         trunk.build((B, h, w, C))
         trunk.set_weights(make_weights())
@@ -195,16 +231,24 @@ def run_ours(args):
         launches_per_step = 6 + 4 * N_BLOCKS + 7
     x = x_host.cuda()
     y_host = torch.empty_like(forward(x).cpu()).pin_memory()
+    if world > 1 and trainer is not None:
+        trainer.flat_w.copy_(trainer.flat_w)     # replicas start from identical weights (same numpy seed on every rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
 
     # ---- the step: captured once into a CUDA graph (24 kernel launches + 12 memsets) ----
+    use_graph = trainer is None                  # the train step (NCCL all-reduce inside) is launched eagerly
     side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
+    graph = None
+    if use_graph:
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                y = forward(x)                   # eager warm-up (packs weights, sizes scratch)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                y = forward(x)
+    else:
         for _ in range(2):
-            y = forward(x)                       # eager warm-up (packs weights, sizes scratch)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
             y = forward(x)
     torch.cuda.synchronize()
 
@@ -225,13 +269,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [s.elapsed_time(e) for s, e in evs]
 
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            forward(x)
+
     def step_device():
-        graph.replay()
+        run_step()
 
     def step_e2e():
         x.copy_(x_host, non_blocking=True)       # H2D of the step's input from pinned memory
-        graph.replay()
-        y_host.copy_(y, non_blocking=True)       # D2H of the step's result
+        run_step()
+        y_host.copy_(y, non_blocking=True)       # D2H of the step's result (inference: HDR map; training: the loss)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -284,7 +334,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
             "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B, "parallelism": f"batch shards x{world}, no collective",
-                       "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": True},
+                       "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": round(t_e2e, 4)},
             "gpu_launches": launches_per_step * args.steps,
@@ -330,7 +380,7 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
-    ap.add_argument("--workload", default="sky", choices=["sky", "trunk"],
+    ap.add_argument("--workload", default="sky", choices=["sky", "trunk", "trunk_train"],
                     help="sky: generator inference, sky branch (default); trunk: the DA residual trunk alone")
     args = ap.parse_args()
     if args.impl == "reference":

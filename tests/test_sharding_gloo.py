@@ -47,6 +47,29 @@ def test_shards_cover_batch_and_timings_take_the_max():
         assert ret[0][3] == ret[1][3] == [2.0, 5.0]
 
 
+def _worker_grad(rank, world, port, ret):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tt = importlib.import_module(PKG_NAME).trunk_train
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # this rank's flat gradient buffer
+    tt.allreduce_flat_(flat)                                           # the train step's single collective
+    ret[rank] = flat.tolist()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_sums_over_ranks():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_grad, args=(world, port, ret), nprocs=world, join=True)
+        ret = dict(ret)
+    want = (torch.arange(10, dtype=torch.float32) * 3).tolist()       # 1x + 2x; the 1/world lives in the RMSprop kernel
+    assert ret[0] == want and ret[1] == want
+
+
 def test_shard_bounds_edge_cases(pkg):
     sb = pkg.sharding.shard_bounds
     assert [sb(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
