@@ -55,6 +55,8 @@ struct BwdParams {
     int B, h, w, C, F, k, k2, CC, FC;   // CC = C/32, FC = F/32
     int in_h, in_w, ph0, pw0, M;
     int parts, tiles_per_part;           // wgrad: pixel partitions
+    int ksplit;                          // dgrad: the k-blocks of a tile are shared out over gridDim.y CTAs (dx is accumulated
+                                         // with atomics anyway), which fills the SMs when there are few pixel tiles
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -96,9 +98,17 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_dgrad_kernel(const BwdP
     const bool m_ok = (tid < 128) && (m < p.M);
     const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
 
-    const int KB = p.k2 * p.CC;
+    const int KB_all = p.k2 * p.CC;
+    const int kb_per = (KB_all + p.ksplit - 1) / p.ksplit;
+    const int kb_lo = blockIdx.y * kb_per;
+    const int KB = min(kb_per, KB_all - kb_lo);          // this CTA's k-blocks: kb_lo .. kb_lo + KB - 1 (local index kb below)
+    if (KB <= 0) {                                       // (uniform per CTA) nothing to do: release TMEM and leave
+        __syncthreads();
+        if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+        return;
+    }
     for (int kb = 0; kb < KB; ++kb) {
-        const int t = kb / p.CC, cc = kb % p.CC;
+        const int t = (kb_lo + kb) / p.CC, cc = (kb_lo + kb) % p.CC;
         uint8_t *bt = b_tile + (kb & 1) * p.FC * 4096;
         // B = kernel rows (t*C + cc*32 + n), n < 32: [32 x F] K-major in f
         for (int e = tid; e < 32 * p.F / 4; e += BWD_THREADS) {
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_dgrad_kernel(const BwdP
         }
         // drain the PREVIOUS k-block while this one's MMAs run (its barrier phase: use count of that buffer)
         if (kb > 0) {
-            const int pk = kb - 1, pt = pk / p.CC, pcc = pk % p.CC;
+            const int pk = kb - 1, pt = (kb_lo + pk) / p.CC, pcc = (kb_lo + pk) % p.CC;
             mbar_wait(bar0 + 8 * (pk & 1), (pk >> 1) & 1);
             tc_fence_after();
             if (warp < 4) {
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_dgrad_kernel(const BwdP
         __syncthreads();
     }
     {   // drain the last k-block
-        const int pk = KB - 1, pt = pk / p.CC, pcc = pk % p.CC;
+        const int pk = KB - 1, pt = (kb_lo + pk) / p.CC, pcc = (kb_lo + pk) % p.CC;
         mbar_wait(bar0 + 8 * (pk & 1), (pk >> 1) & 1);
         tc_fence_after();
         if (warp < 4) {
@@ -313,7 +323,7 @@ static int fill_bwd_params(BwdParams &p, const float *x, const float *offsets, c
     pad_axis(w, k, &p.pw0, &pwt);
     p.in_h = h + pht; p.in_w = w + pwt;
     p.M = B * h * w;
-    p.parts = 1; p.tiles_per_part = 0;
+    p.parts = 1; p.tiles_per_part = 0; p.ksplit = 1;
     return SKY_OK;
 }
 
@@ -337,7 +347,12 @@ extern "C" int sky_da_conv2d_bwd_data(const float *dy, const float *offsets, con
         SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    da_conv2d_dgrad_kernel<<<(p.M + BLOCK_M - 1) / BLOCK_M, BWD_THREADS, smem, st>>>(p);
+    const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    int ksplit = (2 * 148 + tiles - 1) / tiles;          // about two waves of CTAs
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > p.k2 * p.CC) ksplit = p.k2 * p.CC;
+    p.ksplit = ksplit;
+    da_conv2d_dgrad_kernel<<<dim3(tiles, ksplit), BWD_THREADS, smem, st>>>(p);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }
@@ -370,8 +385,8 @@ extern "C" int sky_da_conv2d_bwd_filter(const float *x, const float *dy, const f
     SKY_CHECK_CUDA(cudaGetLastError());
     if (dbias) {
         SKY_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)F * sizeof(float), st));
-        int ysplit = (p.M + 255) / 256;
-        if (ysplit > 296) ysplit = 296;
+        int ysplit = (p.M + 31) / 32;
+        if (ysplit > 8 * 148) ysplit = 8 * 148;
         dim3 g2((F + 127) / 128, ysplit);
         col_sum_kernel<<<g2, 128, 0, st>>>(dy, dbias, p.M, F);
         SKY_CHECK_CUDA(cudaGetLastError());
