@@ -10,3 +10,4 @@ from . import sharding                  # noqa: F401
 from . import ops                        # noqa: F401
 from .generator import model             # noqa: F401
 from . import trunk_train              # noqa: F401
+from . import sunpose_net              # noqa: F401

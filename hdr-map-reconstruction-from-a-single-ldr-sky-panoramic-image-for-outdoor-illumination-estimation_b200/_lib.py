@@ -34,6 +34,9 @@ SIGNATURES = {
     "sky_instnorm_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp]),
     "sky_mse_loss": (_i, [_vp] * 4 + [ctypes.c_long, _vp]),
     "sky_rmsprop_step": (_i, [_vp] * 3 + [ctypes.c_long, _f, _f, _f, _f, _vp]),
+    "sky_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sky_dense_fwd": (_i, [_vp] * 4 + [_i, _i, _i, _i, _vp]),
+    "sky_softmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),
     "sky_debug_band_trace": (_i, [_vp]),
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }

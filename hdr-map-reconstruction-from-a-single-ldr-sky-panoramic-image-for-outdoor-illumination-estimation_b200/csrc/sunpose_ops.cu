@@ -1,0 +1,157 @@
+// Small kernels of the sun-position network (sunpose_net.py): 2x2/2 SAME max-pool (ops.maxpool2d, ops.py:287-300),
+// Keras Dense as a weight-streaming skinny GEMM (fc1: [B, 8192] x [8192, 4096], fc2: [B, 4096] x [4096, 4096]; B = 32 rows
+// against 134 MB / 67 MB of fp32 weights => HBM-bound, fp32 FMA on the CUDA cores, split-K over the SMs), the bias + ReLU
+// finalisation of the split-K partial sums, and the row softmax (tf.nn.softmax, sunpose_net.py:70).
+#include "sky_common.cuh"
+
+namespace sky {
+
+// tf.nn.max_pool(ksize 2, strides 2, SAME): out = ceil(n/2), window clipped at the bottom / right edge.
+__global__ void maxpool2x2_kernel(const float *__restrict__ x, float *__restrict__ y, int B, int h, int w, int C, int oh, int ow)
+{
+    const int cv = C / 4;
+    const long total = (long)B * oh * ow * cv;
+    for (long o = blockIdx.x * (long)blockDim.x + threadIdx.x; o < total; o += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(o % cv) * 4;
+        const int ox = (int)((o / cv) % ow), oy = (int)((o / ((long)cv * ow)) % oh), b = (int)(o / ((long)cv * ow * oh));
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int yy = 2 * oy + dy, xx = 2 * ox + dx;
+                if (yy < h && xx < w) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(x + (((size_t)b * h + yy) * w + xx) * C + c));
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+            }
+        *reinterpret_cast<float4 *>(y + (((size_t)b * oh + oy) * ow + ox) * C + c) = m;
+    }
+}
+
+constexpr int DN_THREADS = 128;  // output columns per CTA
+constexpr int DN_BM = 32;        // batch rows per pass (accumulators per thread)
+constexpr int DN_BK = 64;        // k values staged per step
+
+// y[b, n] += sum_{k in this CTA's K range} x[b, k] * W[k, n]      (y zeroed by the caller; fp32)
+// grid: (N / 128, ksplit, ceil(B / 32)).  Thread t owns column n0 + t: one coalesced weight load feeds 32 FMAs.
+__global__ void __launch_bounds__(DN_THREADS)
+dense_splitk_kernel(const float *__restrict__ x, const float *__restrict__ W, float *__restrict__ y, int B, int K, int N, int k_per)
+{
+    __shared__ __align__(16) float xs[DN_BK][DN_BM];      // transposed activation tile: xs[k][b]
+    const int n = blockIdx.x * DN_THREADS + threadIdx.x;
+    const int b0 = blockIdx.z * DN_BM;
+    const int k_lo = blockIdx.y * k_per, k_hi = min(K, k_lo + k_per);
+    float acc[DN_BM];
+#pragma unroll
+    for (int b = 0; b < DN_BM; ++b) acc[b] = 0.f;
+    for (int k0 = k_lo; k0 < k_hi; k0 += DN_BK) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < DN_BK * DN_BM; e += DN_THREADS) {
+            const int kk = e % DN_BK, b = e / DN_BK;           // consecutive threads -> consecutive k: coalesced rows of x
+            xs[kk][b] = (b0 + b < B && k0 + kk < k_hi) ? __ldg(x + (size_t)(b0 + b) * K + k0 + kk) : 0.f;
+        }
+        __syncthreads();
+        if (n < N) {
+            const int kn = min(DN_BK, k_hi - k0);
+#pragma unroll 4
+            for (int kk = 0; kk < kn; ++kk) {
+                const float wv = __ldg(W + (size_t)(k0 + kk) * N + n);
+                const float4 *xr = reinterpret_cast<const float4 *>(xs[kk]);
+#pragma unroll
+                for (int q = 0; q < DN_BM / 4; ++q) {
+                    const float4 xv = xr[q];
+                    acc[4 * q + 0] = fmaf(xv.x, wv, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(xv.y, wv, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(xv.z, wv, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(xv.w, wv, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    if (n < N) {
+#pragma unroll
+        for (int b = 0; b < DN_BM; ++b)
+            if (b0 + b < B) atomicAdd(y + (size_t)(b0 + b) * N + n, acc[b]);
+    }
+}
+
+// y = act(y + bias)
+__global__ void dense_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total, int N, int relu)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        float v = y[e] + __ldg(bias + (int)(e % N));
+        y[e] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+
+// row softmax; one CTA per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float *__restrict__ x, float *__restrict__ y, int N)
+{
+    __shared__ float red[8];
+    const float *row = x + (size_t)blockIdx.x * N;
+    float *out = y + (size_t)blockIdx.x * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, row[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) s += expf(row[i] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    const float inv = 1.f / s;
+    for (int i = threadIdx.x; i < N; i += 256) out[i] = expf(row[i] - m) * inv;
+}
+
+}  // namespace sky
+
+using namespace sky;
+
+extern "C" int sky_maxpool2x2_fwd(const float *x, float *y, int B, int h, int w, int C, void *stream)
+{
+    SKY_REQUIRE(x && y && B > 0 && h > 0 && w > 0 && C > 0, SKY_ERR_INVALID, "bad arguments");
+    SKY_REQUIRE(C % 4 == 0, SKY_ERR_UNSUPPORTED, "max-pool kernel needs C %% 4 == 0 (got %d)", C);
+    const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+    const long total = (long)B * oh * ow * (C / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxpool2x2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, float *y, int B, int K, int N, int relu, void *stream)
+{
+    SKY_REQUIRE(x && W && bias && y && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SKY_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * N * sizeof(float), st));
+    const int ncta = (N + DN_THREADS - 1) / DN_THREADS, bcta = (B + DN_BM - 1) / DN_BM;
+    int ksplit = (4 * 148 + ncta * bcta - 1) / (ncta * bcta);          // about four waves of CTAs
+    int k_per = (K + ksplit - 1) / ksplit;
+    k_per = (k_per + DN_BK - 1) / DN_BK * DN_BK;
+    ksplit = (K + k_per - 1) / k_per;
+    dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    const long total = (long)B * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    dense_finalize_kernel<<<blocks, 256, 0, st>>>(y, bias, total, N, relu);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_softmax_rows(const float *x, float *y, int rows, int N, void *stream)
+{
+    SKY_REQUIRE(x && y && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, y, N);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}

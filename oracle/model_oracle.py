@@ -92,6 +92,68 @@ def sky_branch(ldr, w, k=3, acc_dtype=torch.float32, decompress=True):
     return hdr_log_decompression(sky) if decompress else sky
 
 
+def maxpool2x2_same(x):
+    """tf.nn.max_pool(ksize 2, strides 2, 'SAME') on NHWC (ops.py:299-300): out = ceil(n/2), -inf padding at the far edge."""
+    B, h, w, C = x.shape
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (0, w % 2, 0, h % 2), value=float("-inf"))
+    return torch.nn.functional.max_pool2d(xp, 2, 2).permute(0, 2, 3, 1).contiguous()
+
+
+def sunpose_layer(x, w, k, distortion_aware=True, acc_dtype=torch.float32):
+    """sunposeLayer.call (sunpose_net.py:19-30): (conv -> IN -> relu) x 2; conv = the distortion-aware layer (:11,16) or the
+    plain SAME conv (:10,15).  w: conv{1,2}_kernel [k*k*C, F], conv{1,2}_bias, norm{1,2}_gamma / _beta."""
+    dt = acc_dtype
+    for i in (1, 2):
+        kern, bias = O._as_t(w[f"conv{i}_kernel"]), O._as_t(w[f"conv{i}_bias"])
+        if distortion_aware:
+            x = O.conv2d_forward(x, kern, bias, k, acc_dtype=dt)
+        else:
+            C = kern.shape[0] // (k * k)
+            x = conv2d_same(x, kern.reshape(k, k, C, -1), bias, acc_dtype=dt)
+        x = torch.relu(instance_norm(x, O._as_t(w[f"norm{i}_gamma"]).to(dt), O._as_t(w[f"norm{i}_beta"]).to(dt)))
+    return x
+
+
+def sunpose_estimation(x, w, distortion_aware=True, acc_dtype=torch.float32):
+    """sunpose_net.model.sunposeEstimation (sunpose_net.py:54-72) -> (softmax [B, H*W], [act1, act2, act3])."""
+    dt = acc_dtype
+    x = O._as_t(x).to(dt)
+    acts = []
+    for name, k in (("sunlayer1", 7), ("sunlayer2", 3), ("sunlayer3", 3)):
+        a = sunpose_layer(x, w[name], k, distortion_aware, dt)
+        acts.append(a)
+        x = maxpool2x2_same(a)
+    flat = x.reshape(x.shape[0], -1)                                    # Keras Flatten: (h, w, c)
+    h1 = torch.relu(flat @ O._as_t(w["fc1"][0]).to(dt) + O._as_t(w["fc1"][1]).to(dt))
+    h2 = torch.relu(h1 @ O._as_t(w["fc2"][0]).to(dt) + O._as_t(w["fc2"][1]).to(dt))
+    return torch.softmax(h2, dim=-1), acts
+
+
+def random_sunpose_weights(seed, H, W, affine_noise=True):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = 3
+    for name, f, k in (("sunlayer1", 32, 7), ("sunlayer2", 64, 3), ("sunlayer3", 128, 3)):
+        d = {}
+        c = cin
+        for i in (1, 2):
+            lim = (6.0 / (k * k * c + f)) ** 0.5
+            d[f"conv{i}_kernel"] = rng.uniform(-lim, lim, (k * k * c, f)).astype(np.float32)
+            d[f"conv{i}_bias"] = (0.05 * rng.standard_normal(f) * affine_noise).astype(np.float32)
+            d[f"norm{i}_gamma"] = (1 + 0.1 * rng.standard_normal(f) * affine_noise).astype(np.float32)
+            d[f"norm{i}_beta"] = (0.1 * rng.standard_normal(f) * affine_noise).astype(np.float32)
+            c = f
+        w[name] = d
+        cin = f
+    flat = (H // 8) * (W // 8) * 128
+    fc = H * W
+    for name, kin in (("fc1", flat), ("fc2", fc)):
+        lim = (6.0 / (kin + fc)) ** 0.5
+        w[name] = (rng.uniform(-lim, lim, (kin, fc)).astype(np.float32), (0.05 * rng.standard_normal(fc) * affine_noise).astype(np.float32))
+    return w
+
+
 def random_generator_weights(seed, k=3, affine_noise=True):
     """numpy-seeded weights for the sky branch with the reference's initialiser distributions (Keras glorot_uniform on
     the 4-D kernels), biases / gamma / beta optionally perturbed so they are exercised."""
