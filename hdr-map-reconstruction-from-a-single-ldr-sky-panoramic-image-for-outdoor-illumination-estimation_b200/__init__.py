@@ -11,3 +11,6 @@ from . import ops                        # noqa: F401
 from .generator import model             # noqa: F401
 from . import trunk_train              # noqa: F401
 from . import sunpose_net              # noqa: F401
+from . import sunrad_net               # noqa: F401
+from . import grad_cam                 # noqa: F401
+from . import inference                # noqa: F401

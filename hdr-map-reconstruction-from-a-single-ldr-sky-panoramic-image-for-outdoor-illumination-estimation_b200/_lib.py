@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libskydome_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
-EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 256
+EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_SUN_BLEND, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 16, 256
 MATH_TF32, MATH_3XTF32 = 0, 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -39,6 +39,16 @@ SIGNATURES = {
     "sky_softmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),
     "sky_debug_band_trace": (_i, [_vp]),
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sky_conv2d_fwd_blend": (_i, [_vp] * 6 + [_f] + [_i] * 6 + [_f, _i, _vp]),
+    "sky_softmax_max_bwd": (_i, [_vp] * 4 + [_i, _i, _vp]),
+    "sky_transpose": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sky_dense_bwd_data": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
+    "sky_maxpool2x2_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
+    "sky_gradcam": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
+    "sky_sunrad_input": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "sky_bn_fold": (_i, [_vp] * 5 + [_f, _vp, _vp, ctypes.c_long, _i, _vp]),
+    "sky_max_nonneg": (_i, [_vp, _vp, ctypes.c_long, _vp]),
+    "sky_sun_radiance": (_i, [_vp] * 5 + [_i, _i, _f, _vp]),
 }
 
 

@@ -18,15 +18,37 @@ struct FwdArgs {
     const float *packed;
     const float *bias;
     const float *residual;
+    const float *aux = nullptr; // SKY_EPI_SUN_BLEND: the sky prediction in the log domain, [M][3]
+    float threshold = 0.f;      // SKY_EPI_SUN_BLEND: the alpha ramp width (inference.py:36)
     float *y;
     double *stats;              // [B][F][2] running (sum, sum of squares) of y per sample and filter, or NULL
     int B, h, w, C, F, k;
+    int ldF = 0;                // filters of the whole layer when this launch covers a slice of them (0: == F); y, residual,
+                                // stats are pre-offset to the slice and strided by ldF
     int flags;
     float slope;
     int math_mode;
     int plain_stride;           // 0: distortion-aware sampling; 1 or 2: plain SAME conv with that stride (direct kernel only)
     cudaStream_t stream;
 };
+
+#ifdef __CUDACC__
+// SKY_EPI_SUN_BLEND — the tail of inference.generator_in_step (inference.py:90-92, 106-110) for one pixel.  v: the sun
+// prediction in the log domain (what sun_decode returns, generator.py:153-156); sky: the sky prediction in the log domain.
+//   alpha = min(1, max(0, max_c(logDecompress(sky_c)) - 1 + T) / T);  v_c = (1 - alpha) * sky_c + alpha * v_c
+// (hdr_logDecompression of the blend is the SKY_EPI_LOG_DECOMPRESS step that follows).
+__device__ __forceinline__ void sun_blend3(float v[3], const float *__restrict__ sky, float threshold)
+{
+    const float s0 = __ldg(sky), s1 = __ldg(sky + 1), s2 = __ldg(sky + 2);
+    const float gmax = fmaxf(fmaxf(s0, s1), s2);                       // exp is monotonic: max of the linear values
+    const float lin = __fdiv_rn(__fsub_rn(expf(__fmul_rn(gmax, 2.3978953f)), 1.f), 10.f);
+    const float alpha = fminf(1.f, __fdiv_rn(fmaxf(0.f, __fadd_rn(__fsub_rn(lin, 1.f), threshold)), threshold));
+    const float na = __fsub_rn(1.f, alpha);
+    v[0] = __fadd_rn(__fmul_rn(na, s0), __fmul_rn(alpha, v[0]));
+    v[1] = __fadd_rn(__fmul_rn(na, s1), __fmul_rn(alpha, v[1]));
+    v[2] = __fadd_rn(__fmul_rn(na, s2), __fmul_rn(alpha, v[2]));
+}
+#endif
 
 // direct-gather kernel (any C): corners read straight from global/L2
 int launch_fwd_direct(const FwdArgs &a);

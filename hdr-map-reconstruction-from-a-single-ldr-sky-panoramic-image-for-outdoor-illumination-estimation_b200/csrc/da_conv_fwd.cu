@@ -24,7 +24,7 @@ constexpr int NUM_THREADS = NUM_PRODUCER_THREADS + 64;   // + MMA warp + weight-
 // all taps of one 32-channel chunk, then the next chunk), so consecutive taps of a chunk are contiguous; otherwise
 // k-block kb simply covers kernel rows [32 kb, 32 kb + 32).
 __global__ void da_pack_weights_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int K, int F, int Fp,
-                                       int KB, int planes, int C, int k2)
+                                       int KB, int planes, int C, int k2, int ldk)
 {
     const long total = (long)KB * Fp * BLOCK_K;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -37,7 +37,7 @@ __global__ void da_pack_weights_kernel(const float *__restrict__ kernel, float *
             kidx = t * C + cc * BLOCK_K + kk;
         }
         float v = 0.f;
-        if (kidx < K && n < F) v = kernel[(size_t)kidx * F + n];
+        if (kidx < K && n < F) v = kernel[(size_t)kidx * ldk + n];
         const uint32_t hi = f32_to_tf32_rna(v);
         const size_t tile_floats = (size_t)Fp * BLOCK_K;
         const size_t o = (sw128_offset((uint32_t)n, (uint32_t)(kk >> 2)) >> 2) + (kk & 3);
@@ -58,9 +58,12 @@ struct FwdParams {
     const float *packed;
     const float *bias;
     const float *residual;
+    const float *aux;       // SKY_EPI_SUN_BLEND: sky prediction (log domain) [M][3]
+    float threshold;
     float *y;
     double *stats;
     int B, h, w, C, F, Fp, k, k2, K, KB;
+    int ldF;                // row stride of y / residual / stats (filters of the whole layer; == F unless the launch is a filter slice)
     int in_h, in_w, ph0, pw0;
     int M;                  // B*oh*ow
     int oh, ow;             // output map (== h, w for the distortion-aware layers)
@@ -214,8 +217,34 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     ++kb;
                 }
             }
+        } else if ((p.C & 3) == 0) {
+            // C % 4 == 0 (the 6 -> 8 channel-padded sunRadNet input, sunrad_net.py:37): a 16-byte chunk of the A row is four
+            // channels of ONE tap, so it is one sampling + one 128-bit gather per corner, like the fast path
+            int pj[BLOCK_M / 16], pi[BLOCK_M / 16], pb[BLOCK_M / 16];
+#pragma unroll
+            for (int r = 0; r < BLOCK_M / 16; ++r) {
+                const int m = m0 + row_base + 16 * r;
+                pj[r] = m % p.ow; pi[r] = (m / p.ow) % p.oh; pb[r] = m < p.M ? m / (p.ow * p.oh) : -1;
+            }
+            for (; kb < p.KB; ++kb) {
+                const int s = kb % STAGES;
+                const int kidx = kb * BLOCK_K + chunk * 4;
+                const bool k_ok = kidx < p.K;
+                const int t = k_ok ? kidx / p.C : 0, c = kidx % p.C;
+                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                uint8_t *a_tile = smem + s * stage_bytes;
+#pragma unroll
+                for (int r = 0; r < BLOCK_M / 16; ++r) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k_ok && pb[r] >= 0) v = blend4(p.x, sample_corners(p, pb[r], pi[r], pj[r], t), c);
+                    store_a_chunk(a_tile, row_base + 16 * r, chunk, v, SPLIT3);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
+            }
         } else {
-            // generic channel counts (3-channel image layers, C not a multiple of 32): geometry per element
+            // generic channel counts (3-channel image layers, C not a multiple of 4): geometry per element
             for (; kb < p.KB; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
@@ -255,7 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
         tc_fence_after();
         const int m = m0 + warp * 32 + lane;         // TMEM lane == tile row
         const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const bool vec_ok = (p.F % 4) == 0;
+        const bool vec_ok = (p.F % 4) == 0 && (p.ldF % 4) == 0;
         for (int c0 = 0; c0 < p.Fp; c0 += 16) {
             uint32_t r[16];
             tmem_ld_32x16(taddr_row + (uint32_t)c0, r);
@@ -269,18 +298,25 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     if (f < p.F) {
                         val += __ldg(p.bias + f);
                         if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
-                        if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.F + f);
+                        if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.ldF + f);
                         if (p.flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
-                        if (p.flags & SKY_EPI_LOG_DECOMPRESS) val = (expf(val * 2.3978953f) - 1.f) / 10.f;   // log(11) as fp32
-                        if (p.stats) {   // generic path: plain atomics (the band-staged kernel reduces per tile first)
-                            double *st = p.stats + ((size_t)(m / (p.oh * p.ow)) * p.F + f) * 2;
-                            atomicAdd(st, (double)val);
-                            atomicAdd(st + 1, (double)val * (double)val);
-                        }
                     }
                     o[q] = val;
                 }
-                float *dst = p.y + (size_t)m * p.F + c0;
+                if ((p.flags & SKY_EPI_SUN_BLEND) && c0 == 0) sun_blend3(o, p.aux + (size_t)m * 3, p.threshold);   // F == 3
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int f = c0 + q;
+                    if (f < p.F) {
+                        if (p.flags & SKY_EPI_LOG_DECOMPRESS) o[q] = (expf(o[q] * 2.3978953f) - 1.f) / 10.f;   // log(11) as fp32
+                        if (p.stats) {   // generic path: plain atomics (the band-staged kernel reduces per tile first)
+                            double *st = p.stats + ((size_t)(m / (p.oh * p.ow)) * p.ldF + f) * 2;
+                            atomicAdd(st, (double)o[q]);
+                            atomicAdd(st + 1, (double)o[q] * (double)o[q]);
+                        }
+                    }
+                }
+                float *dst = p.y + (size_t)m * p.ldF + c0;
                 if (vec_ok && c0 + 16 <= p.F) {
 #pragma unroll
                     for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(dst + q) = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
@@ -449,27 +485,42 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
 
 using namespace sky;
 
+// Layers with more than 256 filters (sunRadNet d4: 512, sunrad_net.py:40) are run as slices of <= 256 filters, each with
+// its own packed image; the images are stored back to back.
+static inline int slice_count(int F) { return (F + 255) / 256; }
+static inline int slice_filters(int F, int s) { return (F - 256 * s) < 256 ? (F - 256 * s) : 256; }
+static inline size_t slice_bytes(int C, int Fs, int k, int math_mode)
+{
+    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K, Fp = f_pad_of(Fs);
+    const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
+    return (size_t)KB * planes * Fp * BLOCK_K * sizeof(float);
+}
+
 extern "C" size_t sky_da_packed_weight_bytes(int C, int F, int k, int math_mode)
 {
     if (C <= 0 || F <= 0 || k <= 0) return 0;
-    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K, Fp = f_pad_of(F);
-    const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
-    return (size_t)KB * planes * Fp * BLOCK_K * sizeof(float);
+    size_t total = 0;
+    for (int s = 0; s < slice_count(F); ++s) total += slice_bytes(C, slice_filters(F, s), k, math_mode);
+    return total;
 }
 
 extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int F, int k, int math_mode, void *stream)
 {
     SKY_REQUIRE(kernel && packed, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(C > 0 && F > 0 && k > 0, SKY_ERR_INVALID, "non-positive dimension");
-    SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
     SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
-    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K, Fp = f_pad_of(F);
+    const int K = k * k * C, KB = (K + BLOCK_K - 1) / BLOCK_K;
     const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
-    const long total = (long)KB * Fp * BLOCK_K;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, K, F, Fp, KB, planes, C, k * k);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    uint8_t *dst = (uint8_t *)packed;
+    for (int s = 0; s < slice_count(F); ++s) {
+        const int Fs = slice_filters(F, s), Fp = f_pad_of(Fs);
+        const long total = (long)KB * Fp * BLOCK_K;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel + 256 * s, (float *)dst, K, Fs, Fp, KB, planes, C, k * k, F);
+        SKY_CHECK_CUDA(cudaGetLastError());
+        dst += slice_bytes(C, Fs, k, math_mode);
+    }
     return SKY_OK;
 }
 
@@ -477,6 +528,7 @@ int sky::launch_fwd_direct(const FwdArgs &a)
 {
     FwdParams p;
     p.x = a.x; p.offsets = a.offsets; p.packed = a.packed; p.bias = a.bias; p.residual = a.residual; p.y = a.y; p.stats = a.stats;
+    p.aux = a.aux; p.threshold = a.threshold; p.ldF = a.ldF > 0 ? a.ldF : a.F;
     p.B = a.B; p.h = a.h; p.w = a.w; p.C = a.C; p.F = a.F; p.Fp = f_pad_of(a.F); p.k = a.k; p.k2 = a.k * a.k;
     p.K = a.k * a.k * a.C; p.KB = (p.K + BLOCK_K - 1) / BLOCK_K;
     int pht, pwt;
@@ -523,29 +575,64 @@ extern "C" int sky_da_conv2d_fwd(const float *x, const float *offsets, const flo
     return launch_fwd_direct(a);
 }
 
+// Plain SAME conv, any filter count: slices of <= 256 filters, each a launch over its own packed image.
+static int conv2d_plain(FwdArgs a, int stride)
+{
+    SKY_REQUIRE(a.B > 0 && a.h > 0 && a.w > 0 && a.C > 0 && a.F > 0, SKY_ERR_INVALID, "non-positive dimension");
+    SKY_REQUIRE(a.k >= 1 && a.k <= 15, SKY_ERR_UNSUPPORTED, "kernel size %d outside 1..15", a.k);
+    SKY_REQUIRE(stride == 1 || stride == 2, SKY_ERR_UNSUPPORTED, "stride %d not supported (the path uses 1 and 2)", stride);
+    SKY_REQUIRE(a.x && a.packed && a.bias && a.y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(!(a.flags & SKY_EPI_RESIDUAL) || a.residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
+    SKY_REQUIRE(!(a.flags & SKY_EPI_SUN_BLEND) || (a.aux && a.F == 3 && a.threshold > 0.f), SKY_ERR_INVALID,
+                "SKY_EPI_SUN_BLEND needs the sky prediction, 3 filters and a positive threshold");
+    SKY_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.y & 15) == 0 && ((uintptr_t)a.packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
+    SKY_REQUIRE(a.math_mode == SKY_MATH_TF32 || a.math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", a.math_mode);
+    SKY_REQUIRE((long)a.B * a.h * a.w * (long)(a.C > a.F ? a.C : a.F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
+    a.offsets = nullptr; a.offsets_host = nullptr; a.plain_stride = stride;
+    const int F = a.F;
+    if (F <= 256) {
+        if ((a.C % BLOCK_K) == 0 && !(a.flags & SKY_EPI_FORCE_DIRECT)) {
+            int rc = launch_fwd_band(a);        // identity sampler in the band-staged kernel (any stride the band fits)
+            if (rc != SKY_ERR_UNSUPPORTED) return rc;
+        }
+        return launch_fwd_direct(a);
+    }
+    const uint8_t *packed = (const uint8_t *)a.packed;
+    for (int s = 0; s < slice_count(F); ++s) {
+        FwdArgs b = a;
+        b.F = slice_filters(F, s); b.ldF = F;
+        b.packed = (const float *)packed; b.bias = a.bias + 256 * s; b.y = a.y + 256 * s;
+        b.residual = a.residual ? a.residual + 256 * s : nullptr;
+        b.stats = a.stats ? a.stats + 2 * 256 * s : nullptr;
+        int rc = launch_fwd_direct(b);
+        if (rc != SKY_OK) return rc;
+        packed += slice_bytes(a.C, b.F, a.k, a.math_mode);
+    }
+    return SKY_OK;
+}
+
 extern "C" int sky_conv2d_fwd(const float *x, const void *packed, const float *bias, float *y, const float *residual, double *stats,
                               int B, int h, int w, int C, int F, int k, int stride, int epilogue_flags, float slope,
                               int math_mode, void *stream)
 {
-    SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension");
-    SKY_REQUIRE(k >= 1 && k <= 15, SKY_ERR_UNSUPPORTED, "kernel size %d outside 1..15", k);
-    SKY_REQUIRE(stride == 1 || stride == 2, SKY_ERR_UNSUPPORTED, "stride %d not supported (the path uses 1 and 2)", stride);
-    SKY_REQUIRE(x && packed && bias && y, SKY_ERR_INVALID, "NULL pointer");
-    SKY_REQUIRE(F <= 256, SKY_ERR_UNSUPPORTED, "filters=%d > 256 not supported by the tensor-core path", F);
-    SKY_REQUIRE(!(epilogue_flags & SKY_EPI_RESIDUAL) || residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
-    SKY_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
-    SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
-    SKY_REQUIRE((long)B * h * w * (long)(C > F ? C : F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
+    SKY_REQUIRE(!(epilogue_flags & SKY_EPI_SUN_BLEND), SKY_ERR_INVALID, "SKY_EPI_SUN_BLEND is taken by sky_conv2d_fwd_blend");
     FwdArgs a;
-    a.x = x; a.offsets = nullptr; a.offsets_host = nullptr; a.packed = (const float *)packed; a.bias = bias;
+    a.x = x; a.packed = (const float *)packed; a.bias = bias;
     a.residual = residual; a.y = y; a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k;
     a.flags = epilogue_flags; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
-    a.plain_stride = stride;
-    if ((C % BLOCK_K) == 0 && !(epilogue_flags & SKY_EPI_FORCE_DIRECT)) {
-        int rc = launch_fwd_band(a);        // identity sampler in the band-staged kernel (any stride the band fits)
-        if (rc != SKY_ERR_UNSUPPORTED) return rc;
-    }
-    return launch_fwd_direct(a);
+    return conv2d_plain(a, stride);
+}
+
+extern "C" int sky_conv2d_fwd_blend(const float *x, const void *packed, const float *bias, float *y, const float *residual,
+                                    const float *sky_gamma, float threshold, int B, int h, int w, int C, int k,
+                                    int epilogue_flags, float slope, int math_mode, void *stream)
+{
+    FwdArgs a;
+    a.x = x; a.packed = (const float *)packed; a.bias = bias;
+    a.residual = residual; a.y = y; a.stats = nullptr; a.B = B; a.h = h; a.w = w; a.C = C; a.F = 3; a.k = k;
+    a.aux = sky_gamma; a.threshold = threshold;
+    a.flags = epilogue_flags | SKY_EPI_SUN_BLEND; a.slope = slope; a.math_mode = math_mode; a.stream = (cudaStream_t)stream;
+    return conv2d_plain(a, 1);
 }
 
 extern "C" int sky_da_conv2d_fwd_simt(const float *x, const float *offsets, const float *kernel, const float *bias, float *y,

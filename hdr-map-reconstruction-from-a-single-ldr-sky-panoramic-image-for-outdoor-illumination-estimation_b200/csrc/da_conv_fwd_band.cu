@@ -59,6 +59,8 @@ __device__ __forceinline__ void trace_stamp(const int flags, int slot)
 
 struct BandParams {
     const float *x, *offsets, *packed, *bias, *residual;
+    const float *aux;                      // SKY_EPI_SUN_BLEND: sky prediction (log domain), [pixels][3]
+    float threshold;
     float *y;
     double *stats;
     int B, h, w, C, F, Fp, k, k2, CC, KB;
@@ -445,6 +447,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 0.f);
                             }
+                            if ((p.flags & SKY_EPI_SUN_BLEND) && f == 0) sun_blend3(v, p.aux + go, p.threshold);   // F == 3: go = 3 * pixel
                             if (p.flags & SKY_EPI_LOG_DECOMPRESS) {   // tf_utils.hdr_logDecompression, log(11) as fp32
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) v[u] = (expf(v[u] * 2.3978953f) - 1.f) / 10.f;
@@ -708,7 +711,9 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
 int launch_fwd_band(const FwdArgs &a)
 {
     if (a.C % BLOCK_K != 0 || (a.offsets_host == nullptr && a.plain_stride == 0)) return SKY_ERR_UNSUPPORTED;
+    if (a.ldF > 0 && a.ldF != a.F) return SKY_ERR_UNSUPPORTED;      // filter slices take the direct kernel
     BandParams p;
+    p.aux = a.aux; p.threshold = a.threshold;
     p.x = a.x; p.offsets = a.offsets; p.packed = a.packed; p.bias = a.bias; p.residual = a.residual; p.y = a.y; p.stats = a.stats;
     p.B = a.B; p.h = a.h; p.w = a.w; p.C = a.C; p.F = a.F; p.Fp = f_pad_of(a.F); p.k = a.k; p.k2 = a.k * a.k;
     p.CC = a.C / BLOCK_K; p.KB = p.k2 * p.CC;

@@ -80,7 +80,7 @@ dense_splitk_kernel(const float *__restrict__ x, const float *__restrict__ W, fl
 __global__ void dense_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total, int N, int relu)
 {
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        float v = y[e] + __ldg(bias + (int)(e % N));
+        float v = y[e] + (bias ? __ldg(bias + (int)(e % N)) : 0.f);
         y[e] = relu ? fmaxf(v, 0.f) : v;
     }
 }
@@ -130,7 +130,7 @@ extern "C" int sky_maxpool2x2_fwd(const float *x, float *y, int B, int h, int w,
 
 extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, float *y, int B, int K, int N, int relu, void *stream)
 {
-    SKY_REQUIRE(x && W && bias && y && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    SKY_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     SKY_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * N * sizeof(float), st));
     const int ncta = (N + DN_THREADS - 1) / DN_THREADS, bcta = (B + DN_BM - 1) / DN_BM;
@@ -140,11 +140,13 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
     ksplit = (K + k_per - 1) / k_per;
     dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
     SKY_CHECK_CUDA(cudaGetLastError());
-    const long total = (long)B * N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    dense_finalize_kernel<<<blocks, 256, 0, st>>>(y, bias, total, N, relu);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    if (bias || relu) {      // bias == NULL: the plain product (sky_dense_bwd_data)
+        const long total = (long)B * N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dense_finalize_kernel<<<blocks, 256, 0, st>>>(y, bias, total, N, relu);
+        SKY_CHECK_CUDA(cudaGetLastError());
+    }
     return SKY_OK;
 }
 

@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import LIB, check
 from . import ops
 from .distortion_aware_ops import _require_cuda, _stream, conv2d as da_conv2d
+from .sunrad_net import sunRadNet
 
 
 class InstanceNormalization:
@@ -188,6 +189,17 @@ class model:
         self._dec = [_NormAct(c, device) for c in (self.conv3_f, self.conv2_f)]
         self.norm3_f, self.norm2_f = (d.norm for d in self._dec)
         self.conv1_f = ops.conv2d(output_channels=3, k_h=7, k_w=7, strides=1, **kw)
+        # sun_decode (generator.py:78-85)
+        self.conv3_u = ops.deconv2d(output_channels=64, output_imshape=[int(im_height / 2), int(im_width / 2)], k_h=3, k_w=3,
+                                    method='resize', **kw)
+        self.conv2_u = ops.deconv2d(output_channels=32, output_imshape=[int(im_height), int(im_width)], k_h=3, k_w=3,
+                                    method='resize', **kw)
+        self._dec_u = [_NormAct(c, device) for c in (self.conv3_u, self.conv2_u)]
+        self.norm3_u, self.norm2_u = (d.norm for d in self._dec_u)
+        self.conv1_u = ops.conv2d(output_channels=3, k_h=7, k_w=7, strides=1, **kw)
+        # enhanceSunRadiance (generator.py:88)
+        self.sun = sunRadNet(**kw)
+        self._gmax = None
 
     def encode(self, x, training="training"):
         for stage in self._enc:                       # generator.py:94-106
@@ -205,11 +217,54 @@ class model:
         """inference.py:84-86: hdr_logDecompression(sky_decode(encode(ldr), ldr)) — the linear-radiance sky prediction."""
         return self.sky_decode(self.encode(ldr), ldr, log_decompress=True)
 
-    def sun_decode(self, *a, **k):
-        raise NotImplementedError("sun branch (generator.py:127-156) is not built in this round")
+    def sun_decode(self, x, sun_cam1, sun_cam2, sun_cam3, sun_rad, training="training", *, blend_with=None, threshold=0.12,
+                   log_decompress=False):
+        """generator.py:127-156.  The CAM skip connections are commented out in the reference (:130-149), so the maps are unused
+        here too.  `blend_with` = the sky prediction in the log domain: the alpha blend of inference.py:90-92,106-109 (and, with
+        log_decompress, the final hdr_logDecompression of :110) then happen in conv1_u's epilogue."""
+        for stage in self._dec_u:                     # :136-147
+            x = stage(x)
+        blend = None if blend_with is None else (blend_with, threshold)
+        return self.conv1_u(x, leaky_slope=0.1, residual=sun_rad, relu=True, log_decompress=log_decompress, blend=blend)   # :150-156
 
-    def sun_rad_estimation(self, *a, **k):
-        raise NotImplementedError("sun radiance estimation (generator.py:158-169) is not built in this round")
+    def sun_rad_estimation(self, jpeg_img_float, sun_cam1, sun_cam2, sun_cam3, sunpose_pred, training="training", *,
+                           log_compress=False):
+        """generator.py:158-169 -> (sun_rad_t [B,H,W,3], gamma, beta).  reduce_max (:160), both resizes (:161-162) and the concat
+        (:164) are two small kernels in front of sunRadNet; log_compress=True returns hdr_logCompression(sun_rad_t)
+        (inference.py:105) straight from the radiance kernel.  The maximum is over the tensor this process holds (its batch shard)."""
+        ldr = _require_cuda(jpeg_img_float, "jpeg_img_float")
+        B, H, W, _ = ldr.shape
+        sm = _require_cuda(sunpose_pred, "sunpose_pred").reshape(B, H, W, 1)
+        if self._gmax is None:
+            self._gmax = torch.zeros(1, dtype=torch.float32, device=ldr.device)
+        check(LIB.sky_max_nonneg(sm.data_ptr(), self._gmax.data_ptr(), sm.numel(), _stream()))            # :160
+        plz = torch.empty((B, H, W, 8), dtype=torch.float32, device=ldr.device)                            # 6 channels + 2 of padding
+        c1, c2, c3 = (_require_cuda(c, "sun_cam") for c in (sun_cam1, sun_cam2, sun_cam3))
+        check(LIB.sky_sunrad_input(ldr.data_ptr(), c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), plz.data_ptr(), B, H, W,
+                                   c2.shape[1], c2.shape[2], c3.shape[1], c3.shape[2], 8, _stream()))     # :161-164
+        out, gamma, beta = self.sun(sm, plz, training, x_max=self._gmax, log_compress_tiled=log_compress)  # :165
+        if not log_compress:
+            out = out.expand(B, H, W, 3).contiguous()                                                      # :167
+        return out, gamma, beta
+
+    def blending(self, sky_pred, sun_pred, training="training"):
+        """generator.py:171-175: tf.add_n.  (generator_inference fuses it into conv1_u's epilogue instead.)"""
+        return sky_pred + sun_pred
+
+    def generator_inference(self, ldr, sun_model, threshold=0.12):
+        """inference.generator_in_step (inference.py:81-112): LDR panorama -> linear HDR panorama."""
+        from . import grad_cam
+        res_out = self.encode(ldr, training=False)                                          # :83
+        sky_pred_gamma = self.sky_decode(res_out, ldr, training=False)                      # :84 (:85 is folded into the blend)
+        sunpose_cmf, (sunlayer1, sunlayer2, sunlayer3) = sun_model.sunposeEstimation(ldr, training=False)   # :87
+        y_c = sun_model.class_score(sunpose_cmf)                                            # :98
+        sun_cam1 = grad_cam.layer(y_c, sunlayer1)                                           # :100-102
+        sun_cam2 = grad_cam.layer(y_c, sunlayer2)
+        sun_cam3 = grad_cam.layer(y_c, sunlayer3)
+        sun_rad_gamma, _, _ = self.sun_rad_estimation(ldr, sun_cam1, sun_cam2, sun_cam3, sunpose_cmf, training=False,
+                                                      log_compress=True)                    # :104-105
+        return self.sun_decode(res_out, sun_cam1, sun_cam2, sun_cam3, sun_rad_gamma, training=False, blend_with=sky_pred_gamma,
+                               threshold=threshold, log_decompress=True)                    # :106-110
 
     def build(self, batch_size=None):
         """Create every variable by tracing shapes (the reference builds lazily on the first call)."""
@@ -224,20 +279,40 @@ class model:
             st.conv.build(shp)
             st.norm.build(shp[:3] + (st.conv.output_channels,))
         self.conv1_f.build((B, H, W, 32))
+        for st, shp in zip(self._dec_u, [(B, H // 4, W // 4, 128), (B, H // 2, W // 2, 64)]):
+            st.conv.build(shp)
+            st.norm.build(shp[:3] + (st.conv.output_channels,))
+        self.conv1_u.build((B, H, W, 32))
+        self.sun.build(B, H, W)
 
     def set_weights(self, w):
         """w: dict keyed by the reference's attribute names: conv1_d/conv2_d/conv3_d/conv3_f/conv2_f/conv1_f ->
         (kernel [k,k,C,F], bias), norm*_d / norm*_f -> (gamma, beta), res -> list of res-block dicts."""
-        for name in ("conv1_d", "conv2_d", "conv3_d", "conv1_f"):
+        for name in ("conv1_d", "conv2_d", "conv3_d", "conv1_f", "conv1_u"):
+            if name not in w:
+                continue
             layer = getattr(self, name)
             layer.w.copy_(torch.as_tensor(w[name][0]))
             layer.biases.copy_(torch.as_tensor(w[name][1]))
-        for name in ("conv3_f", "conv2_f"):
+        for name in ("conv3_f", "conv2_f", "conv3_u", "conv2_u"):
+            if name not in w:
+                continue
             layer = getattr(self, name)
             layer.kernel.copy_(torch.as_tensor(w[name][0]))
             layer.biases.copy_(torch.as_tensor(w[name][1]))
-        for name in ("norm1_d", "norm2_d", "norm3_d", "norm3_f", "norm2_f"):
+        for name in ("norm1_d", "norm2_d", "norm3_d", "norm3_f", "norm2_f", "norm3_u", "norm2_u"):
+            if name not in w:
+                continue
             norm = getattr(self, name)
             norm.gamma.copy_(torch.as_tensor(w[name][0]))
             norm.beta.copy_(torch.as_tensor(w[name][1]))
         self.res.set_weights(w["res"])
+        if "sun" in w:
+            # sunRadNet: d1..d4 -> dict(kernel [4,4,C,F] (, gamma, beta, moving_mean, moving_variance)); gamma / beta -> (kernel [flat,1], bias [1])
+            for name in ("d1", "d2", "d3", "d4"):
+                d, src = getattr(self.sun, name), w["sun"][name]
+                for key, val in src.items():
+                    getattr(d, key).copy_(torch.as_tensor(val))
+            for head in ("gamma", "beta"):
+                getattr(self.sun, head + "_kernel").copy_(torch.as_tensor(w["sun"][head][0]))
+                getattr(self.sun, head + "_bias").copy_(torch.as_tensor(w["sun"][head][1]))

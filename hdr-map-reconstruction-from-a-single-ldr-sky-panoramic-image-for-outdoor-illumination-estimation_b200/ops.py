@@ -79,7 +79,22 @@ class _PlainConvCore:
             self._packed_key = key
         return self._packed
 
-    def _conv(self, x, leaky_slope=None, residual=None, relu=False, log_decompress=False, stats=None):
+    def backward_data(self, x, dy):
+        """Gradient of a stride-1, odd-k SAME conv w.r.t. its input: the distortion-aware data-gradient kernel with an all-zero
+        offset table (every tap lands on a grid point, so the bilinear scatter degenerates to the transposed conv)."""
+        if self.stride != 1 or self.k_h % 2 == 0:
+            raise NotImplementedError("data gradient is built for the stride-1 odd-kernel layers of sunpose_net.py")
+        x, dy = _require_cuda(x, "x"), _require_cuda(dy, "dy")
+        B, h, w, C = x.shape
+        k, F = self.k_h, self.output_channels
+        if self._zero_tab is None or self._zero_tab.shape[0] != h:
+            self._zero_tab = torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        check(LIB.sky_da_conv2d_bwd_data(dy.data_ptr(), self._zero_tab.data_ptr(), self._weight().data_ptr(), dx.data_ptr(),
+                                         B, h, w, C, F, k, 0, _stream()))
+        return dx
+
+    def _conv(self, x, leaky_slope=None, residual=None, relu=False, log_decompress=False, stats=None, blend=None):
         B, h, w, C = x.shape
         k, F, s = self.k_h, self.output_channels, self.stride
         if C != self._channels_in:
@@ -91,7 +106,16 @@ class _PlainConvCore:
         flags = _epilogue_flags(leaky_slope, residual, relu, log_decompress)
         slope = float(leaky_slope or 0.0)
         mode = _MATH[self.math_mode]
-        if (s == 1 and k % 2 == 1 and k <= 11 and C <= 4 and F <= 32 and residual is None and not relu and not log_decompress):
+        if blend is not None:
+            # conv1_u with the tail of inference.generator_in_step in its epilogue (sky_conv2d_fwd_blend)
+            sky_gamma, threshold = blend
+            sky_gamma = _require_cuda(sky_gamma, "sky_gamma")
+            if F != 3 or s != 1 or stats is not None or tuple(sky_gamma.shape) != (B, oh, ow, 3):
+                raise ValueError("blend epilogue: 3 filters, stride 1, sky prediction of the output's shape")
+            check(LIB.sky_conv2d_fwd_blend(x.data_ptr(), self._packed_weights().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
+                                           _ptr(residual), sky_gamma.data_ptr(), float(threshold), B, h, w, C, k, flags, slope,
+                                           mode, _stream()))
+        elif (s == 1 and k % 2 == 1 and k <= 11 and C <= 4 and F <= 32 and residual is None and not relu and not log_decompress):
             # image-like input (conv1_d): fp32 CUDA-core kernel, the unpacked variable is read directly
             check(LIB.sky_conv2d_smallc_fwd(x.data_ptr(), self._weight().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
                                             _ptr(stats), B, h, w, C, F, k, flags, slope, _stream()))

@@ -11,6 +11,7 @@ wired in as the commented lines generator.py:14,18 do:
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import da_oracle as O
@@ -196,3 +197,157 @@ def random_trunk_weights(n_blocks, C, k, seed, affine_noise=True):
             w[f"norm{i}_beta"] = torch.from_numpy((0.1 * rng.standard_normal(C) * affine_noise).astype(np.float32))
         blocks.append(w)
     return blocks
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sun branch of generator inference (inference.py:81-112)
+# ---------------------------------------------------------------------------------------------------------------------
+def hdr_log_compression(x, valid_dr=10.0):
+    """tf_utils.hdr_logCompression (tf_utils.py:263-271)."""
+    return torch.log(1.0 + valid_dr * x) / torch.log(torch.tensor(1.0 + valid_dr, dtype=x.dtype))
+
+
+def grad_cam_layer(y_c, A_k):
+    """grad_cam.layer (grad_cam.py:29-45): tf.gradients(y_c, A_k) sums y_c over the batch; the samples are independent."""
+    grad = torch.autograd.grad(y_c.sum(), A_k, retain_graph=True)[0]
+    weights = grad.mean(dim=(1, 2))                                       # :34
+    cam = torch.einsum('bc,bwhc->bwh', weights, A_k)                      # :35
+    return torch.relu(cam).unsqueeze(-1)                                  # :38-43
+
+
+def batch_norm_inference(x, gamma, beta, mean, var, eps=1e-3):
+    """Keras BatchNormalization with training=False: moving statistics, epsilon 1e-3."""
+    inv = gamma * torch.rsqrt(var + eps)
+    return x * inv + (beta - mean * inv)
+
+
+def sunrad_net(x, actv_map, w, eps=1e-5, acc_dtype=torch.float32, return_heads=False):
+    """sunRadNet.call (sunrad_net.py:46-71), inference mode.  w: d1..d4 -> dict(kernel [4,4,C,F] (, gamma, beta, moving_mean,
+    moving_variance)), gamma / beta -> (kernel [flat, 1], bias [1])."""
+    dt = acc_dtype
+    h = actv_map.to(dt)
+    for name, stride in (("d1", 2), ("d2", 2), ("d3", 2), ("d4", 1)):
+        d = w[name]
+        kern = O._as_t(d["kernel"]).to(dt)
+        h = conv2d_same(h, kern, torch.zeros(kern.shape[-1], dtype=dt), stride=stride, acc_dtype=dt)     # use_bias=False
+        if "gamma" in d:
+            h = batch_norm_inference(h, *(O._as_t(d[k]).to(dt) for k in ("gamma", "beta", "moving_mean", "moving_variance")))
+        h = leaky_relu(h, 0.3)                                              # Keras LeakyReLU() default alpha
+    flat = h.reshape(h.shape[0], -1)
+    gamma = flat @ O._as_t(w["gamma"][0]).to(dt) + O._as_t(w["gamma"][1]).to(dt)
+    beta = flat @ O._as_t(w["beta"][0]).to(dt) + O._as_t(w["beta"][1]).to(dt)
+    gamma_in = torch.sigmoid(gamma).reshape(-1, 1, 1, 1)
+    beta_in = torch.sigmoid(beta).reshape(-1, 1, 1, 1)
+    v = -((1.0 - x.to(dt)) ** 2.0)
+    v = v / (beta_in + eps)
+    v = torch.exp(v)
+    v = v * gamma_in
+    const = beta_in * torch.sqrt(torch.tensor(float(np.float32(np.pi)), dtype=dt))
+    v = v / (const + eps)
+    v = torch.where(v > 30000.0, torch.full_like(v, 30000.0), v)
+    return (v, gamma_in, beta_in) if return_heads else v
+
+
+def decode_branch(x, inp_add, w, names, dt):
+    """sky_decode / sun_decode (generator.py:110-156): two resize-deconv + IN + lrelu, 7x7 conv, lrelu, + addend, relu."""
+    c3, n3, c2, n2, c1 = names
+    H, W = inp_add.shape[1], inp_add.shape[2]
+
+    def norm_act(y, name):
+        g, b = (O._as_t(v).to(dt) for v in w[name])
+        return leaky_relu(instance_norm(y, g, b), 0.1)
+
+    x = O.resize_bilinear(x, H // 2, W // 2)
+    x = norm_act(conv2d_same(x, *w[c3], acc_dtype=dt), n3)
+    x = O.resize_bilinear(x, H, W)
+    x = norm_act(conv2d_same(x, *w[c2], acc_dtype=dt), n2)
+    y = leaky_relu(conv2d_same(x, *w[c1], acc_dtype=dt), 0.1)
+    return torch.relu(inp_add + y)
+
+
+def generator_inference(ldr, wg, ws, k=3, threshold=0.12, distortion_aware_sunpose=True, acc_dtype=torch.float32, details=False):
+    """inference.generator_in_step (inference.py:81-112).  wg: generator weights (random_generator_weights(..., sun=True)),
+    ws: sun-position weights (random_sunpose_weights)."""
+    import numpy as np
+    dt = acc_dtype
+    inp = O._as_t(ldr).to(dt)
+    B, H, W, _ = inp.shape
+
+    def norm_act(y, name):
+        g, b = (O._as_t(v).to(dt) for v in wg[name])
+        return leaky_relu(instance_norm(y, g, b), 0.1)
+
+    x = norm_act(conv2d_same(inp, *wg["conv1_d"], stride=1, acc_dtype=dt), "norm1_d")          # encode, :83
+    x = norm_act(conv2d_same(x, *wg["conv2_d"], stride=2, acc_dtype=dt), "norm2_d")
+    x = norm_act(conv2d_same(x, *wg["conv3_d"], stride=2, acc_dtype=dt), "norm3_d")
+    blocks = [{kk: O._as_t(v) for kk, v in blk.items()} for blk in wg["res"]]
+    res_out = res_layer(x, blocks, k, acc_dtype=dt)
+    sky_gamma = decode_branch(res_out, inp, wg, ("conv3_f", "norm3_f", "conv2_f", "norm2_f", "conv1_f"), dt)   # :84
+    sky_lin = hdr_log_decompression(sky_gamma)                                                 # :85
+
+    x_sun = inp.clone().requires_grad_(True)           # so that the activation maps are part of an autograd graph
+    sm, acts = sunpose_estimation(x_sun, ws, distortion_aware=distortion_aware_sunpose, acc_dtype=dt)   # :87
+    sunpose_pred = sm.reshape(B, H, W, 1)
+    alpha = sky_lin.amax(dim=3)                                                                # :91
+    alpha = torch.clamp((alpha - 1.0 + threshold).clamp(min=0.0) / threshold, max=1.0)         # :92
+    alpha_c3 = alpha.unsqueeze(-1).expand(B, H, W, 3)
+    y_c = sm.amax(dim=1)                                                                       # :98 (ties share the gradient, like TF)
+    cams = [grad_cam_layer(y_c, a).detach() for a in acts]                                     # :100-102
+    sm, sunpose_pred = sm.detach(), sunpose_pred.detach()
+    normed = sunpose_pred / sunpose_pred.max()                                                 # generator.py:160
+    r2 = O.resize_bilinear(cams[1], H, W)                                                      # :161-162
+    r3 = O.resize_bilinear(cams[2], H, W)
+    plz = torch.cat([inp, cams[0], r2, r3], dim=-1)                                            # :164
+    sun_rad = sunrad_net(normed, plz, wg["sun"], acc_dtype=dt)                                 # :165
+    sun_rad_lin = sun_rad.expand(B, H, W, 3)                                                   # :167
+    sun_rad_gamma = hdr_log_compression(sun_rad_lin)                                           # inference.py:105
+    sun_gamma = decode_branch(res_out, sun_rad_gamma, wg, ("conv3_u", "norm3_u", "conv2_u", "norm2_u", "conv1_u"), dt)   # :106
+    y_gamma = (1.0 - alpha_c3) * sky_gamma + alpha_c3 * sun_gamma                              # :108-110
+    y_lin = hdr_log_decompression(y_gamma)                                                     # :111
+    if details:
+        return dict(y_lin=y_lin, sky_gamma=sky_gamma, sm=sm, cams=cams, sun_rad_gamma=sun_rad_gamma, sun_gamma=sun_gamma,
+                    alpha=alpha, acts=[a.detach() for a in acts], plz=plz)
+    return y_lin
+
+
+def random_sunrad_weights(seed, H, W, bn_noise=True):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    w = {}
+    cin = 6
+    for name, f, norm in (("d1", 64, False), ("d2", 128, True), ("d3", 256, True), ("d4", 512, True)):
+        d = {"kernel": (0.02 * rng.standard_normal((4, 4, cin, f))).astype(np.float32)}
+        if norm:
+            d["gamma"] = (1 + 0.1 * rng.standard_normal(f) * bn_noise).astype(np.float32)
+            d["beta"] = (0.1 * rng.standard_normal(f) * bn_noise).astype(np.float32)
+            d["moving_mean"] = (0.01 * rng.standard_normal(f) * bn_noise).astype(np.float32)
+            d["moving_variance"] = (1 + 0.2 * rng.uniform(-1, 1, f) * bn_noise).astype(np.float32)
+        w[name] = d
+        cin = f
+    flat = (H // 8) * (W // 8) * 512
+    lim = (6.0 / (flat + 1)) ** 0.5
+    for head in ("gamma", "beta"):
+        w[head] = (rng.uniform(-lim, lim, (flat, 1)).astype(np.float32), (0.1 * rng.standard_normal(1) * bn_noise).astype(np.float32))
+    return w
+
+
+def random_full_generator_weights(seed, H, W, k=3, affine_noise=True):
+    """random_generator_weights plus the sun decoder (conv3_u, conv2_u, conv1_u, norms) and sunRadNet."""
+    import numpy as np
+    w = random_generator_weights(seed, k, affine_noise)
+    rng = np.random.default_rng(seed + 77)
+
+    def conv(name, kk, cin, cout):
+        lim = (6.0 / (kk * kk * cin + kk * kk * cout)) ** 0.5
+        w[name] = (rng.uniform(-lim, lim, (kk, kk, cin, cout)).astype(np.float32),
+                   (0.05 * rng.standard_normal(cout) * affine_noise).astype(np.float32))
+
+    def norm(name, c):
+        w[name] = ((1 + 0.1 * rng.standard_normal(c) * affine_noise).astype(np.float32),
+                   (0.1 * rng.standard_normal(c) * affine_noise).astype(np.float32))
+
+    conv("conv3_u", 3, 128, 64); norm("norm3_u", 64)
+    conv("conv2_u", 3, 64, 32); norm("norm2_u", 32)
+    conv("conv1_u", 7, 32, 3)
+    w["sun"] = random_sunrad_weights(seed + 99, H, W, affine_noise)
+    return w
