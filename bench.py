@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native distortion-aware convolution path.
 
-Workload (config.workload): BASELINE.json config 1, "generator inference, random-init weights, synthetic 32x128 LDR
-sky-dome panoramas, batch 32", restricted to the sky branch that is built so far (inference.py:84-86): encoder ->
-six res-blocks with the distortion-aware convolutions of generator.py:14,18 -> sky decoder -> hdr_logDecompression.
-The sun branch (sunpose_net, Grad-CAM, sunRadNet, sun_decode, blending) is not built yet.
-`--workload trunk` times the DA residual trunk alone.
+Workload (config.workload, default `inference`): BASELINE.json configs[0], "generator inference, random-init weights,
+synthetic 32x128 LDR sky-dome panoramas, batch 32" = inference.generator_in_step (inference.py:81-112): encoder -> six
+res-blocks with the distortion-aware convolutions of generator.py:14,18 -> sky decoder; sun-position network (distortion-aware
+wiring of sunpose_net.py:11,16) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun decoder -> alpha blend -> linear HDR.
+`--workload sky` times the sky branch alone (inference.py:84-86), `--workload trunk` the DA residual trunk alone,
+`--workload trunk_train` the data-parallel train step of the trunk.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU under torchrun)
     python bench.py --impl reference [--steps K] [--warmup W]      reference arm: the oracle's CPU restatement of the
@@ -31,6 +32,7 @@ sys.path.insert(0, ROOT)
 N_BLOCKS, C, K_SIZE = 6, 128, 3
 UNIT = "panoramas/s"
 METRICS = {"trunk_train": "panoramas/sec (32x128, data-parallel train step of the DA residual trunk: fwd + L2 loss + bwd + 1 NCCL all-reduce + RMSprop)",
+           "inference": "panoramas/sec (32x128, generator inference: inference.generator_in_step, sky + sun branch)",
            "sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
            "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)"}
 
@@ -58,6 +60,10 @@ def make_input(batch, h, w, seed):
 
 
 def workload_name(batch, H, W, workload="sky"):
+    if workload == "inference":
+        return (f"generator_inference (inference.py:81-112): LDR [{batch},{H},{W},3] -> encode + 6 DA resBlocks -> sky_decode; "
+                f"sunpose_net (DA convs, 2 Dense {H * W}) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun_decode -> alpha blend -> "
+                f"hdr_logDecompression; random-init weights, B={batch}/GPU")
     if workload == "trunk_train":
         return (f"res_trunk_train_step: 6 resBlocks with distortion-aware convs, forward + synthetic L2 objective + backward "
                 f"(IN/LeakyReLU bwd, DA dgrad/wgrad/dbias) + one all-reduce of the flat gradient buffer (7.1 MB) + fused Keras RMSprop, "
@@ -85,6 +91,47 @@ def make_generator_weights(seed=0):
         w[name] = (np.ones(c, np.float32), np.zeros(c, np.float32))
     w["res"] = make_weights(seed + 1)
     return w
+
+
+def make_inference_weights(H, W, seed=0):
+    """Full generator (sky + sun decoder + sunRadNet) and sun-position weights with the reference's initialiser distributions:
+    glorot_uniform kernels and zero biases, gamma 1 / beta 0 norms, N(0, 0.02) sunRadNet convs with fresh BatchNormalization."""
+    rng = np.random.default_rng(seed + 50)
+    wg = make_generator_weights(seed)
+
+    def conv(kk, cin, cout):
+        lim = (6.0 / (kk * kk * cin + kk * kk * cout)) ** 0.5
+        return (rng.uniform(-lim, lim, (kk, kk, cin, cout)).astype(np.float32), np.zeros(cout, np.float32))
+
+    wg["conv3_u"], wg["conv2_u"], wg["conv1_u"] = conv(3, 128, 64), conv(3, 64, 32), conv(7, 32, 3)
+    wg["norm3_u"], wg["norm2_u"] = (np.ones(64, np.float32), np.zeros(64, np.float32)), (np.ones(32, np.float32), np.zeros(32, np.float32))
+    sun, cin = {}, 6
+    for name, f, norm in (("d1", 64, False), ("d2", 128, True), ("d3", 256, True), ("d4", 512, True)):
+        d = {"kernel": (0.02 * rng.standard_normal((4, 4, cin, f))).astype(np.float32)}
+        if norm:
+            d.update(gamma=np.ones(f, np.float32), beta=np.zeros(f, np.float32), moving_mean=np.zeros(f, np.float32),
+                     moving_variance=np.ones(f, np.float32))
+        sun[name], cin = d, f
+    flat = (H // 8) * (W // 8) * 512
+    lim = (6.0 / (flat + 1)) ** 0.5
+    for head in ("gamma", "beta"):
+        sun[head] = (rng.uniform(-lim, lim, (flat, 1)).astype(np.float32), np.zeros(1, np.float32))
+    wg["sun"] = sun
+    ws, cin = {}, 3
+    for name, f, k in (("sunlayer1", 32, 7), ("sunlayer2", 64, 3), ("sunlayer3", 128, 3)):
+        d, c = {}, cin
+        for i in (1, 2):
+            lim = (6.0 / (k * k * c + f)) ** 0.5
+            d[f"conv{i}_kernel"] = rng.uniform(-lim, lim, (k * k * c, f)).astype(np.float32)
+            d[f"conv{i}_bias"] = np.zeros(f, np.float32)
+            d[f"norm{i}_gamma"], d[f"norm{i}_beta"] = np.ones(f, np.float32), np.zeros(f, np.float32)
+            c = f
+        ws[name], cin = d, f
+    fc = H * W
+    for name, kin in (("fc1", (H // 8) * (W // 8) * 128), ("fc2", fc)):
+        lim = (6.0 / (kin + fc)) ** 0.5
+        ws[name] = (rng.uniform(-lim, lim, (kin, fc)).astype(np.float32), np.zeros(fc, np.float32))
+    return wg, ws
 
 
 def make_ldr(batch, H, W, seed):
@@ -115,8 +162,11 @@ def oracle_step_fn(args, sample):
         blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
         x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
         return lambda: M.res_layer(x, blocks, K_SIZE)
-    w = make_generator_weights()
     ldr = make_ldr(sample, args.height, args.width, seed=1)
+    if args.workload == "inference":
+        wg, ws = make_inference_weights(args.height, args.width)
+        return lambda: M.generator_inference(ldr, wg, ws, K_SIZE)
+    w = make_generator_weights()
     return lambda: M.sky_branch(ldr, w, K_SIZE)
 
 
@@ -220,6 +270,16 @@ def run_ours(args):
         forward = trunk
         x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
         launches_per_step = 4 * N_BLOCKS         # per res-block: 2 conv + 2 instance-norm kernels (ours)
+    elif args.workload == "inference":
+        gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=args.math)
+        x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
+        sun.sunposeEstimation(x_host.cuda())          # builds the lazily created layers
+        wg, ws = make_inference_weights(H, W)
+        gen.set_weights(wg)
+        sun.set_weights(ws)
+        trunk = gen.res
+        forward = lambda inp: pkg.inference.generator_in_step(gen, sun, inp)
+        launches_per_step = None                      # counted from the entry points one step calls (see below)
     else:
         gen = pkg.model(batch_size=B, im_height=H, im_width=W, da_kernel_size=K_SIZE, math_mode=args.math)
         gen.build(B)
@@ -231,6 +291,14 @@ def run_ours(args):
         launches_per_step = 6 + 4 * N_BLOCKS + 7
     x = x_host.cuda()
     y_host = torch.empty_like(forward(x).cpu()).pin_memory()
+    # kernel launches of one step, from the C-ABI entry points it calls (weights are packed / transposed by now)
+    pkg._lib.LIB.counts = {}
+    forward(x)
+    counted = pkg._lib.LIB.launches()
+    abi_calls = dict(pkg._lib.LIB.counts)
+    pkg._lib.LIB.counts = None
+    if launches_per_step is None:
+        launches_per_step = counted
     if world > 1 and trainer is not None:
         trainer.flat_w.copy_(trainer.flat_w)     # replicas start from identical weights (same numpy seed on every rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
@@ -337,7 +405,7 @@ def run_ours(args):
                        "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": round(t_e2e, 4)},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps, "abi_calls_per_step": abi_calls,
             "roofline": {"kernel": "da_conv2d_fwd_band_kernel (128->128, k=3, M=%d)" % (B * h * w), "bound": "tensor",
                          "achieved": round(achieved, 2), "peak": round(bf16_peak / 2, 1), "unit": "TFLOP/s",
                          "frac": round(achieved / (bf16_peak / 2), 4), "traffic": traffic,
@@ -380,8 +448,8 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
-    ap.add_argument("--workload", default="sky", choices=["sky", "trunk", "trunk_train"],
-                    help="sky: generator inference, sky branch (default); trunk: the DA residual trunk alone")
+    ap.add_argument("--workload", default="inference", choices=["inference", "sky", "trunk", "trunk_train"],
+                    help="inference: full generator inference (default); sky: its sky branch; trunk: the DA residual trunk alone")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

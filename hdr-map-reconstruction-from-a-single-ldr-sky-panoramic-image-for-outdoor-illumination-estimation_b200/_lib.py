@@ -27,6 +27,7 @@ SIGNATURES = {
     "sky_da_conv2d_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "sky_conv2d_fwd": (_i, [_vp] * 6 + [_i] * 8 + [_f, _i, _vp]),
     "sky_conv2d_smallc_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_f, _vp]),
+    "sky_da_conv2d_smallc_fwd": (_i, [_vp] * 7 + [_i] * 7 + [_f, _vp]),
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
@@ -70,7 +71,36 @@ def load():
     return lib
 
 
-LIB = load()
+# kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
+# makes.  Entry points not listed launch one kernel.
+LAUNCHES_PER_CALL = {"sky_dense_fwd": 2, "sky_dense_bwd_data": 2, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
+                     "sky_da_offsets_host": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
+                     "sky_debug_band_trace": 0}
+
+
+class _Lib:
+    """Attribute access to the C ABI with an optional per-entry-point call counter (`counts`: dict or None)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.counts = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+
+        def call(*args):
+            if self.counts is not None:
+                self.counts[name] = self.counts.get(name, 0) + 1
+            return fn(*args)
+        call.__name__ = name
+        setattr(self, name, call)       # resolved once; later lookups bypass __getattr__
+        return call
+
+    def launches(self):
+        return sum(n * LAUNCHES_PER_CALL.get(k, 1) for k, n in (self.counts or {}).items())
+
+
+LIB = _Lib(load())
 
 
 def check(rc):

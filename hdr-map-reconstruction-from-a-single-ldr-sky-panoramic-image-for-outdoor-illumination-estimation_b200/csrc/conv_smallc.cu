@@ -4,58 +4,19 @@
 // the input patch (k rows x (128 + k - 1) pixels) and the whole kernel variable are staged in shared memory, fp32 FMA
 // in the reference's (tap, c) order.  Epilogue: bias, optional LeakyReLU, coalesced stores, per-(sample, filter)
 // moments for the instance norm that follows.
-#include "sky_common.cuh"
+#include "da_conv.cuh"
 
 namespace sky {
 
 constexpr int SC_THREADS = 128;   // pixels per block (one row segment)
 constexpr int SC_FMAX = 32;
 
-template <int C>
-__global__ void __launch_bounds__(SC_THREADS)
-conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kernel, const float *__restrict__ bias,
-                     float *__restrict__ y, double *__restrict__ stats, int h, int w, int F, int k, int flags, float slope)
+// bias, optional LeakyReLU, coalesced stores, per-(sample, filter) moments for the instance norm that follows
+__device__ __forceinline__ void smallc_epilogue(float (&acc)[SC_FMAX], const float *__restrict__ bias, float *__restrict__ y,
+                                                double *__restrict__ stats, float *red, int b, int i, int j, int h, int w, int F,
+                                                int flags, float slope)
 {
-    extern __shared__ float sm[];
-    const int r = k / 2, pw = SC_THREADS + k - 1;
-    float *wts = sm;                          // [k*k*C][SC_FMAX]
-    float *patch = sm + k * k * C * SC_FMAX;  // [k][pw][C]
-    float *red = patch + k * pw * C;          // [4 warps][SC_FMAX][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * SC_THREADS, i = blockIdx.y, b = blockIdx.z;
-
-    for (int e = tid; e < k * k * C * SC_FMAX; e += SC_THREADS) {
-        const int f = e % SC_FMAX, row = e / SC_FMAX;
-        wts[e] = f < F ? kernel[(size_t)row * F + f] : 0.f;
-    }
-    for (int e = tid; e < k * pw * C; e += SC_THREADS) {
-        const int c = e % C, px = (e / C) % pw, a = e / (C * pw);
-        const int yy = i + a - r, xx = x0 + px - r;
-        patch[e] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? x[(((size_t)b * h + yy) * w + xx) * C + c] : 0.f;
-    }
-    __syncthreads();
-
-    float acc[SC_FMAX];
-#pragma unroll
-    for (int f = 0; f < SC_FMAX; ++f) acc[f] = 0.f;
-    for (int a = 0; a < k; ++a)
-        for (int bb = 0; bb < k; ++bb) {
-            const float *pv = patch + (a * pw + tid + bb) * C;
-            const float4 *wrow = reinterpret_cast<const float4 *>(wts + (a * k + bb) * C * SC_FMAX);
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float v = pv[c];
-#pragma unroll
-                for (int f4 = 0; f4 < SC_FMAX / 4; ++f4) {
-                    const float4 wv = wrow[c * (SC_FMAX / 4) + f4];
-                    acc[4 * f4 + 0] = fmaf(v, wv.x, acc[4 * f4 + 0]);
-                    acc[4 * f4 + 1] = fmaf(v, wv.y, acc[4 * f4 + 1]);
-                    acc[4 * f4 + 2] = fmaf(v, wv.z, acc[4 * f4 + 2]);
-                    acc[4 * f4 + 3] = fmaf(v, wv.w, acc[4 * f4 + 3]);
-                }
-            }
-        }
-    const int j = x0 + tid;
     const bool ok = j < w;
 #pragma unroll
     for (int f = 0; f < SC_FMAX; ++f) {
@@ -96,6 +57,161 @@ conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kern
     }
 }
 
+template <int C>
+__global__ void __launch_bounds__(SC_THREADS)
+conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kernel, const float *__restrict__ bias,
+                     float *__restrict__ y, double *__restrict__ stats, int h, int w, int F, int k, int flags, float slope)
+{
+    extern __shared__ float sm[];
+    const int r = k / 2, pw = SC_THREADS + k - 1;
+    float *wts = sm;                          // [k*k*C][SC_FMAX]
+    float *patch = sm + k * k * C * SC_FMAX;  // [k][pw][C]
+    float *red = patch + k * pw * C;          // [4 warps][SC_FMAX][2]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * SC_THREADS, i = blockIdx.y, b = blockIdx.z;
+
+    for (int e = tid; e < k * k * C * SC_FMAX; e += SC_THREADS) {
+        const int f = e % SC_FMAX, row = e / SC_FMAX;
+        wts[e] = f < F ? kernel[(size_t)row * F + f] : 0.f;
+    }
+    for (int e = tid; e < k * pw * C; e += SC_THREADS) {
+        const int c = e % C, px = (e / C) % pw, a = e / (C * pw);
+        const int yy = i + a - r, xx = x0 + px - r;
+        patch[e] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? x[(((size_t)b * h + yy) * w + xx) * C + c] : 0.f;
+    }
+    __syncthreads();
+
+    float acc[SC_FMAX];
+#pragma unroll
+    for (int f = 0; f < SC_FMAX; ++f) acc[f] = 0.f;
+    for (int a = 0; a < k; ++a)
+        for (int bb = 0; bb < k; ++bb) {
+            const float *pv = patch + (a * pw + tid + bb) * C;
+            const float4 *wrow = reinterpret_cast<const float4 *>(wts + (a * k + bb) * C * SC_FMAX);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float v = pv[c];
+#pragma unroll
+                for (int f4 = 0; f4 < SC_FMAX / 4; ++f4) {
+                    const float4 wv = wrow[c * (SC_FMAX / 4) + f4];
+                    acc[4 * f4 + 0] = fmaf(v, wv.x, acc[4 * f4 + 0]);
+                    acc[4 * f4 + 1] = fmaf(v, wv.y, acc[4 * f4 + 1]);
+                    acc[4 * f4 + 2] = fmaf(v, wv.z, acc[4 * f4 + 2]);
+                    acc[4 * f4 + 3] = fmaf(v, wv.w, acc[4 * f4 + 3]);
+                }
+            }
+        }
+    smallc_epilogue(acc, bias, y, stats, red, b, i, x0 + tid, h, w, F, flags, slope);
+}
+
+
+// The distortion-aware layer on an image-like input (sunlayer1.conv1 with the wiring of sunpose_net.py:11: 7x7, 3 -> 32 on the LDR
+// panorama).  Same structure as above, but every (pixel, tap) is sampled with the reference geometry (da_sample) and blended from
+// four corners.  The rows [i + hy_lo, i + hy_hi] (halo from the offset table) are staged at FULL width, so the 360-degree wrap
+// stays inside the staged rows; corners in other rows (zenith-row taps on tall maps) are read from global memory.
+template <int C>
+__global__ void __launch_bounds__(SC_THREADS)
+da_conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ offsets, const float *__restrict__ kernel,
+                        const float *__restrict__ bias, float *__restrict__ y, double *__restrict__ stats, int h, int w, int F, int k,
+                        int hy_lo, int nrows, int in_h, int in_w, int ph0, int pw0, int flags, float slope)
+{
+    extern __shared__ float sm[];
+    const int k2 = k * k;
+    float *wts = sm;                           // [k*k*C][SC_FMAX]
+    float2 *offs = reinterpret_cast<float2 *>(sm + k2 * C * SC_FMAX);   // [k2] (y, x) offsets of this output row
+    float *rows = sm + k2 * C * SC_FMAX + 2 * k2;   // [nrows][w][C]
+    float *red = rows + nrows * w * C;              // [4 warps][SC_FMAX][2]
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * SC_THREADS, i = blockIdx.y, b = blockIdx.z;
+    const int r0 = i + hy_lo;                  // first staged input row (may be negative: zero halo)
+
+    for (int e = tid; e < k2 * C * SC_FMAX; e += SC_THREADS) {
+        const int f = e % SC_FMAX, row = e / SC_FMAX;
+        wts[e] = f < F ? kernel[(size_t)row * F + f] : 0.f;
+    }
+    for (int e = tid; e < nrows * w * C; e += SC_THREADS) {
+        const int yy = r0 + e / (w * C);
+        rows[e] = (yy >= 0 && yy < h) ? x[((size_t)b * h + yy) * w * C + e % (w * C)] : 0.f;
+    }
+    for (int t = tid; t < k2; t += SC_THREADS) offs[t] = reinterpret_cast<const float2 *>(offsets)[(size_t)i * k2 + t];
+    __syncthreads();
+
+    const int j = x0 + tid;
+    float acc[SC_FMAX];
+#pragma unroll
+    for (int f = 0; f < SC_FMAX; ++f) acc[f] = 0.f;
+    if (j < w) {
+        const float *img = x + (size_t)b * h * w * C;
+        for (int t = 0; t < k2; ++t) {
+            const float2 o = offs[t];
+            const Sample s = da_sample(i, j, t / k, t % k, o.x, o.y, in_h, in_w);
+            const int ys[4] = { s.y0 - ph0, s.y0 - ph0, s.y1 - ph0, s.y1 - ph0 };
+            const int xs[4] = { s.x0 - pw0, s.x1 - pw0, s.x0 - pw0, s.x1 - pw0 };
+            const float wq[4] = { s.w0, s.w1, s.w2, s.w3 };
+            float pix[C];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool inside = ys[q] >= 0 && ys[q] < h && xs[q] >= 0 && xs[q] < w;     // else: zero halo (:125-150)
+                const int rr = ys[q] - r0;
+                const float *src = (rr >= 0 && rr < nrows) ? rows + (rr * w + xs[q]) * C : img + ((size_t)ys[q] * w + xs[q]) * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float px = inside ? src[c] : 0.f;
+                    pix[c] = (q == 0) ? __fmul_rn(wq[0], px) : __fadd_rn(pix[c], __fmul_rn(wq[q], px));   // add_n order (:112-113)
+                }
+            }
+            const float4 *wrow = reinterpret_cast<const float4 *>(wts + t * C * SC_FMAX);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int f4 = 0; f4 < SC_FMAX / 4; ++f4) {
+                    const float4 wv = wrow[c * (SC_FMAX / 4) + f4];
+                    acc[4 * f4 + 0] = fmaf(pix[c], wv.x, acc[4 * f4 + 0]);
+                    acc[4 * f4 + 1] = fmaf(pix[c], wv.y, acc[4 * f4 + 1]);
+                    acc[4 * f4 + 2] = fmaf(pix[c], wv.z, acc[4 * f4 + 2]);
+                    acc[4 * f4 + 3] = fmaf(pix[c], wv.w, acc[4 * f4 + 3]);
+                }
+            }
+        }
+    }
+    smallc_epilogue(acc, bias, y, stats, red, b, i, j, h, w, F, flags, slope);
+}
+
+static int launch_fwd_smallc_da(const FwdArgs &a, const float *kernel)
+{
+    if (a.C > 4 || a.F > SC_FMAX || a.k > 11 || a.offsets_host == nullptr || (a.flags & ~SKY_EPI_LEAKY_RELU) ||
+        (a.F == SC_FMAX && ((uintptr_t)a.y & 15) != 0))
+        return SKY_ERR_UNSUPPORTED;
+    int hy_lo, hy_hi, hx_lo, hx_hi, ph0, pht, pw0, pwt;
+    compute_halo(a.offsets_host, a.h, a.w, a.k, &hy_lo, &hy_hi, &hx_lo, &hx_hi);
+    pad_axis(a.h, a.k, &ph0, &pht);
+    pad_axis(a.w, a.k, &pw0, &pwt);
+    const int nrows = hy_hi - hy_lo + 1;
+    const size_t smem = ((size_t)a.k * a.k * a.C * SC_FMAX + (size_t)nrows * a.w * a.C + 4 * SC_FMAX * 2 + 2 * a.k * a.k) * sizeof(float);
+    if (smem > 200 * 1024) return SKY_ERR_UNSUPPORTED;
+    dim3 grid((a.w + SC_THREADS - 1) / SC_THREADS, a.h, a.B);
+#define SKY_LAUNCH_SCDA(CC)                                                                                                   \
+    do {                                                                                                                      \
+        static bool configured = false;                                                                                       \
+        if (!configured) {                                                                                                    \
+            SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_smallc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+            configured = true;                                                                                                \
+        }                                                                                                                     \
+        da_conv2d_smallc_kernel<CC><<<grid, SC_THREADS, smem, a.stream>>>(a.x, a.offsets, kernel, a.bias, a.y, a.stats, a.h, \
+                                                                          a.w, a.F, a.k, hy_lo, nrows, a.h + pht, a.w + pwt, ph0, pw0,   \
+                                                                          a.flags, a.slope);                                            \
+    } while (0)
+    switch (a.C) {
+        case 1: SKY_LAUNCH_SCDA(1); break;
+        case 2: SKY_LAUNCH_SCDA(2); break;
+        case 3: SKY_LAUNCH_SCDA(3); break;
+        default: SKY_LAUNCH_SCDA(4); break;
+    }
+#undef SKY_LAUNCH_SCDA
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
 }  // namespace sky
 
 using namespace sky;
@@ -131,4 +247,23 @@ extern "C" int sky_conv2d_smallc_fwd(const float *x, const float *kernel, const 
 #undef SKY_LAUNCH_SC
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
+}
+
+extern "C" int sky_da_conv2d_smallc_fwd(const float *x, const float *offsets, const float *offsets_host, const float *kernel,
+                                        const float *bias, float *y, double *stats, int B, int h, int w, int C, int F, int k,
+                                        int epilogue_flags, float slope, void *stream)
+{
+    SKY_REQUIRE(x && offsets && offsets_host && kernel && bias && y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(B > 0 && h > 0 && w > 0, SKY_ERR_INVALID, "non-positive dimension");
+    SKY_REQUIRE(k % 2 == 1, SKY_ERR_EVEN_KERNEL, "kernel_size must be odd number, current kernel size : %d", k);
+    SKY_REQUIRE(C >= 1 && C <= 4 && F >= 1 && F <= SC_FMAX && k >= 3 && k <= 11, SKY_ERR_UNSUPPORTED,
+                "small-C distortion-aware conv covers C <= 4, F <= 32, odd k in 3..11 (got C=%d F=%d k=%d)", C, F, k);
+    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_LEAKY_RELU)), SKY_ERR_UNSUPPORTED, "small-C conv supports only the LeakyReLU epilogue");
+    FwdArgs a;
+    a.x = x; a.offsets = offsets; a.offsets_host = offsets_host; a.packed = nullptr; a.bias = bias; a.residual = nullptr; a.y = y;
+    a.stats = stats; a.B = B; a.h = h; a.w = w; a.C = C; a.F = F; a.k = k; a.flags = epilogue_flags; a.slope = slope;
+    a.math_mode = 0; a.plain_stride = 0; a.stream = (cudaStream_t)stream;
+    int rc = launch_fwd_smallc_da(a, kernel);
+    SKY_REQUIRE(rc != SKY_ERR_UNSUPPORTED, rc, "small-C distortion-aware conv: panorama too wide for the staged rows (w=%d)", w);
+    return rc;
 }

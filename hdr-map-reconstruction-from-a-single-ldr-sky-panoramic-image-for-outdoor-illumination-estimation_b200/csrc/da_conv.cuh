@@ -23,6 +23,7 @@ struct FwdArgs {
     float *y;
     double *stats;              // [B][F][2] running (sum, sum of squares) of y per sample and filter, or NULL
     int B, h, w, C, F, k;
+    int nslices = 0;            // > 0: this launch covers nslices equal slices of F filters each (blockIdx.z), ldF = nslices * F
     int ldF = 0;                // filters of the whole layer when this launch covers a slice of them (0: == F); y, residual,
                                 // stats are pre-offset to the slice and strided by ldF
     int flags;
@@ -52,6 +53,8 @@ __device__ __forceinline__ void sun_blend3(float v[3], const float *__restrict__
 
 // direct-gather kernel (any C): corners read straight from global/L2
 int launch_fwd_direct(const FwdArgs &a);
+// halo of input pixels (relative to an output pixel) the taps of a distortion-aware layer touch (da_conv_fwd_band.cu)
+void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi);
 // band-staged persistent kernel (C % 32 == 0): input band in shared memory via TMA.  Returns SKY_ERR_UNSUPPORTED
 // (without setting the error text) when no tiling fits, so the caller can take the direct kernel.
 int launch_fwd_band(const FwdArgs &a);

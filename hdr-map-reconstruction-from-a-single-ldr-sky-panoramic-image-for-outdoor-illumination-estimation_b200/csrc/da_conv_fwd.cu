@@ -63,6 +63,9 @@ struct FwdParams {
     float *y;
     double *stats;
     int B, h, w, C, F, Fp, k, k2, K, KB;
+    int kb_per_split;       // split-K: k-blocks per blockIdx.y slice (KB when not split); split launches add raw partial sums into y
+    int nslices;            // filter slices in blockIdx.z (each F filters, packed images / bias / y columns slice_* apart)
+    size_t slice_packed_bytes;
     int ldF;                // row stride of y / residual / stats (filters of the whole layer; == F unless the launch is a filter slice)
     int in_h, in_w, ph0, pw0;
     int M;                  // B*oh*ow
@@ -156,6 +159,10 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * BLOCK_M;
+    const int kb_lo = blockIdx.y * p.kb_per_split, kb_hi = min(p.KB, kb_lo + p.kb_per_split);   // this CTA's k-blocks
+    const bool split = p.kb_per_split < p.KB;
+    const int f_slice = blockIdx.z * p.F;                                                            // first filter of this slice
+    const uint8_t *packed = reinterpret_cast<const uint8_t *>(p.packed) + (size_t)blockIdx.z * p.slice_packed_bytes;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < p.Fp) tmem_cols <<= 1;
 
@@ -181,14 +188,15 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
         const bool fast = (p.C % BLOCK_K) == 0;
         const int chunk = tid & 7;            // 16-byte chunk inside the 128-byte row
         const int row_base = tid >> 3;        // rows row_base + 16*i
-        int kb = 0;
+        int kb = kb_lo;
         if (fast) {
             const int cpt = p.C / BLOCK_K;    // k-blocks per tap
             // this thread's own pixel (row = tid) for the per-tap coordinate table
             const int m = m0 + tid;
             const bool m_ok = m < p.M;
             const int j = m % p.ow, i = (m / p.ow) % p.oh, b_img = m / (p.ow * p.oh);
-            for (int kk = 0; kk < cpt * p.k2; ++kk) {     // chunk-major k-block order (matches the packed weights)
+            (void)cpt;
+            for (int kk = kb_lo; kk < kb_hi; ++kk) {      // chunk-major k-block order (matches the packed weights)
                 const int cc = kk / p.k2, t = kk % p.k2;
                 CornerRef cr;
                 if (m_ok) {
@@ -201,8 +209,8 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                 tab[tid] = cr;
                 named_bar_sync(1, NUM_PRODUCER_THREADS);
                 {
-                    const int s = kb % STAGES;
-                    mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                    const int s = (kb - kb_lo) % STAGES;
+                    mbar_wait(empty0 + 8 * s, (((kb - kb_lo) / STAGES) & 1) ^ 1);
                     uint8_t *a_tile = smem + s * stage_bytes;
                     const int ch = cc * BLOCK_K + chunk * 4;
 #pragma unroll 4
@@ -226,12 +234,12 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                 const int m = m0 + row_base + 16 * r;
                 pj[r] = m % p.ow; pi[r] = (m / p.ow) % p.oh; pb[r] = m < p.M ? m / (p.ow * p.oh) : -1;
             }
-            for (; kb < p.KB; ++kb) {
-                const int s = kb % STAGES;
+            for (; kb < kb_hi; ++kb) {
+                const int s = (kb - kb_lo) % STAGES;
                 const int kidx = kb * BLOCK_K + chunk * 4;
                 const bool k_ok = kidx < p.K;
                 const int t = k_ok ? kidx / p.C : 0, c = kidx % p.C;
-                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+                mbar_wait(empty0 + 8 * s, (((kb - kb_lo) / STAGES) & 1) ^ 1);
                 uint8_t *a_tile = smem + s * stage_bytes;
 #pragma unroll
                 for (int r = 0; r < BLOCK_M / 16; ++r) {
@@ -245,9 +253,9 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
             }
         } else {
             // generic channel counts (3-channel image layers, C not a multiple of 4): geometry per element
-            for (; kb < p.KB; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+            for (; kb < kb_hi; ++kb) {
+                const int s = (kb - kb_lo) % STAGES;
+                mbar_wait(empty0 + 8 * s, (((kb - kb_lo) / STAGES) & 1) ^ 1);
                 uint8_t *a_tile = smem + s * stage_bytes;
                 for (int r = 0; r < BLOCK_M / 16; ++r) {
                     const int row = row_base + 16 * r;
@@ -289,16 +297,31 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
             uint32_t r[16];
             tmem_ld_32x16(taddr_row + (uint32_t)c0, r);
             tmem_ld_wait();
-            if (m < p.M) {
+            if (m < p.M && split) {
+                // split-K: add this CTA's partial sums to y (zeroed by the launcher); bias / activation are applied by
+                // conv_finalize_kernel once every split has landed
+                float *dst = p.y + (size_t)m * p.ldF + f_slice + c0;
+                if (vec_ok && c0 + 16 <= p.F) {
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(__uint_as_float(r[q])),
+                                     "f"(__uint_as_float(r[q + 1])), "f"(__uint_as_float(r[q + 2])), "f"(__uint_as_float(r[q + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (c0 + q < p.F) atomicAdd(dst + q, __uint_as_float(r[q]));
+                }
+            } else if (m < p.M) {
                 float o[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     const int f = c0 + q;
                     float val = __uint_as_float(r[q]);
                     if (f < p.F) {
-                        val += __ldg(p.bias + f);
+                        val += __ldg(p.bias + f_slice + f);
                         if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
-                        if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.ldF + f);
+                        if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.ldF + f_slice + f);
                         if (p.flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
                     }
                     o[q] = val;
@@ -310,13 +333,13 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     if (f < p.F) {
                         if (p.flags & SKY_EPI_LOG_DECOMPRESS) o[q] = (expf(o[q] * 2.3978953f) - 1.f) / 10.f;   // log(11) as fp32
                         if (p.stats) {   // generic path: plain atomics (the band-staged kernel reduces per tile first)
-                            double *st = p.stats + ((size_t)(m / (p.oh * p.ow)) * p.ldF + f) * 2;
+                            double *st = p.stats + ((size_t)(m / (p.oh * p.ow)) * p.ldF + f_slice + f) * 2;
                             atomicAdd(st, (double)o[q]);
                             atomicAdd(st + 1, (double)o[q] * (double)o[q]);
                         }
                     }
                 }
-                float *dst = p.y + (size_t)m * p.ldF + c0;
+                float *dst = p.y + (size_t)m * p.ldF + f_slice + c0;
                 if (vec_ok && c0 + 16 <= p.F) {
 #pragma unroll
                     for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(dst + q) = make_float4(o[q], o[q + 1], o[q + 2], o[q + 3]);
@@ -332,9 +355,9 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
         // =========================== MMA ISSUER (one elected lane) ===========================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BLOCK_M, (uint32_t)p.Fp);
-            for (int kb = 0; kb < p.KB; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                const int s = (kb - kb_lo) % STAGES;
+                mbar_wait(full0 + 8 * s, ((kb - kb_lo) / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
                 const uint32_t b_hi = a_hi + L::PLANES * L::A_BYTES;
@@ -343,7 +366,7 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     const uint32_t koff = ks * UMMA_K * 4;
                     const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
                     const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
-                    umma_tf32(tmem_base, da, db, idesc, (kb | ks) != 0);
+                    umma_tf32(tmem_base, da, db, idesc, ((kb - kb_lo) | ks) != 0);
                     if (SPLIT3) {
                         const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff);
                         const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + b_bytes + koff);
@@ -360,12 +383,12 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
         // =========================== WEIGHT LOADER (one elected lane, bulk async copies) ===========================
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(L::PLANES * b_bytes);
-            for (int kb = 0; kb < p.KB; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+            for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                const int s = (kb - kb_lo) % STAGES;
+                mbar_wait(empty0 + 8 * s, (((kb - kb_lo) / STAGES) & 1) ^ 1);
                 const uint32_t dst = smem_u32(smem + s * stage_bytes + L::PLANES * L::A_BYTES);
                 mbar_arrive_expect_tx(full0 + 8 * s, bytes);
-                bulk_g2s(dst, reinterpret_cast<const uint8_t *>(p.packed) + (size_t)kb * bytes, bytes, full0 + 8 * s);
+                bulk_g2s(dst, packed + (size_t)kb * bytes, bytes, full0 + 8 * s);
             }
         }
         __syncwarp();
@@ -455,6 +478,21 @@ __global__ void resize_bilinear_kernel(const float *__restrict__ x, float *__res
     }
 }
 
+// y = act(y + bias) after a split-K launch (flags: SKY_EPI_LEAKY_RELU only)
+__global__ void conv_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total4, int F4, int flags, float slope)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4; e += (long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<float4 *>(y)[e];
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(e % F4));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (flags & SKY_EPI_LEAKY_RELU) {
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+        }
+        reinterpret_cast<float4 *>(y)[e] = v;
+    }
+}
+
 static int check_conv_args(int B, int h, int w, int C, int F, int k)
 {
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension (B=%d h=%d w=%d C=%d F=%d)", B, h, w, C, F);
@@ -475,9 +513,18 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
         configured = 227 * 1024;
     }
     SKY_REQUIRE(smem <= 227 * 1024, SKY_ERR_UNSUPPORTED, "shared memory %d B exceeds 227 KB (F=%d)", smem, p.F);
-    const int grid = (p.M + BLOCK_M - 1) / BLOCK_M;
-    da_conv2d_fwd_tc_kernel<STAGES, SPLIT3><<<grid, NUM_THREADS, smem, st>>>(p);
+    const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int ksplit = (p.KB + p.kb_per_split - 1) / p.kb_per_split;
+    if (ksplit > 1) SKY_CHECK_CUDA(cudaMemsetAsync(p.y, 0, (size_t)p.M * p.ldF * sizeof(float), st));
+    da_conv2d_fwd_tc_kernel<STAGES, SPLIT3><<<dim3(tiles, ksplit, p.nslices), NUM_THREADS, smem, st>>>(p);
     SKY_CHECK_CUDA(cudaGetLastError());
+    if (ksplit > 1) {
+        const long total4 = (long)p.M * p.ldF / 4;
+        int blocks = (int)((total4 + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        conv_finalize_kernel<<<blocks, 256, 0, st>>>(p.y, p.bias, total4, p.ldF / 4, p.flags, p.slope);
+        SKY_CHECK_CUDA(cudaGetLastError());
+    }
     return SKY_OK;
 }
 
@@ -545,6 +592,20 @@ int sky::launch_fwd_direct(const FwdArgs &a)
     }
     p.M = a.B * p.oh * p.ow;
     p.flags = a.flags; p.slope = a.slope;
+    p.nslices = a.nslices > 0 ? a.nslices : 1;
+    p.slice_packed_bytes = slice_bytes(a.C, a.F, a.k, a.math_mode);
+    p.kb_per_split = p.KB;
+    {
+        // Few output tiles and a long K (sunRadNet d3 / d4: 16 tiles, 64 / 128 k-blocks): split K over blockIdx.y so the SMs are
+        // used; the partial sums meet in y through vector reductions and conv_finalize_kernel applies bias + LeakyReLU.
+        const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M * p.nslices;
+        const bool simple_epilogue = !(a.flags & ~(SKY_EPI_LEAKY_RELU | SKY_EPI_FORCE_DIRECT)) && a.stats == nullptr;
+        if (simple_epilogue && tiles * 2 <= 148 && p.KB >= 16 && (p.ldF % 4) == 0 && (a.F % 4) == 0 && (a.ldF == 0 || a.nslices > 0)) {
+            int ksplit = 148 / tiles;
+            if (ksplit > p.KB / 4) ksplit = p.KB / 4;
+            if (ksplit > 1) p.kb_per_split = (p.KB + ksplit - 1) / ksplit;
+        }
+    }
     if (a.math_mode == SKY_MATH_TF32) {
         // 3 stages of 16 KB + Fp*128 B keep two CTAs resident per SM for F <= 128
         return p.Fp <= 128 ? launch_fwd<3, false>(p, a.stream) : launch_fwd<4, false>(p, a.stream);
@@ -596,6 +657,11 @@ static int conv2d_plain(FwdArgs a, int stride)
             if (rc != SKY_ERR_UNSUPPORTED) return rc;
         }
         return launch_fwd_direct(a);
+    }
+    if (F % 256 == 0) {          // equal slices: one launch, slices in blockIdx.z
+        FwdArgs b = a;
+        b.F = 256; b.ldF = F; b.nslices = F / 256;
+        return launch_fwd_direct(b);
     }
     const uint8_t *packed = (const uint8_t *)a.packed;
     for (int s = 0; s < slice_count(F); ++s) {

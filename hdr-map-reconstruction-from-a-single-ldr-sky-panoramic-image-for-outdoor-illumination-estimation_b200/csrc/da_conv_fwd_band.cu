@@ -309,18 +309,23 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                 mbar_wait_sleep(rt_empty0 + 8 * tb, ((git >> 1) & 1) ^ 1);
                 uint32_t *ti = rt_i + tb * tab_n + grun;
                 float4 *tw = rt_w + tb * tab_n + grun;
-                // 3x3 layers: fetch the row's nine offsets up front (independent loads) instead of one dependent
-                // global round trip per tap — this is on the critical path of a CTA's first tile
-                float2 pre[9];
-                const bool prefetched = (p.k2 == 9) && !p.plain;
-                if (prefetched) {
+                // The row's offsets are fetched nine taps at a time (independent loads) instead of one dependent global round
+                // trip per tap — this is on the critical path of a CTA's first tile, and for 7x7 layers (49 taps) the dependent
+                // loads alone cost more than the tile's tensor work.
+                const uint32_t inv_k = (65536u + (uint32_t)p.k - 1u) / (uint32_t)p.k;      // t / k == (t * inv_k) >> 16 for t < 225, k <= 15
+                for (int t0 = 0; t0 < p.k2; t0 += 9) {
+                    float2 pre[9];
+                    if (!p.plain) {
 #pragma unroll
-                    for (int q = 0; q < 9; ++q)
-                        pre[q] = pix_ok ? __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * 9 + q) : make_float2(0.f, 0.f);
-                }
-                int t = 0;
-                for (int a = 0; a < p.k; ++a)
-                    for (int b = 0; b < p.k; ++b, ++t) {
+                        for (int q = 0; q < 9; ++q)
+                            pre[q] = (pix_ok && t0 + q < p.k2) ? __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t0 + q)
+                                                              : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int t = t0 + q;
+                        if (t >= p.k2) break;
+                        const int a = (int)(((uint32_t)t * inv_k) >> 16), b = t - a * p.k;
                         Sample s;
                         s.y0 = s.y1 = s.x0 = s.x1 = 0; s.dy1 = s.dy0 = s.dx1 = s.dx0 = 0.f;
                         if (p.plain) {
@@ -336,18 +341,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                             }
                             continue;
                         }
-                        if (pix_ok) {
-                            float2 yx;
-                            if (prefetched) {
-                                yx = pre[0];
-#pragma unroll
-                                for (int q = 1; q < 9; ++q)
-                                    if (q == t) yx = pre[q];
-                            } else {
-                                yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
-                            }
-                            s = da_sample(i, j, a, b, yx.x, yx.y, p.in_h, p.in_w);
-                        }
+                        if (pix_ok) s = da_sample(i, j, a, b, pre[q].x, pre[q].y, p.in_h, p.in_w);
                         // the run's first pixel defines the run; every in-image pixel must agree with it
                         const int src = lane & ~(RUN - 1);
                         const int fy0 = __shfl_sync(0xffffffffu, s.y0, src), fy1 = __shfl_sync(0xffffffffu, s.y1, src);
@@ -370,18 +364,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                                         integer_taps ? 1 : 0)
                                             : make_int4(0, 0, 0, 0);
                                 f = make_float4(s.dy1, s.dy0, s.dx1, s.dx0);
-                                if (!regular) {   // the exact per-pixel path needs the tap's offsets, not the factors
-                                    float2 yx;
-                                    if (prefetched) {
-                                        yx = pre[0];
-#pragma unroll
-                                        for (int q = 1; q < 9; ++q)
-                                            if (q == t) yx = pre[q];
-                                    } else {
-                                        yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
-                                    }
-                                    f = make_float4(yx.x, yx.y, 0.f, 0.f);
-                                }
+                                if (!regular) f = make_float4(pre[q].x, pre[q].y, 0.f, 0.f);   // the exact per-pixel path needs the tap's offsets, not the factors
                             } else {
                                 e.z = 1;   // run entirely outside the panorama (tile overhang): rows are never stored; read anything
                             }
@@ -389,6 +372,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                             tw[t * NRUN] = f;
                         }
                     }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(rt_full0 + 8 * tb);
 
@@ -601,7 +585,7 @@ namespace sky {
 // the zenith-row taps — whose x offset of about -2w comes back as a small positive shift after the reference's two
 // 360-degree wraps — are covered too.  Shifts beyond +-(2k+6) columns are left to the exact fallback path.  The estimate
 // only affects speed: the kernel re-checks every corner against the band it actually holds.
-static void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi)
+void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi)
 {
     int ph0, pht, pw0, pwt;
     pad_axis(h, k, &ph0, &pht);

@@ -228,11 +228,20 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(tmap), "r"(c), "r"(x), "r"(y), "r"(b), "r"(bar)
         : "memory");
 }
+// 2-D tiled TMA load (column, row) of a row-major fp32 matrix; out-of-bounds elements are zero-filled.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *tmap, int col, int row, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(col), "r"(row), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 // Host: encode a 4-D fp32 NHWC tensor map with box (box_c, box_w, box_h, 1), no swizzle.
 int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, int w, int C, int box_c, int box_w, int box_h);
+// Host: encode a row-major fp32 matrix [rows][cols] with box (box_cols, box_rows), no swizzle (cols % 4 == 0, 16-byte aligned base).
+int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows);
 }  // namespace sky
 #endif

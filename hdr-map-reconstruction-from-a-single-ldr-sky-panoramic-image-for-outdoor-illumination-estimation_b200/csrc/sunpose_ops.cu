@@ -76,6 +76,88 @@ dense_splitk_kernel(const float *__restrict__ x, const float *__restrict__ W, fl
     }
 }
 
+// ---- weight-streaming Dense for wide layers (N % 4 == 0, K % 4 == 0, N >= 256) ---------------------------------------------------
+// The layer is HBM-bound on W (fc1: 134 MB, fc2: 67 MB per pass against 32 rows of activations), so the kernel is built around
+// keeping bytes in flight: one producer lane streams [32 k][256 n] weight tiles and the matching [32 b][32 k] activation tiles
+// through a 4-stage shared-memory ring with two 2-D TMA tensor loads per stage (out-of-bounds rows / columns arrive as zeros, so
+// ragged K, N and B need no special cases); eight consumer warps — two groups that each take half of a stage's k-rows — own two
+// columns per thread and 2 x 32 fp32 accumulators: per 4 k-rows a thread issues 8 LDS.32 of weights and 32 broadcast LDS.128 of
+// activations for 256 FMAs.  Split-K over blockIdx.y; partial sums meet in y with atomics.
+constexpr int DS_BN = 256, DS_BK = 32, DS_STAGES = 4, DS_CONSUMERS = 256, DS_THREADS = DS_CONSUMERS + 32;
+constexpr int DS_W_STAGE = DS_BK * DS_BN * 4, DS_X_STAGE = DN_BM * DS_BK * 4;
+constexpr int DS_SMEM = DS_STAGES * (DS_W_STAGE + DS_X_STAGE) + 2 * DS_STAGES * 8 + 1024;
+
+__global__ void __launch_bounds__(DS_THREADS, 1)
+dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, float *__restrict__ y, int B,
+                    int K, int N, int k_per)
+{
+    extern __shared__ uint8_t ds_raw[];
+    uint8_t *ds_smem = ds_raw + ((1024u - (smem_u32(ds_raw) & 1023u)) & 1023u);
+    float *Ws = reinterpret_cast<float *>(ds_smem);                                   // [STAGES][BK][BN]
+    float *xs = reinterpret_cast<float *>(ds_smem + DS_STAGES * DS_W_STAGE);          // [STAGES][32 b][BK]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ds_smem + DS_STAGES * (DS_W_STAGE + DS_X_STAGE));
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + DS_STAGES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * DS_BN, b0 = blockIdx.z * DN_BM;
+    const int k_lo = blockIdx.y * k_per, k_hi = min(K, k_lo + k_per);
+    const int nsteps = (k_hi - k_lo + DS_BK - 1) / DS_BK;
+    if (tid == 0) {
+        for (int s = 0; s < DS_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);                        // the producer's arrive.expect_tx
+            mbar_init(empty0 + 8 * s, DS_CONSUMERS / 32);       // one arrival per consumer warp
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == DS_CONSUMERS / 32) {
+        if (lane == 0) {
+            prefetch_tmap(&tmap_w);
+            prefetch_tmap(&tmap_x);
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % DS_STAGES, k0 = k_lo + it * DS_BK;
+                mbar_wait(empty0 + 8 * s, ((it / DS_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(DS_W_STAGE + DS_X_STAGE));
+                tma_load_2d(smem_u32(Ws + s * DS_BK * DS_BN), &tmap_w, n0, k0, full0 + 8 * s);
+                tma_load_2d(smem_u32(xs + s * DN_BM * DS_BK), &tmap_x, k0, b0, full0 + 8 * s);
+            }
+        }
+    } else {
+        // ---------------- consumers: columns n0 + ct and n0 + 128 + ct, k-rows [16 * khalf, 16 * khalf + 16) of every stage ----------------
+        const int ct = tid & 127, khalf = tid >> 7;
+        float acc0[DN_BM], acc1[DN_BM];
+#pragma unroll
+        for (int b = 0; b < DN_BM; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % DS_STAGES;
+            mbar_wait(full0 + 8 * s, (it / DS_STAGES) & 1);
+            const float *wt = Ws + s * DS_BK * DS_BN + ct, *xt = xs + s * DN_BM * DS_BK;
+#pragma unroll 1
+            for (int k4 = khalf * (DS_BK / 2); k4 < (khalf + 1) * (DS_BK / 2); k4 += 4) {
+                float w0[4], w1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { w0[u] = wt[(k4 + u) * DS_BN]; w1[u] = wt[(k4 + u) * DS_BN + 128]; }
+#pragma unroll
+                for (int b = 0; b < DN_BM; ++b) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xt + b * DS_BK + k4);
+                    acc0[b] = fmaf(xv.x, w0[0], acc0[b]); acc1[b] = fmaf(xv.x, w1[0], acc1[b]);
+                    acc0[b] = fmaf(xv.y, w0[1], acc0[b]); acc1[b] = fmaf(xv.y, w1[1], acc1[b]);
+                    acc0[b] = fmaf(xv.z, w0[2], acc0[b]); acc1[b] = fmaf(xv.z, w1[2], acc1[b]);
+                    acc0[b] = fmaf(xv.w, w0[3], acc0[b]); acc1[b] = fmaf(xv.w, w1[3], acc1[b]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+        const int na = n0 + ct, nb = n0 + 128 + ct;
+#pragma unroll
+        for (int b = 0; b < DN_BM; ++b)
+            if (b0 + b < B) {
+                if (na < N) atomicAdd(y + (size_t)(b0 + b) * N + na, acc0[b]);
+                if (nb < N) atomicAdd(y + (size_t)(b0 + b) * N + nb, acc1[b]);
+            }
+    }
+}
+
 // y = act(y + bias)
 __global__ void dense_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total, int N, int relu)
 {
@@ -128,18 +210,8 @@ extern "C" int sky_maxpool2x2_fwd(const float *x, float *y, int B, int h, int w,
     return SKY_OK;
 }
 
-extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, float *y, int B, int K, int N, int relu, void *stream)
+static int dense_finish(float *y, const float *bias, int B, int N, int relu, cudaStream_t st)
 {
-    SKY_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    SKY_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * N * sizeof(float), st));
-    const int ncta = (N + DN_THREADS - 1) / DN_THREADS, bcta = (B + DN_BM - 1) / DN_BM;
-    int ksplit = (4 * 148 + ncta * bcta - 1) / (ncta * bcta);          // about four waves of CTAs
-    int k_per = (K + ksplit - 1) / ksplit;
-    k_per = (k_per + DN_BK - 1) / DN_BK * DN_BK;
-    ksplit = (K + k_per - 1) / k_per;
-    dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
-    SKY_CHECK_CUDA(cudaGetLastError());
     if (bias || relu) {      // bias == NULL: the plain product (sky_dense_bwd_data)
         const long total = (long)B * N;
         int blocks = (int)((total + 255) / 256);
@@ -148,6 +220,43 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
         SKY_CHECK_CUDA(cudaGetLastError());
     }
     return SKY_OK;
+}
+
+extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, float *y, int B, int K, int N, int relu, void *stream)
+{
+    SKY_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SKY_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * N * sizeof(float), st));
+    const int bcta = (B + DN_BM - 1) / DN_BM;
+    if (N % 4 == 0 && K % 4 == 0 && N >= DS_BN && ((uintptr_t)W & 15) == 0 && ((uintptr_t)x & 15) == 0) {
+        static bool configured = false;
+        if (!configured) {
+            SKY_CHECK_CUDA(cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM));
+            configured = true;
+        }
+        CUtensorMap tmap_w, tmap_x;
+        int rc = encode_2d_tensor_map(&tmap_w, W, K, N, DS_BN, DS_BK);
+        if (rc != SKY_OK) return rc;
+        rc = encode_2d_tensor_map(&tmap_x, x, B, K, DS_BK, DN_BM);
+        if (rc != SKY_OK) return rc;
+        const int ncta = (N + DS_BN - 1) / DS_BN;
+        int ksplit = 148 / (ncta * bcta);                                  // one wave of CTAs, one per SM
+        if (ksplit < 1) ksplit = 1;
+        int k_per = (K + ksplit - 1) / ksplit;
+        k_per = (k_per + DS_BK - 1) / DS_BK * DS_BK;
+        ksplit = (K + k_per - 1) / k_per;
+        dense_stream_kernel<<<dim3(ncta, ksplit, bcta), DS_THREADS, DS_SMEM, st>>>(tmap_w, tmap_x, y, B, K, N, k_per);
+        SKY_CHECK_CUDA(cudaGetLastError());
+        return dense_finish(y, bias, B, N, relu, st);
+    }
+    const int ncta = (N + DN_THREADS - 1) / DN_THREADS;
+    int ksplit = (4 * 148 + ncta * bcta - 1) / (ncta * bcta);          // about four waves of CTAs
+    int k_per = (K + ksplit - 1) / ksplit;
+    k_per = (k_per + DN_BK - 1) / DN_BK * DN_BK;
+    ksplit = (K + k_per - 1) / k_per;
+    dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return dense_finish(y, bias, B, N, relu, st);
 }
 
 extern "C" int sky_softmax_rows(const float *x, float *y, int rows, int N, void *stream)

@@ -35,4 +35,19 @@ int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, in
     return SKY_OK;
 }
 
+int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows)
+{
+    EncodeTiledFn enc = get_encoder();
+    SKY_REQUIRE(enc != nullptr, SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)cols * 4 };
+    cuuint32_t box[2] = { (cuuint32_t)box_cols, (cuuint32_t)box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKY_REQUIRE(r == CUDA_SUCCESS, SKY_ERR_CUDA, "cuTensorMapEncodeTiled (2-D) failed with CUresult %d (rows=%ld cols=%ld box=%dx%d)", (int)r,
+                rows, cols, box_rows, box_cols);
+    return SKY_OK;
+}
+
 }  // namespace sky

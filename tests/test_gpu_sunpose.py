@@ -73,3 +73,21 @@ def test_sunpose_forward_vs_oracle(pkg, da):
         assert rel_l2(a.cpu().numpy(), wa.numpy()) <= 5e-3, rel_l2(a.cpu().numpy(), wa.numpy())
     assert abs(sm.sum(-1).cpu().numpy() - 1).max() < 1e-4
     assert rel_l2(sm.cpu().numpy(), want_sm.numpy()) <= 2e-2, rel_l2(sm.cpu().numpy(), want_sm.numpy())
+
+
+@pytest.mark.parametrize("B,K,N", [(32, 1000, 1028), (5, 96, 256), (40, 4096, 512)])
+def test_dense_streaming_kernel(pkg, B, K, N):
+    """Wide layers (N % 4 == 0, N >= 256) take the bulk-copy weight-streaming kernel: ragged K tail, ragged column tile, B < 32 and
+    B > 32 (two row chunks).  fp32 FMA, split-K with atomics: 1e-5 relative L2 against fp64."""
+    sp = pkg.sunpose_net
+    rng = np.random.default_rng(B + K + N)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    W = rng.standard_normal((K, N)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    d = sp.Dense(N)
+    d.build((B, K))
+    d.kernel.copy_(torch.from_numpy(W))
+    d.bias.copy_(torch.from_numpy(b))
+    want = x.astype(np.float64) @ W.astype(np.float64) + b
+    assert rel_l2(d(torch.from_numpy(x).cuda()).cpu().numpy(), want) < 1e-5
+    assert rel_l2(d(torch.from_numpy(x).cuda(), relu=True).cpu().numpy(), np.maximum(want, 0)) < 1e-5
