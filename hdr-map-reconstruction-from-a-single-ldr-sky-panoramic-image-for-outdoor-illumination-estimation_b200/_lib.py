@@ -42,6 +42,9 @@ SIGNATURES = {
     "sky_resize_bilinear_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_conv2d_fwd_blend": (_i, [_vp] * 6 + [_f] + [_i] * 6 + [_f, _i, _vp]),
     "sky_softmax_max_bwd": (_i, [_vp] * 4 + [_i, _i, _vp]),
+    "sky_softmax_pick_bwd": (_i, [_vp] * 5 + [_i, _i, _vp]),
+    "sky_argmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sky_blend_split": (_i, [_vp, _vp, _f] + [_vp] * 5 + [ctypes.c_long, _vp]),
     "sky_transpose": (_i, [_vp, _vp, _i, _i, _vp]),
     "sky_dense_bwd_data": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
     "sky_maxpool2x2_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
@@ -49,6 +52,15 @@ SIGNATURES = {
     "sky_sunrad_input": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "sky_bn_fold": (_i, [_vp] * 5 + [_f, _vp, _vp, ctypes.c_long, _i, _vp]),
     "sky_max_nonneg": (_i, [_vp, _vp, ctypes.c_long, _vp]),
+    "sky_ldr_synth": (_i, [_vp] * 9 + [_i] * 5 + [_vp]),
+    "sky_hdr_log_codec": (_i, [_vp, _vp, ctypes.c_long, _i, _vp]),
+    "sky_loss_reduce": (_i, [_i, _vp, _vp, ctypes.c_long, _vp, _vp]),
+    "sky_kl_divergence": (_i, [_vp, _vp, ctypes.c_long, _vp, _vp]),
+    "sky_dog_base": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sky_dog_l1": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sky_adam_step": (_i, [_vp] * 4 + [ctypes.c_long, _f, _f, _f, _f, ctypes.c_long, _f, _vp]),
+    "sky_concat2_pad": (_i, [_vp, _i, _vp, _i, _vp, _i, ctypes.c_long, _vp]),
+    "sky_vgg_preprocess": (_i, [_vp, _vp, ctypes.c_long, _f, _f, _f, _vp]),
     "sky_sun_radiance": (_i, [_vp] * 5 + [_i, _i, _f, _vp]),
 }
 

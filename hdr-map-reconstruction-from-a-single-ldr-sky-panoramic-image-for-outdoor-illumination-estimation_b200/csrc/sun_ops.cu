@@ -20,8 +20,11 @@ namespace sky {
 // One CTA per row.  y_c = max_i sm_i; TF's reduce_max gradient spreads 1 evenly over ties; the softmax backward gives
 // g_a[i] = sm_i * (ind_i / cnt - sum_j ind_j sm_j / cnt) = sm_i * (ind_i / cnt - y_c); the ReLU in front of the softmax
 // (sunpose_net.py:68) passes it where its output is positive (ReluGrad tests the output).
+// With `pick` (one class index per row: tf.gather_nd at argmax(sunpose_gt), train.py:263-265) the score is sm[pick] instead of the
+// maximum: g_a[i] = sm_i * ((i == pick) - sm[pick]).
 __global__ void __launch_bounds__(256) softmax_max_bwd_kernel(const float *__restrict__ sm, const float *__restrict__ act,
-                                                              float *__restrict__ yc, float *__restrict__ g, int N)
+                                                              const int *__restrict__ pick, float *__restrict__ yc,
+                                                              float *__restrict__ g, int N)
 {
     __shared__ float redf[8];
     __shared__ int redi[8];
@@ -29,6 +32,16 @@ __global__ void __launch_bounds__(256) softmax_max_bwd_kernel(const float *__res
     const float *arow = act + (size_t)blockIdx.x * N;
     float *out = g + (size_t)blockIdx.x * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (pick) {
+        const int j = pick[blockIdx.x];
+        const float sj = row[j];
+        if (threadIdx.x == 0 && yc) yc[blockIdx.x] = sj;
+        for (int i = threadIdx.x; i < N; i += 256) {
+            const float ga = row[i] * ((i == j ? 1.f : 0.f) - sj);
+            out[i] = arow[i] > 0.f ? ga : 0.f;
+        }
+        return;
+    }
     float m = -INFINITY;
     for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, row[i]);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -263,7 +276,7 @@ using namespace sky;
 extern "C" int sky_softmax_max_bwd(const float *sm, const float *act, float *yc, float *g, int rows, int N, void *stream)
 {
     SKY_REQUIRE(sm && act && g && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
-    softmax_max_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, act, yc, g, N);
+    softmax_max_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, act, nullptr, yc, g, N);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }
@@ -357,6 +370,84 @@ extern "C" int sky_sun_radiance(const float *sm, const float *gmax, const float 
     // deltafunc_const = tf.sqrt(pi) (sunrad_net.py:35): fp32 sqrt of fp32(pi)
     const float sqrt_pi = sqrtf(3.14159265358979323846f);
     sun_radiance_kernel<<<ew_blocks((long)B * hw), 256, 0, (cudaStream_t)stream>>>(sm, gmax, gb, out3, lin1, B, hw, eps, sqrt_pi);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+// first index of the row maximum (tf.math.argmax)
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float *__restrict__ x, int *__restrict__ idx, int N)
+{
+    __shared__ float vals[256];
+    __shared__ int ids[256];
+    const float *row = x + (size_t)blockIdx.x * N;
+    float m = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int i = threadIdx.x; i < N; i += 256)
+        if (row[i] > m) { m = row[i]; mi = i; }
+    vals[threadIdx.x] = m; ids[threadIdx.x] = mi;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const float o = vals[threadIdx.x + s];
+            const int oi = ids[threadIdx.x + s];
+            if (o > vals[threadIdx.x] || (o == vals[threadIdx.x] && oi < ids[threadIdx.x])) { vals[threadIdx.x] = o; ids[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) idx[blockIdx.x] = ids[0];
+}
+
+// The un-fused tail of train.generator_in_step (train.py:256-259, 289-298): alpha from the sky prediction, the two scaled branches,
+// their sum and the three decompressed images.  One pixel (3 channels) per thread.
+__global__ void blend_split_kernel(const float *__restrict__ sky_gamma, const float *__restrict__ sun_gamma, float thr,
+                                   float *__restrict__ y_gamma, float *__restrict__ y_lin, float *__restrict__ sky_lin,
+                                   float *__restrict__ sun_lin, float *__restrict__ alpha_out, long npix)
+{
+    const float l11 = 2.3978953f;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < npix; p += (long)gridDim.x * blockDim.x) {
+        const float *s = sky_gamma + 3 * p, *u = sun_gamma + 3 * p;
+        const float s0 = s[0], s1 = s[1], s2 = s[2];
+        const float gmax = fmaxf(fmaxf(s0, s1), s2);
+        const float lin = __fdiv_rn(__fsub_rn(expf(__fmul_rn(gmax, l11)), 1.f), 10.f);
+        const float a = fminf(1.f, __fdiv_rn(fmaxf(0.f, __fadd_rn(__fsub_rn(lin, 1.f), thr)), thr));
+        const float na = __fsub_rn(1.f, a);
+        if (alpha_out) alpha_out[p] = a;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float sk = __fmul_rn(na, s[c]), sn = __fmul_rn(a, u[c]);
+            const float yg = __fadd_rn(sk, sn);
+            y_gamma[3 * p + c] = yg;
+            y_lin[3 * p + c] = __fdiv_rn(__fsub_rn(expf(__fmul_rn(yg, l11)), 1.f), 10.f);
+            if (sky_lin) sky_lin[3 * p + c] = __fdiv_rn(__fsub_rn(expf(__fmul_rn(sk, l11)), 1.f), 10.f);
+            if (sun_lin) sun_lin[3 * p + c] = __fdiv_rn(__fsub_rn(expf(__fmul_rn(sn, l11)), 1.f), 10.f);
+        }
+    }
+}
+
+extern "C" int sky_softmax_pick_bwd(const float *sm, const float *act, const int *pick, float *yc, float *g, int rows, int N, void *stream)
+{
+    SKY_REQUIRE(sm && act && pick && g && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    sky::softmax_max_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, act, pick, yc, g, N);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_argmax_rows(const float *x, int *idx, int rows, int N, void *stream)
+{
+    SKY_REQUIRE(x && idx && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    argmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, idx, N);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
+extern "C" int sky_blend_split(const float *sky_gamma, const float *sun_gamma, float threshold, float *y_gamma, float *y_lin,
+                               float *sky_lin, float *sun_lin, float *alpha, long npix, void *stream)
+{
+    SKY_REQUIRE(sky_gamma && sun_gamma && y_gamma && y_lin && npix > 0 && threshold > 0.f, SKY_ERR_INVALID, "bad arguments");
+    long blocks = (npix + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    blend_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(sky_gamma, sun_gamma, threshold, y_gamma, y_lin, sky_lin, sun_lin, alpha,
+                                                                      npix);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }

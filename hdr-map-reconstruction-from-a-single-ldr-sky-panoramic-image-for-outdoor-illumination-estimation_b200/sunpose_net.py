@@ -209,12 +209,13 @@ class model:
         self._saved = (sm, actv1_s, actv2_s, tuple(pool3_s.shape), [sunlayer1, sunlayer2, sunlayer3])
         return sm, [sunlayer1, sunlayer2, sunlayer3]
 
-    def class_score(self, sm):
-        """y_c = tf.math.reduce_max(sunpose_cmf, axis=1) (inference.py:98) as a handle that can be differentiated with
-        respect to the three activation maps — what grad_cam.layer's tf.gradients(y_c, A_k) (grad_cam.py:31) asks for."""
+    def class_score(self, sm, sunpose_gt=None):
+        """y_c = tf.math.reduce_max(sunpose_cmf, axis=1) (inference.py:98) — or, with `sunpose_gt`, the softmax entry at
+        argmax(sunpose_gt) (train.py:263-265) — as a handle that can be differentiated with respect to the three activation maps:
+        what grad_cam.layer's tf.gradients(y_c, A_k) (grad_cam.py:31) asks for."""
         if self._saved is None or sm is not self._saved[0]:
             raise ValueError("class_score() takes the softmax returned by the last sunposeEstimation() call")
-        return ClassScore(self)
+        return ClassScore(self, sunpose_gt)
 
 
 class ClassScore:
@@ -222,13 +223,20 @@ class ClassScore:
     -> pool1 that yields d(sum_b y_c[b]) / dA_k for the three maps (run once, on first use).  TensorFlow would run one
     backward sub-graph per tf.gradients call; the three share every node, so one sweep gives identical values."""
 
-    def __init__(self, net):
+    def __init__(self, net, sunpose_gt=None):
         self._net = net
         sm, actv1_s, actv2_s, pool_shape, acts = net._saved
         B, n = sm.shape
         self.value = torch.empty(B, dtype=torch.float32, device=sm.device)
         self._seed = torch.empty_like(sm)
-        check(LIB.sky_softmax_max_bwd(sm.data_ptr(), actv2_s.data_ptr(), self.value.data_ptr(), self._seed.data_ptr(), B, n, _stream()))
+        if sunpose_gt is None:
+            check(LIB.sky_softmax_max_bwd(sm.data_ptr(), actv2_s.data_ptr(), self.value.data_ptr(), self._seed.data_ptr(), B, n, _stream()))
+        else:
+            gt = _require_cuda(sunpose_gt, "sunpose_gt")
+            self.pick = torch.empty(B, dtype=torch.int32, device=sm.device)
+            check(LIB.sky_argmax_rows(gt.data_ptr(), self.pick.data_ptr(), B, n, _stream()))
+            check(LIB.sky_softmax_pick_bwd(sm.data_ptr(), actv2_s.data_ptr(), self.pick.data_ptr(), self.value.data_ptr(),
+                                           self._seed.data_ptr(), B, n, _stream()))
         self._grads = None
 
     def _sweep(self):

@@ -351,3 +351,148 @@ def random_full_generator_weights(seed, H, W, k=3, affine_noise=True):
     conv("conv1_u", 7, 32, 3)
     w["sun"] = random_sunrad_weights(seed + 99, H, W, affine_noise)
     return w
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# train / test step around the generator (train.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def apply_rf(x, rf):
+    """tf_utils.apply_rf / interp_1d / sample_1d (tf_utils.py:191-255): x [b, ...] in [0, 1], rf [b, k]."""
+    b, k = rf.shape
+    pos = (k - 1) * x.reshape(b, -1)
+    y0 = torch.floor(pos)
+    y1 = y0 + 1
+    v0 = torch.gather(rf, 1, y0.long().clamp(0, k - 1))
+    v1 = torch.gather(rf, 1, y1.long().clamp(0, k - 1))
+    return ((y1 - pos) * v0 + (pos - y0) * v1).reshape(x.shape)
+
+
+def ldr_synth(hdr, t, crf, sigma_s=None, sigma_c=None, noise_s=None, noise_c=None, quantize=True):
+    """train._preprocessing (train.py:54-94) with the random draws as inputs; JPEG round trip omitted."""
+    b = hdr.shape[0]
+    x = hdr * t.reshape(b, 1, 1, 1)
+    tmp = x
+    if noise_s is not None:
+        tmp = tmp + noise_s * (sigma_s.reshape(b, 1, 1, -1) * x)
+    if noise_c is not None:
+        tmp = tmp + sigma_c.reshape(b, 1, 1, -1) * noise_c
+    hdr_t = torch.relu(tmp)
+    ldr = apply_rf(hdr_t.clamp(0, 1), crf)
+    if quantize:
+        ldr = torch.round(ldr * 255.0) / 255.0
+    return hdr_t, ldr
+
+
+def kl_divergence(y_true, y_pred):
+    """tf.keras.losses.KLDivergence: clip to [1e-7, 1], sum over the last axis, mean over the batch."""
+    t, p = y_true.clamp(1e-7, 1.0), y_pred.clamp(1e-7, 1.0)
+    return (t * torch.log(t / p)).sum(-1).mean()
+
+
+def gaussian_filter2d(x, sigma):
+    """tfa.image.gaussian_filter2d(filter_shape=(3, 3), sigma, padding='REFLECT') on NHWC."""
+    g = torch.softmax(-torch.tensor([1.0, 0.0, 1.0], dtype=x.dtype) / (2.0 * sigma * sigma), 0)
+    k2 = torch.outer(g, g)
+    C = x.shape[-1]
+    xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect")
+    y = torch.nn.functional.conv2d(xp, k2[None, None].repeat(C, 1, 1, 1), groups=C)
+    return y.permute(0, 2, 3, 1)
+
+
+def dog(img):
+    """tf_utils.DoG (tf_utils.py:61-73) -> four difference images."""
+    B, h, w, C = img.shape
+    up = O.resize_bilinear(img, 2 * h, 2 * w)
+    base = gaussian_filter2d(up, 1.2489996)
+    s1 = [1.2262735, 1.5450078, 1.9465878, 2.452547]
+    s2 = [1.5450078, 1.9465878, 2.452547, 3.0900156]
+    return [gaussian_filter2d(base, b) - gaussian_filter2d(base, a) for a, b in zip(s1, s2)]
+
+
+def dog_l1(a, b):
+    return sum((x - y).abs().mean() for x, y in zip(dog(a), dog(b)))
+
+
+def vgg16_pools(bgr, data_dict, mean=(103.939, 116.779, 123.68), acc_dtype=torch.float32):
+    """Vgg16.call (vgg16.py:130-165) -> (pool1, pool2, pool3)."""
+    dt = acc_dtype
+    x = 255.0 * bgr.to(dt) - torch.tensor(mean, dtype=dt)
+
+    def conv(x, name):
+        w, b = data_dict[name]
+        return torch.relu(conv2d_same(x, w, b, acc_dtype=dt))
+
+    p1 = maxpool2x2_same(conv(conv(x, "conv1_1"), "conv1_2"))
+    p2 = maxpool2x2_same(conv(conv(p1, "conv2_1"), "conv2_2"))
+    p3 = maxpool2x2_same(conv(conv(conv(p2, "conv3_1"), "conv3_2"), "conv3_3"))
+    return p1, p2, p3
+
+
+def discriminator(ldr, hdr, w, acc_dtype=torch.float32):
+    """discriminator.model.call (discriminator.py:41-50), BatchNormalization in inference mode; Conv2D(1, 4) is VALID."""
+    dt = acc_dtype
+    h = torch.cat([ldr.to(dt), hdr.to(dt)], dim=-1)
+    for name, stride in (("d1", 2), ("d2", 2), ("d3", 2), ("d4", 1)):
+        d = w[name]
+        kern = O._as_t(d["kernel"]).to(dt)
+        h = conv2d_same(h, kern, torch.zeros(kern.shape[-1], dtype=dt), stride=stride, acc_dtype=dt)
+        if "gamma" in d:
+            h = batch_norm_inference(h, *(O._as_t(d[k]).to(dt) for k in ("gamma", "beta", "moving_mean", "moving_variance")))
+        h = leaky_relu(h, 0.3)
+    kern, bias = O._as_t(w["out"][0]).to(dt), O._as_t(w["out"][1]).to(dt)
+    y = torch.nn.functional.conv2d(h.permute(0, 3, 1, 2), kern.permute(3, 2, 0, 1), bias=bias)
+    return y.permute(0, 2, 3, 1)
+
+
+def random_discriminator_weights(seed, bn_noise=True):
+    w = random_sunrad_weights(seed, 32, 128, bn_noise)
+    rng = np.random.default_rng(seed + 1)
+    out = {k: w[k] for k in ("d1", "d2", "d3", "d4")}
+    out["out"] = ((0.02 * rng.standard_normal((4, 4, 512, 1))).astype(np.float32), (0.1 * rng.standard_normal(1) * bn_noise).astype(np.float32))
+    return out
+
+
+def generator_test_step(ldr, hdr_t, sunpose_gt, wg, ws, wd, vgg_dict, k=3, threshold=0.12, acc_dtype=torch.float32):
+    """train.generator_in_step(training=False) + discriminator_in_step(training=False) (train.py:239-380) -> dict of losses."""
+    dt = acc_dtype
+    inp = O._as_t(ldr).to(dt)
+    hdr_t = O._as_t(hdr_t).to(dt)
+    gt = O._as_t(sunpose_gt).to(dt)
+    B, H, W, _ = inp.shape
+
+    def norm_act(y, name):
+        g, b = (O._as_t(v).to(dt) for v in wg[name])
+        return leaky_relu(instance_norm(y, g, b), 0.1)
+
+    x = norm_act(conv2d_same(inp, *wg["conv1_d"], stride=1, acc_dtype=dt), "norm1_d")
+    x = norm_act(conv2d_same(x, *wg["conv2_d"], stride=2, acc_dtype=dt), "norm2_d")
+    x = norm_act(conv2d_same(x, *wg["conv3_d"], stride=2, acc_dtype=dt), "norm3_d")
+    blocks = [{kk: O._as_t(v) for kk, v in blk.items()} for blk in wg["res"]]
+    res_out = res_layer(x, blocks, k, acc_dtype=dt)
+    sky_gamma = decode_branch(res_out, inp, wg, ("conv3_f", "norm3_f", "conv2_f", "norm2_f", "conv1_f"), dt)
+    sky_lin = hdr_log_decompression(sky_gamma)
+    x_sun = inp.clone().requires_grad_(True)
+    sm, acts = sunpose_estimation(x_sun, ws, distortion_aware=True, acc_dtype=dt)
+    alpha = torch.clamp((sky_lin.amax(dim=3) - 1.0 + threshold).clamp(min=0.0) / threshold, max=1.0).unsqueeze(-1)
+    y_c = torch.gather(sm, 1, gt.argmax(dim=1, keepdim=True))[:, 0]                     # train.py:278-280
+    cams = [grad_cam_layer(y_c, a).detach() for a in acts]
+    sm = sm.detach()
+    pred = sm.reshape(B, H, W, 1)
+    plz = torch.cat([inp, cams[0], O.resize_bilinear(cams[1], H, W), O.resize_bilinear(cams[2], H, W)], dim=-1)
+    sun_rad = sunrad_net(pred / pred.max(), plz, wg["sun"], acc_dtype=dt).expand(B, H, W, 3)
+    sun_gamma = decode_branch(res_out, hdr_log_compression(sun_rad), wg, ("conv3_u", "norm3_u", "conv2_u", "norm2_u", "conv1_u"), dt)
+    sky_s, sun_s = (1.0 - alpha) * sky_gamma, alpha * sun_gamma
+    y_gamma = sky_s + sun_s
+    y_lin = hdr_log_decompression(y_gamma)
+    out = dict(y_final_gamma=y_gamma, y_final_lin=y_lin, sky_pred_lin=hdr_log_decompression(sky_s), sun_pred_lin=hdr_log_decompression(sun_s))
+    out["kl"] = kl_divergence(gt, sm)
+    pa, pb = vgg16_pools(y_gamma, vgg_dict, acc_dtype=dt), vgg16_pools(hdr_log_compression(hdr_t), vgg_dict, acc_dtype=dt)
+    out["perceptual"] = sum((a - b).abs().mean() for a, b in zip(pa, pb))
+    out["dog"] = dog_l1(y_lin, hdr_t)
+    out["l1"] = (y_lin - hdr_t).abs().mean()
+    d_fake = discriminator(inp, y_lin, wd, dt)
+    out["gen"] = ((d_fake - 1.0) ** 2).mean()
+    out["total"] = out["kl"] + 1000.0 * out["dog"] + out["gen"] + 10.0 * out["l1"] + 0.01 * out["perceptual"]
+    d_real = discriminator(inp, hdr_t, wd, dt)
+    out["disc"] = 0.5 * ((d_fake ** 2).mean() + ((d_real - 1.0) ** 2).mean())
+    return out
