@@ -15,3 +15,4 @@ from . import sunrad_net               # noqa: F401
 from . import grad_cam                 # noqa: F401
 from . import inference                # noqa: F401
 from . import tf_utils, discriminator, vgg16, train   # noqa: F401
+from . import train_sun   # noqa: F401

@@ -207,6 +207,7 @@ class model:
         actv2_s = self.fc2(actv1_s, relu=True)                                       # :67-68
         sm = softmax(actv2_s)                                                        # :70
         self._saved = (sm, actv1_s, actv2_s, tuple(pool3_s.shape), [sunlayer1, sunlayer2, sunlayer3])
+        self._saved_flat = flat
         return sm, [sunlayer1, sunlayer2, sunlayer3]
 
     def class_score(self, sm, sunpose_gt=None):

@@ -496,3 +496,32 @@ def generator_test_step(ldr, hdr_t, sunpose_gt, wg, ws, wd, vgg_dict, k=3, thres
     d_real = discriminator(inp, hdr_t, wd, dt)
     out["disc"] = 0.5 * ((d_fake ** 2).mean() + ((d_real - 1.0) ** 2).mean())
     return out
+
+
+def sun_train_step_grads(ldr, sunpose_gt, ws, acc_dtype=torch.float64):
+    """train_sun.sun_train_step (train_sun.py:220-264) up to the gradients: loss = KLDivergence(gt, sm) + sum_l mean|DoG_l(pred) - DoG_l(gt)|,
+    autograd w.r.t. every variable of the sun-position network (distortion-aware wiring).  Returns (loss, grads in the layout of ws)."""
+    dt = acc_dtype
+    leaves = {}
+
+    def leaf(a):
+        t = O._as_t(a).to(dt).clone().requires_grad_(True)
+        return t
+
+    w = {}
+    for name in ("sunlayer1", "sunlayer2", "sunlayer3"):
+        w[name] = {k: leaf(v) for k, v in ws[name].items()}
+    for name in ("fc1", "fc2"):
+        w[name] = tuple(leaf(v) for v in ws[name])
+    x = O._as_t(ldr).to(dt)
+    gt = O._as_t(sunpose_gt).to(dt)
+    B, H, W, _ = x.shape
+    sm, _ = sunpose_estimation(x, w, distortion_aware=True, acc_dtype=dt)
+    loss = kl_divergence(gt, sm) + dog_l1(sm.reshape(B, H, W, 1), gt.reshape(B, H, W, 1))
+    flat = [w[n][k] for n in ("sunlayer1", "sunlayer2", "sunlayer3") for k in sorted(w[n])] + [t for n in ("fc1", "fc2") for t in w[n]]
+    grads = torch.autograd.grad(loss, flat)
+    it = iter(grads)
+    out = {n: {k: next(it) for k in sorted(w[n])} for n in ("sunlayer1", "sunlayer2", "sunlayer3")}
+    for n in ("fc1", "fc2"):
+        out[n] = (next(it), next(it))
+    return loss.detach(), out
