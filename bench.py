@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native distortion-aware convolution path.
 
-Workload (config.workload, default `inference`): BASELINE.json configs[0], "generator inference, random-init weights,
-synthetic 32x128 LDR sky-dome panoramas, batch 32" = inference.generator_in_step (inference.py:81-112): encoder -> six
-res-blocks with the distortion-aware convolutions of generator.py:14,18 -> sky decoder; sun-position network (distortion-aware
-wiring of sunpose_net.py:11,16) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun decoder -> alpha blend -> linear HDR.
+Workload (config.workload, default `sun_train`): BASELINE.json configs[1], the sun pre-train step at batch 32, 32x128 =
+train_sun.sun_train_step (train_sun.py:220-264): sun-position network forward (distortion-aware wiring of sunpose_net.py:11,16) ->
+Grad-CAM x3 at the ground-truth class -> KLDivergence + DoG L1 -> backward through every layer -> (world > 1: gradient all-reduce,
+the 201 MB Dense part overlapped with the conv backward) -> Adam.  At N = 1 the same line carries `inference`: BASELINE configs[0],
+"generator inference, random-init weights, synthetic 32x128 LDR sky-dome panoramas, batch 32" = inference.generator_in_step
+(inference.py:81-112), which `--workload inference` also times on its own (with its own e2e / roofline keys).
 `--workload sky` times the sky branch alone (inference.py:84-86), `--workload trunk` the DA residual trunk alone,
 `--workload trunk_train` the data-parallel train step of the trunk.
 
@@ -32,6 +34,7 @@ sys.path.insert(0, ROOT)
 N_BLOCKS, C, K_SIZE = 6, 128, 3
 UNIT = "panoramas/s"
 METRICS = {"trunk_train": "panoramas/sec (32x128, data-parallel train step of the DA residual trunk: fwd + L2 loss + bwd + 1 NCCL all-reduce + RMSprop)",
+           "sun_train": "panoramas/sec (32x128, sun-position network pre-train step: train_sun.sun_train_step, fwd + Grad-CAM + KL/DoG loss + bwd + Adam)",
            "inference": "panoramas/sec (32x128, generator inference: inference.generator_in_step, sky + sun branch)",
            "sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
            "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)"}
@@ -60,6 +63,10 @@ def make_input(batch, h, w, seed):
 
 
 def workload_name(batch, H, W, workload="sky"):
+    if workload == "sun_train":
+        return (f"sun_train_step (train_sun.py:220-264): LDR [{batch},{H},{W},3] -> sunpose_net (distortion-aware convs, 2 Dense {H * W}) -> "
+                f"Grad-CAM x3 at the ground-truth class -> KLDivergence + DoG L1 -> backward through every layer -> gradient all-reduce "
+                f"(world > 1) -> Adam; random-init weights, B={batch}/GPU")
     if workload == "inference":
         return (f"generator_inference (inference.py:81-112): LDR [{batch},{H},{W},3] -> encode + 6 DA resBlocks -> sky_decode; "
                 f"sunpose_net (DA convs, 2 Dense {H * W}) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun_decode -> alpha blend -> "
@@ -134,6 +141,21 @@ def make_inference_weights(H, W, seed=0):
     return wg, ws
 
 
+def make_sunpose_gt(batch, H, W, seed):
+    """sunpose_gt = von Mises-Fisher bump (kappa = 80) over the H*W sky bins (train.py:42-52) at a random sun position."""
+    rng = np.random.default_rng(seed)
+    ii, jj = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    elev = (H - ii - 0.5) * (np.pi / 2) / H
+    azim = (jj + 0.5) * (2 * np.pi) / W - np.pi
+    bins = np.stack([np.cos(elev) * np.sin(azim), np.sin(elev), np.cos(elev) * np.cos(azim)], -1).reshape(-1, 3)
+    out = np.empty((batch, H * W), np.float32)
+    for b in range(batch):
+        c = bins[rng.integers(0, H * W)]
+        p = np.exp(80.0 * (bins @ c - 1.0))
+        out[b] = (p / p.sum()).astype(np.float32)
+    return out
+
+
 def make_ldr(batch, H, W, seed):
     """LDR = round(255 u) / 255, u ~ U[0,1)  (mimics train.py:84-92)."""
     return (np.round(255 * np.random.default_rng(seed).uniform(0, 1, (batch, H, W, 3))) / 255).astype(np.float32)
@@ -163,6 +185,25 @@ def oracle_step_fn(args, sample):
         x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
         return lambda: M.res_layer(x, blocks, K_SIZE)
     ldr = make_ldr(sample, args.height, args.width, seed=1)
+    if args.workload == "sun_train":
+        _, ws = make_inference_weights(args.height, args.width)
+        gt = make_sunpose_gt(sample, args.height, args.width, seed=2)
+        state = {}
+
+        def step():
+            # autograd through the restated forward + loss, then Adam (train_sun.py:257-258) on every variable
+            _, grads = M.sun_train_step_grads(ldr, gt, ws, acc_dtype=torch.float32, with_gradcam=True)
+            t = state["t"] = state.get("t", 0) + 1
+            lr_t = 1e-4 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+            for name in ws:
+                items = list(ws[name].items()) if isinstance(ws[name], dict) else list(enumerate(ws[name]))
+                for key, val in items:
+                    g = grads[name][key].numpy()
+                    m, v = state.setdefault((name, key), [np.zeros_like(g), np.zeros_like(g)])
+                    m *= 0.9; m += 0.1 * g
+                    v *= 0.999; v += 0.001 * g * g
+                    val -= (lr_t * m / (np.sqrt(v) + 1e-7)).astype(np.float32)
+        return step
     if args.workload == "inference":
         wg, ws = make_inference_weights(args.height, args.width)
         return lambda: M.generator_inference(ldr, wg, ws, K_SIZE)
@@ -231,6 +272,42 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measure_inference(pkg, args, rank, flush):
+    """Device-resident throughput of full generator inference (BASELINE configs[0]) measured in the same process: CUDA-graph replay,
+    L2 flushed between steps, CUDA events.  Reported next to the train-step line so one run carries both halves of the metric."""
+    import torch
+    B, H, W = args.batch, args.height, args.width
+    gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=args.math)
+    x = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).cuda()
+    sun.sunposeEstimation(x)
+    wg, ws = make_inference_weights(H, W)
+    gen.set_weights(wg)
+    sun.set_weights(ws)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            pkg.inference.generator_in_step(gen, sun, x)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            pkg.inference.generator_in_step(gen, sun, x)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        graph.replay()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        graph.replay()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    t = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+    return {"workload": workload_name(B, H, W, "inference"), "value": round(B / (t * 1e-3), 1), "unit": UNIT, "ms_per_step": round(t, 4),
+            "steps": args.steps, "cuda_graph": True}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -270,6 +347,18 @@ def run_ours(args):
         forward = trunk
         x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
         launches_per_step = 4 * N_BLOCKS         # per res-block: 2 conv + 2 instance-norm kernels (ours)
+    elif args.workload == "sun_train":
+        sun = pkg.sunpose_net.model(im_height=H, im_width=W, math_mode=args.math)
+        trainer = pkg.train_sun.SunTrainer(sun, B, H, W, lr=1e-4)
+        sun.set_weights(make_inference_weights(H, W)[1])
+        gt_dev = torch.from_numpy(make_sunpose_gt(B, H, W, seed=200 + rank)).cuda()
+        x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
+        trunk = None
+
+        def forward(inp):
+            trainer.sun_train_step([None, inp], gt_dev)
+            return trainer.loss
+        launches_per_step = None
     elif args.workload == "inference":
         gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=args.math)
         x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
@@ -368,14 +457,22 @@ def run_ours(args):
 
     # ---- dominant kernel: the band-staged DA conv, timed per launch with CUDA events on its stream ----
     conv_ms = []
-    blk = trunk.sequence[0]
-    stats = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
-    xt = torch.from_numpy(make_input(B, h, w, seed=7)).cuda()          # a trunk-shaped activation
+    if args.workload == "sun_train":
+        # sunlayer1.conv2 (32 -> 32, 7x7, full resolution): the largest single launch of the step, forward direction
+        pc, pk, pf, pm = 32, 7, 32, B * H * W
+        probe_layer = sun.sunlayer1.conv2
+        xt = torch.randn(B, H, W, pc, device="cuda")
+        stats = torch.zeros(B, pf, 2, dtype=torch.float64, device="cuda")
+    else:
+        pc, pk, pf, pm = C, K_SIZE, C, B * h * w
+        probe_layer = trunk.sequence[0].conv1
+        xt = torch.from_numpy(make_input(B, h, w, seed=7)).cuda()          # a trunk-shaped activation
+        stats = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
     for rep in range(12 + 3):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        blk.conv1.call(xt, stats=stats)
+        probe_layer.call(xt, stats=stats)
         e.record()
         torch.cuda.synchronize()
         if rep >= 3:
@@ -386,12 +483,20 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)           # max over ranks
     t_dev, t_e2e = (float(v) / args.steps for v in tot.tolist())
+    in_sync = None
+    if world > 1 and trainer is not None:
+        # data-parallel sanity: after the timed steps every replica must hold the same weights (same init, averaged gradients)
+        chk = trainer.flat_w.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool((hi - lo).abs().item() <= 1e-9 * max(1.0, abs(hi.item())))
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else None
         bf16_peak = peaks["bf16_tflops"] if peaks else 1590.0
-        flops = 2.0 * (B * h * w) * (K_SIZE * K_SIZE * C) * C
+        flops = 2.0 * pm * (pk * pk * pc) * pf
         achieved = flops / (conv_t * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -401,12 +506,13 @@ def run_ours(args):
             "metric": METRIC, "value": round(world * B / (t_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
-            "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B, "parallelism": f"batch shards x{world}, no collective",
+            "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B, "parallelism": (f"batch shards x{world}, " + ("gradient all-reduce (NCCL) of the flat buffer, Dense part overlapped with the conv backward"
+                                                                     if trainer is not None else "no collective")),
                        "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
-                    "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": round(t_e2e, 4)},
+                    "d2h_bytes_per_step": y_host.numel() * y_host.element_size(), "ms_per_step": round(t_e2e, 4)},
             "gpu_launches": launches_per_step * args.steps, "abi_calls_per_step": abi_calls,
-            "roofline": {"kernel": "da_conv2d_fwd_band_kernel (128->128, k=3, M=%d)" % (B * h * w), "bound": "tensor",
+            "roofline": {"kernel": "da_conv2d_fwd_band_kernel (%d->%d, k=%d, M=%d)" % (pc, pf, pk, pm), "bound": "tensor",
                          "achieved": round(achieved, 2), "peak": round(bf16_peak / 2, 1), "unit": "TFLOP/s",
                          "frac": round(achieved / (bf16_peak / 2), 4), "traffic": traffic,
                          "peak_note": ("TF32 operands: peak = 1/2 x measured bf16 burst (%s)" % ("of measured" if peaks else "of fallback")),
@@ -414,7 +520,11 @@ def run_ours(args):
                          "flops_per_launch": flops},
             "clocks": clocks,
         }
+        if in_sync is not None:
+            line["replicas_in_sync"] = in_sync
         if world == 1:
+            if args.workload == "sun_train" and not args.no_inference:
+                line["inference"] = measure_inference(pkg, args, rank, flush)
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -448,8 +558,10 @@ def main():
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
-    ap.add_argument("--workload", default="inference", choices=["inference", "sky", "trunk", "trunk_train"],
-                    help="inference: full generator inference (default); sky: its sky branch; trunk: the DA residual trunk alone")
+    ap.add_argument("--workload", default="sun_train", choices=["sun_train", "inference", "sky", "trunk", "trunk_train"],
+                    help="sun_train: the sun-position pre-train step, BASELINE configs[1] (default; the line also carries the full-inference "
+                         "throughput, configs[0]); inference: full generator inference; sky: its sky branch; trunk: the DA residual trunk alone")
+    ap.add_argument("--no-inference", action="store_true", help="sun_train: skip the secondary full-inference measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

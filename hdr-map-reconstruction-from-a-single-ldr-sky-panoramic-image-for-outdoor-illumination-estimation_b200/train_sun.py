@@ -51,7 +51,10 @@ class SunTrainer:
         self.flat_m = torch.zeros_like(self.flat_w)
         self.flat_v = torch.zeros_like(self.flat_w)
         self.grads, off = {}, 0
+        self._fc_offset = None                                      # start of the Dense variables (99 % of the bytes) in the flat buffers
         for (o, a), n, p, s in zip(owners, sizes, pad, shapes):
+            if o is net.fc1 and self._fc_offset is None:
+                self._fc_offset = off
             vw = self.flat_w[off:off + n].view(s)
             vw.copy_(getattr(o, a))
             setattr(o, a, vw)                                       # the layer now reads the flat buffer
@@ -125,6 +128,11 @@ class SunTrainer:
         g_z1 = net.fc2.backward_data(g_z2, act=actv1_s)
         check(LIB.sky_dense_bwd_filter(flat.data_ptr(), g_z1.data_ptr(), self._g(net.fc1, "kernel").data_ptr(),
                                        self._g(net.fc1, "bias").data_ptr(), B, flat.shape[1], n_fc, _stream()))
+        # data-parallel: the Dense gradients (201 MB at 32x128) are complete here, before any conv gradient — their all-reduce is
+        # started now and runs on NCCL's stream under the rest of the backward pass
+        fc_work = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            fc_work = dist.all_reduce(self.flat_g[self._fc_offset:], op=dist.ReduceOp.SUM, async_op=True)
         g = net.fc1.backward_data(g_z1)
         g = maxpool2d_backward(acts[2], g.view(pool_shape))
         g = self._layer_backward(net.sunlayer3, g, True)
@@ -133,7 +141,9 @@ class SunTrainer:
         g = maxpool2d_backward(acts[0], g)
         self._layer_backward(net.sunlayer1, g, False)
         # ---- optimizer (:258) ----
-        allreduce_flat_(self.flat_g)                                              # data-parallel: the step's single collective
+        if fc_work is not None:
+            allreduce_flat_(self.flat_g[:self._fc_offset])                        # conv / norm gradients (1 MB)
+            fc_work.wait()
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.apply_gradients(world)
         return pred, sungt, cams

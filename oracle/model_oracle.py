@@ -498,7 +498,7 @@ def generator_test_step(ldr, hdr_t, sunpose_gt, wg, ws, wd, vgg_dict, k=3, thres
     return out
 
 
-def sun_train_step_grads(ldr, sunpose_gt, ws, acc_dtype=torch.float64):
+def sun_train_step_grads(ldr, sunpose_gt, ws, acc_dtype=torch.float64, with_gradcam=False):
     """train_sun.sun_train_step (train_sun.py:220-264) up to the gradients: loss = KLDivergence(gt, sm) + sum_l mean|DoG_l(pred) - DoG_l(gt)|,
     autograd w.r.t. every variable of the sun-position network (distortion-aware wiring).  Returns (loss, grads in the layout of ws)."""
     dt = acc_dtype
@@ -516,7 +516,12 @@ def sun_train_step_grads(ldr, sunpose_gt, ws, acc_dtype=torch.float64):
     x = O._as_t(ldr).to(dt)
     gt = O._as_t(sunpose_gt).to(dt)
     B, H, W, _ = x.shape
-    sm, _ = sunpose_estimation(x, w, distortion_aware=True, acc_dtype=dt)
+    if with_gradcam:
+        x = x.clone().requires_grad_(True)
+    sm, acts = sunpose_estimation(x, w, distortion_aware=True, acc_dtype=dt)
+    if with_gradcam:        # train_sun.py:231-240 (outside the tape: outputs only)
+        y_c = torch.gather(sm, 1, gt.argmax(dim=1, keepdim=True))[:, 0]
+        cams = [grad_cam_layer(y_c, a).detach() for a in acts]
     loss = kl_divergence(gt, sm) + dog_l1(sm.reshape(B, H, W, 1), gt.reshape(B, H, W, 1))
     flat = [w[n][k] for n in ("sunlayer1", "sunlayer2", "sunlayer3") for k in sorted(w[n])] + [t for n in ("fc1", "fc2") for t in w[n]]
     grads = torch.autograd.grad(loss, flat)
