@@ -107,6 +107,55 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_dgrad_kernel(const BwdP
         if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
         return;
     }
+    // Scatter of one drained k-block.  The kernel is bound by the L2 reduction traffic (ncu: 73 % of the L2 peak on a 7x7 layer), and
+    // half of it is redundant: along a row the right-hand corner of pixel j is the left-hand corner of pixel j + 1 (the offsets
+    // depend on the row and the tap only), so lane l adds its left neighbour's right-corner contribution — passed down by warp
+    // shuffles — to its own left-corner one and issues ONE vector reduction per 16 bytes and corner row instead of two.  Lanes whose
+    // neighbour does not line up (360-degree wrap, zenith row, row ends, image edge) keep their own reduction.
+    auto drain = [&](int pk) {
+        const int pt = (kb_lo + pk) / p.CC, pcc = (kb_lo + pk) % p.CC;
+        mbar_wait(bar0 + 8 * (pk & 1), (pk >> 1) & 1);
+        tc_fence_after();
+        if (warp < 4) {
+            const int lane = tid & 31;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (pk & 1) * 32 + ((uint32_t)(warp * 32) << 16), r);
+            tmem_ld_wait();
+            CornerRef cr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { cr.off[c] = -1; cr.w[c] = 0.f; }
+            if (m_ok) {
+                const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + pt);
+                const Sample s = da_sample(i, j, pt / p.k, pt % p.k, yx.x, yx.y, p.in_h, p.in_w);
+                cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (cr.w[c] == 0.f) cr.off[c] = -1;
+            }
+#pragma unroll
+            for (int rowc = 0; rowc < 2; ++rowc) {          // corner rows: (y0: corners 0, 1), (y1: corners 2, 3)
+                const int offL = cr.off[2 * rowc], offR = cr.off[2 * rowc + 1];
+                const float wL = cr.w[2 * rowc], wR = cr.w[2 * rowc + 1];
+                const int nbR = __shfl_up_sync(0xffffffffu, offR, 1);                   // left neighbour's right corner
+                const bool take = lane > 0 && offL >= 0 && nbR == offL;                 // I carry my left neighbour's right corner
+                const bool given = __shfl_down_sync(0xffffffffu, (int)take, 1) != 0 && lane < 31;   // my right corner is carried
+                float *dstL = p.dx + (offL >= 0 ? offL : 0) + pcc * 32, *dstR = p.dx + (offR >= 0 ? offR : 0) + pcc * 32;
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float vr[4], vl[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        vr[u] = wR * __uint_as_float(r[q + u]);
+                        const float nb = __shfl_up_sync(0xffffffffu, vr[u], 1);
+                        vl[u] = wL * __uint_as_float(r[q + u]) + (take ? nb : 0.f);
+                    }
+                    if (offL >= 0) red_add_v4(dstL + q, vl[0], vl[1], vl[2], vl[3]);
+                    if (offR >= 0 && !given) red_add_v4(dstR + q, vr[0], vr[1], vr[2], vr[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    };
     for (int kb = 0; kb < KB; ++kb) {
         const int t = (kb_lo + kb) / p.CC, cc = (kb_lo + kb) % p.CC;
         uint8_t *bt = b_tile + (kb & 1) * p.FC * 4096;
@@ -130,59 +179,11 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_dgrad_kernel(const BwdP
                               umma_desc_kmajor_sw128(smem_u32(bt + a * 4096) + ks * 32), idesc, (a | ks) != 0);
             umma_commit(bar0 + 8 * (kb & 1));
         }
-        // drain the PREVIOUS k-block while this one's MMAs run (its barrier phase: use count of that buffer)
-        if (kb > 0) {
-            const int pk = kb - 1, pt = (kb_lo + pk) / p.CC, pcc = (kb_lo + pk) % p.CC;
-            mbar_wait(bar0 + 8 * (pk & 1), (pk >> 1) & 1);
-            tc_fence_after();
-            if (warp < 4) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (pk & 1) * 32 + ((uint32_t)(warp * 32) << 16), r);
-                tmem_ld_wait();
-                if (m_ok) {
-                    const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + pt);
-                    const Sample s = da_sample(i, j, pt / p.k, pt % p.k, yx.x, yx.y, p.in_h, p.in_w);
-                    const CornerRef cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (cr.off[c] < 0 || cr.w[c] == 0.f) continue;
-                        float *dst = p.dx + cr.off[c] + pcc * 32;
-#pragma unroll
-                        for (int q = 0; q < 32; q += 4)
-                            red_add_v4(dst + q, cr.w[c] * __uint_as_float(r[q]), cr.w[c] * __uint_as_float(r[q + 1]),
-                                       cr.w[c] * __uint_as_float(r[q + 2]), cr.w[c] * __uint_as_float(r[q + 3]));
-                    }
-                }
-            }
-            tc_fence_before();
-        }
+        // drain the PREVIOUS k-block while this one's MMAs run
+        if (kb > 0) drain(kb - 1);
         __syncthreads();
     }
-    {   // drain the last k-block
-        const int pk = KB - 1, pt = (kb_lo + pk) / p.CC, pcc = (kb_lo + pk) % p.CC;
-        mbar_wait(bar0 + 8 * (pk & 1), (pk >> 1) & 1);
-        tc_fence_after();
-        if (warp < 4) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + (pk & 1) * 32 + ((uint32_t)(warp * 32) << 16), r);
-            tmem_ld_wait();
-            if (m_ok) {
-                const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + pt);
-                const Sample s = da_sample(i, j, pt / p.k, pt % p.k, yx.x, yx.y, p.in_h, p.in_w);
-                const CornerRef cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (cr.off[c] < 0 || cr.w[c] == 0.f) continue;
-                    float *dst = p.dx + cr.off[c] + pcc * 32;
-#pragma unroll
-                    for (int q = 0; q < 32; q += 4)
-                        red_add_v4(dst + q, cr.w[c] * __uint_as_float(r[q]), cr.w[c] * __uint_as_float(r[q + 1]),
-                                   cr.w[c] * __uint_as_float(r[q + 2]), cr.w[c] * __uint_as_float(r[q + 3]));
-                }
-            }
-        }
-        tc_fence_before();
-    }
+    drain(KB - 1);   // the last k-block
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_wgrad_kernel(const BwdP
     uint8_t *b_tile = smem + 4 * 16384;         // FC x 16 KB
     uint64_t *bars = reinterpret_cast<uint64_t *>(b_tile + p.FC * 16384);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 1);
+    CornerRef *ctab = reinterpret_cast<CornerRef *>(b_tile + p.FC * 16384 + 64);      // [4 taps][128 pixels]
     const uint32_t bar0 = smem_u32(bars);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int part = blockIdx.x, tg = blockIdx.y, cc = blockIdx.z;
@@ -232,19 +234,32 @@ __global__ void __launch_bounds__(BWD_THREADS) da_conv2d_wgrad_kernel(const BwdP
             u.x = f32_to_tf32_rna(v.x); u.y = f32_to_tf32_rna(v.y); u.z = f32_to_tf32_rna(v.z); u.w = f32_to_tf32_rna(v.w);
             *reinterpret_cast<uint4 *>(b_tile + (c4 / 8) * 16384 + sw128_b32_offset(row, c4 % 8)) = u;
         }
-        // ---- A: re-gather Pix for the group's taps, 32 channels of chunk cc (exact geometry, corners from global/L2) ----
+        // ---- geometry of the tile: one (tap, pixel) sample per table entry, computed once and shared by the eight threads that
+        //      gather the entry's eight 16-byte channel chunks (the sampling arithmetic used to be redone by each of them: 58 % of
+        //      the kernel's issue slots on a 7x7 layer) ----
+        for (int e = tid; e < 4 * BLOCK_M; e += BWD_THREADS) {
+            const int tl = e / BLOCK_M, row = e % BLOCK_M, t = t_first + tl, m = m0 + row;
+            CornerRef cr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { cr.off[c] = -1; cr.w[c] = 0.f; }
+            if (t < p.k2 && m < p.M) {
+                const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
+                const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
+                const Sample s = da_sample(i, j, t / p.k, t % p.k, yx.x, yx.y, p.in_h, p.in_w);
+                cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+            }
+            ctab[e] = cr;
+        }
+        __syncthreads();
+        // ---- A: re-gather Pix for the group's taps, 32 channels of chunk cc (corners from global/L2) ----
         for (int tl = 0; tl < 4; ++tl) {
             const int t = t_first + tl;
             if (t >= p.k2) break;
             for (int r = 0; r < BLOCK_M / 32; ++r) {
                 const int row = row_base + 32 * r;
-                const int m = m0 + row;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < p.M) {
-                    const int j = m % p.w, i = (m / p.w) % p.h, b_img = m / (p.w * p.h);
-                    const float2 yx = __ldg(reinterpret_cast<const float2 *>(p.offsets) + (size_t)i * p.k2 + t);
-                    const Sample s = da_sample(i, j, t / p.k, t % p.k, yx.x, yx.y, p.in_h, p.in_w);
-                    const CornerRef cr = da_corners(s, b_img, p.h, p.w, p.C, p.ph0, p.pw0);
+                {
+                    const CornerRef cr = ctab[tl * BLOCK_M + row];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (cr.off[c] < 0) continue;
@@ -374,7 +389,7 @@ extern "C" int sky_da_conv2d_bwd_filter(const float *x, const float *dy, const f
     if (parts > ntiles) parts = ntiles;
     p.tiles_per_part = (ntiles + parts - 1) / parts;
     p.parts = (ntiles + p.tiles_per_part - 1) / p.tiles_per_part;
-    const int smem = 4 * 16384 + p.FC * 16384 + 64 + 1024;
+    const int smem = 4 * 16384 + p.FC * 16384 + 64 + 4 * BLOCK_M * (int)sizeof(CornerRef) + 1024;
     static bool configured = false;
     if (!configured) {
         SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

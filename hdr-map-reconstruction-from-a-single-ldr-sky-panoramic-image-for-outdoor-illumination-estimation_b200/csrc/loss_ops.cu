@@ -182,7 +182,22 @@ __global__ void dog_l1_kernel(const float *__restrict__ base_a, const float *__r
 __global__ void adam_kernel(float *__restrict__ w, float *__restrict__ m, float *__restrict__ v, const float *__restrict__ g, long n,
                             float lr_t, float b1, float b2, float eps, float grad_scale)
 {
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    // 7 streams of n floats (4 reads, 3 writes): 128-bit accesses; the tail (n % 4) is handled by the first threads
+    const long n4 = n / 4;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n4; e += (long)gridDim.x * blockDim.x) {
+        const float4 gv = __ldg(reinterpret_cast<const float4 *>(g) + e);
+        float4 mv = reinterpret_cast<float4 *>(m)[e], vv = reinterpret_cast<float4 *>(v)[e], wv = reinterpret_cast<float4 *>(w)[e];
+        const float ga[4] = { gv.x * grad_scale, gv.y * grad_scale, gv.z * grad_scale, gv.w * grad_scale };
+        float *mp = &mv.x, *vp = &vv.x, *wp = &wv.x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            mp[u] = b1 * mp[u] + (1.f - b1) * ga[u];
+            vp[u] = b2 * vp[u] + (1.f - b2) * ga[u] * ga[u];
+            wp[u] -= lr_t * mp[u] / (sqrtf(vp[u]) + eps);
+        }
+        reinterpret_cast<float4 *>(m)[e] = mv; reinterpret_cast<float4 *>(v)[e] = vv; reinterpret_cast<float4 *>(w)[e] = wv;
+    }
+    for (long e = 4 * n4 + blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const float gv = g[e] * grad_scale;
         const float mm = b1 * m[e] + (1.f - b1) * gv, vv = b2 * v[e] + (1.f - b2) * gv * gv;
         m[e] = mm; v[e] = vv;
@@ -280,7 +295,8 @@ extern "C" int sky_adam_step(float *w, float *m, float *v, const float *g, long 
     SKY_REQUIRE(w && m && v && g && n > 0 && step >= 1, SKY_ERR_INVALID, "bad arguments");
     // Keras: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
-    adam_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
+    SKY_REQUIRE((((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0, SKY_ERR_INVALID, "w, m, v, g must be 16-byte aligned");
+    adam_kernel<<<blocks_for((n + 3) / 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }

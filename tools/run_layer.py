@@ -16,6 +16,20 @@ elif kind == "da":
     layer = pkg.conv2d(F, kernel_size=k)
     x = torch.randn(B, h, w, C, device="cuda")
     fn = lambda: layer(x)
+elif kind == "dgrad":
+    B, h, w, C, F, k = a
+    layer = pkg.conv2d(F, kernel_size=k)
+    x = torch.randn(B, h, w, C, device="cuda")
+    layer(x)
+    dy = torch.randn(B, h, w, F, device="cuda")
+    fn = lambda: pkg.distortion_aware_ops.conv2d_backward(layer, x, dy, need_dw=False)
+elif kind == "wgrad":
+    B, h, w, C, F, k = a
+    layer = pkg.conv2d(F, kernel_size=k)
+    x = torch.randn(B, h, w, C, device="cuda")
+    layer(x)
+    dy = torch.randn(B, h, w, F, device="cuda")
+    fn = lambda: pkg.distortion_aware_ops.conv2d_backward(layer, x, dy, need_dx=False)
 else:
     B, h, w, C, F, k, s = a
     layer = pkg.ops.conv2d(output_channels=F, k_h=k, k_w=k, strides=s)
