@@ -501,7 +501,7 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("k7" if args.workload == "sun_train" else "trunk", {}).get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": round(world * B / (t_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
