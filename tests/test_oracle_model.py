@@ -1,0 +1,91 @@
+"""CPU checks of the oracle's restatement of the sun branch and the train / test tail against independent formulations (numpy /
+scipy / closed forms), so that the GPU parity tests compare against something that has itself been pinned.  No GPU needed."""
+import numpy as np
+import torch
+from scipy import ndimage
+
+from oracle import da_oracle as O
+from oracle import model_oracle as M
+
+
+def test_apply_rf_is_piecewise_linear_interpolation():
+    rng = np.random.default_rng(0)
+    k = 1024
+    crf = np.sort(rng.uniform(0, 1, (3, k)), axis=1).astype(np.float64)
+    x = rng.uniform(0, 1, (3, 50)).astype(np.float64)
+    got = M.apply_rf(torch.from_numpy(x), torch.from_numpy(crf)).numpy()
+    want = np.stack([np.interp(x[b], np.linspace(0, 1, k), crf[b]) for b in range(3)])
+    assert np.abs(got - want).max() < 1e-12
+    assert np.allclose(M.apply_rf(torch.ones(3, 1, dtype=torch.float64), torch.from_numpy(crf)).numpy()[:, 0], crf[:, -1])   # x = 1: clamped neighbour
+
+
+def test_log_codec_round_trip_and_kl():
+    x = torch.linspace(0, 3e4, 1000, dtype=torch.float64)
+    assert torch.allclose(M.hdr_log_decompression(M.hdr_log_compression(x)), x, rtol=1e-10, atol=1e-9)
+    assert abs(float(M.hdr_log_compression(torch.tensor([1.0], dtype=torch.float64))) - 1.0) < 1e-12          # log(11)/log(11)
+    p = torch.softmax(torch.randn(4, 100, dtype=torch.float64), -1)
+    q = torch.softmax(torch.randn(4, 100, dtype=torch.float64), -1)
+    want = torch.nn.functional.kl_div(q.log(), p, reduction="batchmean")
+    assert abs(float(M.kl_divergence(p, q)) - float(want)) < 1e-12
+    assert abs(float(M.kl_divergence(p, p))) < 1e-15
+
+
+def test_gaussian_filter_and_dog_against_scipy():
+    rng = np.random.default_rng(1)
+    img = rng.standard_normal((1, 12, 20, 2))
+    for sigma in (1.2489996, 3.0900156):
+        g = np.exp(-np.array([1.0, 0.0, 1.0]) / (2 * sigma * sigma))
+        g /= g.sum()
+        want = np.stack([ndimage.correlate(img[0, :, :, c], np.outer(g, g), mode="mirror") for c in range(2)], -1)[None]   # 'mirror' == tf REFLECT
+        got = M.gaussian_filter2d(torch.from_numpy(img), sigma).numpy()
+        assert np.abs(got - want).max() < 1e-12
+    # DoG is linear: DoG(a) - DoG(b) == DoG(a - b) (the identity the fused L1 kernel relies on to rounding)
+    a, b = torch.from_numpy(rng.standard_normal((1, 8, 8, 1))), torch.from_numpy(rng.standard_normal((1, 8, 8, 1)))
+    for da, db, dd in zip(M.dog(a), M.dog(b), M.dog(a - b)):
+        assert torch.allclose(da - db, dd, atol=1e-12)
+    # x2 bilinear resize with half-pixel centres == scipy zoom of order 1 on the half-pixel grid
+    up = O.resize_bilinear(a, 16, 16).numpy()[0, :, :, 0]
+    assert abs(up[0, 0] - float(a[0, 0, 0, 0])) < 1e-12 and abs(up[1, 1] - float(0.75 * 0.75 * a[0, 0, 0, 0] + 0.75 * 0.25 * (a[0, 0, 1, 0] + a[0, 1, 0, 0]) + 0.0625 * a[0, 1, 1, 0])) < 1e-12
+
+
+def test_grad_cam_layer_closed_form_and_pool_routing():
+    # y_c = sum_c v_c * mean_hw(A_c)  =>  d y_c / dA = v_c / (h w) everywhere, weights = v / (h w), cam = relu(sum_c v_c A_c) / (h w)
+    rng = np.random.default_rng(2)
+    A = torch.from_numpy(rng.standard_normal((2, 4, 6, 5))).requires_grad_(True)
+    v = torch.from_numpy(rng.standard_normal(5))
+    y_c = (A.mean(dim=(1, 2)) * v).sum(-1)
+    cam = M.grad_cam_layer(y_c, A)
+    want = torch.relu((A.detach() * v).sum(-1) / 24.0).unsqueeze(-1)
+    assert torch.allclose(cam, want, atol=1e-14)
+    # max-pool gradient goes to the FIRST maximum of a window in scan order (TensorFlow MaxPoolGrad; ReLU outputs tie at 0 all the time)
+    x = torch.zeros(1, 2, 2, 1, dtype=torch.float64, requires_grad=True)
+    M.maxpool2x2_same(x).sum().backward()
+    assert x.grad.flatten().tolist() == [1.0, 0.0, 0.0, 0.0]
+
+
+def test_batch_norm_fold_identity_and_valid_conv_is_cropped_same():
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal((2, 8, 16, 6)))
+    kern = torch.from_numpy(rng.standard_normal((4, 4, 6, 5)) * 0.1)
+    g, b, m, v = (torch.from_numpy(a) for a in (1 + 0.1 * rng.standard_normal(5), rng.standard_normal(5), rng.standard_normal(5), rng.uniform(0.5, 2, 5)))
+    zero = torch.zeros(5, dtype=torch.float64)
+    ref = M.batch_norm_inference(M.conv2d_same(x, kern, zero, stride=2, acc_dtype=torch.float64), g, b, m, v)
+    s = g * torch.rsqrt(v + 1e-3)
+    folded = M.conv2d_same(x, kern * s, b - m * s, stride=2, acc_dtype=torch.float64)      # what sky_bn_fold feeds the conv kernel
+    assert torch.allclose(ref, folded, atol=1e-12)
+    # Conv2D(1, 4) VALID == the SAME conv cropped by one pixel in front (what discriminator.model does on the GPU)
+    k1 = torch.from_numpy(rng.standard_normal((4, 4, 6, 1)))
+    same = M.conv2d_same(x, k1, torch.zeros(1, dtype=torch.float64), acc_dtype=torch.float64)
+    valid = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), k1.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+    assert torch.allclose(same[:, 1:8 - 2, 1:16 - 2, :], valid, atol=1e-12)
+
+
+def test_generator_inference_oracle_shapes_and_ranges():
+    rng = np.random.default_rng(4)
+    H, W = 32, 128
+    ldr = (np.round(255 * rng.uniform(0, 1, (1, H, W, 3))) / 255).astype(np.float32)
+    d = M.generator_inference(ldr, M.random_full_generator_weights(3, H, W), M.random_sunpose_weights(5, H, W), details=True)
+    assert tuple(d["y_lin"].shape) == (1, H, W, 3) and bool(torch.isfinite(d["y_lin"]).all()) and float(d["y_lin"].min()) >= 0
+    assert abs(float(d["sm"].sum()) - 1) < 1e-5 and float(d["alpha"].min()) >= 0 and float(d["alpha"].max()) <= 1
+    assert [tuple(c.shape) for c in d["cams"]] == [(1, H, W, 1), (1, H // 2, W // 2, 1), (1, H // 4, W // 4, 1)]
+    assert float(d["sun_rad_gamma"].max()) <= float(M.hdr_log_compression(torch.tensor(30000.0))) + 1e-6          # the 30000 clamp
