@@ -259,7 +259,7 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     value = sample / dt
-    METRIC = METRICS[args.workload]
+    METRIC = METRICS[args.workload].replace("32x128", f"{args.height}x{args.width}")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -323,7 +323,7 @@ def run_ours(args):
 
     B, H, W = args.batch, args.height, args.width
     h, w = H // 4, W // 4
-    METRIC = METRICS[args.workload]
+    METRIC = METRICS[args.workload].replace("32x128", f"{args.height}x{args.width}")
     trainer = None
     if args.workload == "trunk_train":
         trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
@@ -551,7 +551,7 @@ def cpu_baseline(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="panoramas per GPU per step")

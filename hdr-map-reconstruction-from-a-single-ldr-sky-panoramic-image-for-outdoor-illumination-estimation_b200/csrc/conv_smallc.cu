@@ -177,6 +177,121 @@ da_conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ o
     smallc_epilogue(acc, bias, y, stats, red, b, i, j, h, w, F, flags, slope);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Plain SAME stride-1 convolution with very few filters (F <= 4): conv1_f / conv1_u of the decoders (generator.py:76,85: 7x7, 32 -> 3).
+// 1.2 GFLOP at B = 32 — the layer is all input reuse, and on the tensor-core path its cost is the 49 producer / MMA hand-shakes per
+// tile (170 us).  Here a CTA stages the (8 + k - 1) x (32 + k - 1) input patch of an 8 x 32 output tile in shared memory (pixel stride
+// C + 4 floats: the 128-bit reads of 32 adjacent pixels spread over all banks) and the kernel variable as [tap][c][4]; a thread owns two
+// output pixels (rows ty and ty + 4), so one broadcast weight read feeds six FMAs.  fp32 FMA on the TF32-rounded packed weights.
+// Epilogue: bias, LeakyReLU, residual, ReLU, alpha blend (SKY_EPI_SUN_BLEND), log decompression — the whole tail of generator inference.
+constexpr int SF_TH = 8, SF_TW = 32, SF_THREADS = 128;
+
+__global__ void __launch_bounds__(SF_THREADS)
+conv2d_smallf_kernel(const float *__restrict__ x, const float *__restrict__ packed, const float *__restrict__ bias,
+                     const float *__restrict__ residual, const float *__restrict__ aux, float *__restrict__ y, int B, int h, int w, int C,
+                     int F, int Fp, int k, int flags, float slope, float threshold)
+{
+    extern __shared__ __align__(16) float sf[];
+    const int k2 = k * k, r = k / 2, PW = SF_TW + k - 1, PH = SF_TH + k - 1, PS = C + 4;
+    float *wts = sf;                              // [k2][C][4]
+    float *patch = sf + (size_t)k2 * C * 4;       // [PH][PW][PS]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int tiles_x = (w + SF_TW - 1) / SF_TW, tiles_y = (h + SF_TH - 1) / SF_TH, ntiles = tiles_x * tiles_y * B;
+
+    // kernel variable from the packed tensor-core image: k-block (c / 32) * k2 + tap, row f, element c % 32 (SWIZZLE_128B)
+    for (int e = tid; e < k2 * C; e += SF_THREADS) {
+        const int t = e / C, c = e % C;
+        int kb = (c / 32) * k2 + t, kk = c & 31;                       // chunk-major k-blocks when C % 32 == 0 (da_pack_weights_kernel)
+        if (C % 32 != 0) { kb = (t * C + c) >> 5; kk = (t * C + c) & 31; }
+        const float *tile = packed + (size_t)kb * Fp * 32;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float *wp = &wv.x;
+        for (int f = 0; f < F; ++f) wp[f] = __ldg(tile + (sw128_offset((uint32_t)f, (uint32_t)(kk >> 2)) >> 2) + (kk & 3));
+        reinterpret_cast<float4 *>(wts)[e] = wv;
+    }
+    const int c4n = C / 4;
+    // persistent over tiles: the unpacked kernel variable is staged once per CTA
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y), trem = tile % (tiles_x * tiles_y);
+    const int i0 = (trem / tiles_x) * SF_TH, j0 = (trem % tiles_x) * SF_TW;
+    __syncthreads();                              // the previous tile's patch is no longer being read
+    for (int e = tid; e < PH * PW * c4n; e += SF_THREADS) {
+        const int c4 = e % c4n, px = (e / c4n) % PW, py = e / (c4n * PW);
+        const int yy = i0 + py - r, xx = j0 + px - r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(reinterpret_cast<const float4 *>(x + (((size_t)b * h + yy) * w + xx) * C) + c4);
+        *reinterpret_cast<float4 *>(patch + (size_t)(py * PW + px) * PS + 4 * c4) = v;
+    }
+    __syncthreads();
+
+    float acc[2][4] = { { 0.f, 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f, 0.f } };
+    for (int a = 0; a < k; ++a)
+        for (int bb = 0; bb < k; ++bb) {
+            const float *p0 = patch + (size_t)((ty + a) * PW + tx + bb) * PS;
+            const float *p1 = p0 + (size_t)4 * PW * PS;                      // output row ty + 4
+            const float4 *wt = reinterpret_cast<const float4 *>(wts) + (size_t)(a * k + bb) * C;
+            for (int c4 = 0; c4 < c4n; ++c4) {
+                const float4 v0 = *reinterpret_cast<const float4 *>(p0 + 4 * c4), v1 = *reinterpret_cast<const float4 *>(p1 + 4 * c4);
+                const float a0[4] = { v0.x, v0.y, v0.z, v0.w }, a1[4] = { v1.x, v1.y, v1.z, v1.w };
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 wv = wt[4 * c4 + u];
+                    acc[0][0] = fmaf(a0[u], wv.x, acc[0][0]); acc[0][1] = fmaf(a0[u], wv.y, acc[0][1]);
+                    acc[0][2] = fmaf(a0[u], wv.z, acc[0][2]); acc[0][3] = fmaf(a0[u], wv.w, acc[0][3]);
+                    acc[1][0] = fmaf(a1[u], wv.x, acc[1][0]); acc[1][1] = fmaf(a1[u], wv.y, acc[1][1]);
+                    acc[1][2] = fmaf(a1[u], wv.z, acc[1][2]); acc[1][3] = fmaf(a1[u], wv.w, acc[1][3]);
+                }
+            }
+        }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int i = i0 + ty + 4 * half, j = j0 + tx;
+        if (i >= h || j >= w) continue;
+        const size_t m = ((size_t)b * h + i) * w + j;
+        float v[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            float val = acc[half][f];
+            if (f < F) {
+                val += __ldg(bias + f);
+                if (flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * slope;
+                if (flags & SKY_EPI_RESIDUAL) val += __ldg(residual + m * F + f);
+                if (flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
+            }
+            v[f] = val;
+        }
+        if (flags & SKY_EPI_SUN_BLEND) sun_blend3(v, aux + m * 3, threshold);            // F == 3
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            if (f < F) {
+                if (flags & SKY_EPI_LOG_DECOMPRESS) v[f] = (expf(v[f] * 2.3978953f) - 1.f) / 10.f;
+                y[m * F + f] = v[f];
+            }
+    }
+    }   // tiles
+}
+
+// Returns SKY_ERR_UNSUPPORTED (without an error text) when the layer is outside what this kernel covers.
+int launch_fwd_smallf(const FwdArgs &a)
+{
+    if (a.F > 4 || a.C % 4 != 0 || a.k % 2 == 0 || a.plain_stride != 1 || a.stats != nullptr || a.math_mode != SKY_MATH_TF32 ||
+        (a.flags & SKY_EPI_FORCE_DIRECT) || a.ldF > 0)
+        return SKY_ERR_UNSUPPORTED;
+    const size_t smem = ((size_t)a.k * a.k * a.C * 4 + (size_t)(SF_TH + a.k - 1) * (SF_TW + a.k - 1) * (a.C + 4)) * sizeof(float);
+    if (smem > 110 * 1024) return SKY_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        SKY_CHECK_CUDA(cudaFuncSetAttribute(conv2d_smallf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        configured = true;
+    }
+    const int ntiles = ((a.w + SF_TW - 1) / SF_TW) * ((a.h + SF_TH - 1) / SF_TH) * a.B;
+    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;          // two resident CTAs per SM
+    conv2d_smallf_kernel<<<grid, SF_THREADS, smem, a.stream>>>(a.x, a.packed, a.bias, a.residual, a.aux, a.y, a.B, a.h, a.w, a.C, a.F, f_pad_of(a.F),
+                                                               a.k, a.flags, a.slope, a.threshold);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
+
 static int launch_fwd_smallc_da(const FwdArgs &a, const float *kernel)
 {
     if (a.C > 4 || a.F > SC_FMAX || a.k > 11 || a.offsets_host == nullptr || (a.flags & ~SKY_EPI_LEAKY_RELU) ||

@@ -55,6 +55,8 @@ __device__ __forceinline__ void sun_blend3(float v[3], const float *__restrict__
 int launch_fwd_direct(const FwdArgs &a);
 // halo of input pixels (relative to an output pixel) the taps of a distortion-aware layer touch (da_conv_fwd_band.cu)
 void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi);
+// fp32 CUDA-core kernel for plain stride-1 layers with F <= 4 filters (conv_smallc.cu); SKY_ERR_UNSUPPORTED when it does not apply
+int launch_fwd_smallf(const FwdArgs &a);
 // band-staged persistent kernel (C % 32 == 0): input band in shared memory via TMA.  Returns SKY_ERR_UNSUPPORTED
 // (without setting the error text) when no tiling fits, so the caller can take the direct kernel.
 int launch_fwd_band(const FwdArgs &a);

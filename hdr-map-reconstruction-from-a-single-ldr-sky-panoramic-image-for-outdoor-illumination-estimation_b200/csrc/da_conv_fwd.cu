@@ -651,6 +651,10 @@ static int conv2d_plain(FwdArgs a, int stride)
     SKY_REQUIRE((long)a.B * a.h * a.w * (long)(a.C > a.F ? a.C : a.F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
     a.offsets = nullptr; a.offsets_host = nullptr; a.plain_stride = stride;
     const int F = a.F;
+    if (F <= 4) {
+        int rc = launch_fwd_smallf(a);          // conv1_f / conv1_u: too few filters for the tensor-core pipeline to pay
+        if (rc != SKY_ERR_UNSUPPORTED) return rc;
+    }
     if (F <= 256) {
         if ((a.C % BLOCK_K) == 0 && !(a.flags & SKY_EPI_FORCE_DIRECT)) {
             int rc = launch_fwd_band(a);        // identity sampler in the band-staged kernel (any stride the band fits)

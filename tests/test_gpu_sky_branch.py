@@ -73,3 +73,21 @@ def test_sky_branch_inference_vs_oracle(pkg, mode, tol_log, tol_lin):
     assert got_log.shape == (B, H, W, 3)
     assert rel_l2(got_log, want_log) <= tol_log, ("log", rel_l2(got_log, want_log))
     assert rel_l2(got_lin, want_lin) <= tol_lin, ("lin", rel_l2(got_lin, want_lin))
+
+
+@pytest.mark.parametrize("C,F,k,shape", [(32, 3, 7, (2, 32, 128)), (32, 3, 3, (1, 13, 45)), (8, 1, 5, (2, 9, 33)), (64, 4, 3, (1, 16, 64))])
+def test_small_filter_count_conv(pkg, C, F, k, shape):
+    """Plain stride-1 layers with F <= 4 filters (conv1_f / conv1_u) take the fp32 CUDA-core kernel that reads the TF32-rounded packed
+    weights: ragged tiles, C % 32 != 0 packing order, every epilogue flag.  2e-3 relative L2 after the exponential of the decompression (weights rounded to TF32, fp32 FMA)."""
+    rng = np.random.default_rng(C + F + k)
+    B, h, w = shape
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    kern = (rng.standard_normal((k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    bias = rng.standard_normal(F).astype(np.float32)
+    res = rng.uniform(0, 1, (B, h, w, F)).astype(np.float32)
+    layer = pkg.ops.conv2d(output_channels=F, k_h=k, k_w=k, strides=1, kernel_initializer=kern, bias_initializer=bias)
+    got = layer(torch.from_numpy(x).cuda(), leaky_slope=0.1, residual=torch.from_numpy(res).cuda(), relu=True, log_decompress=True).cpu().numpy()
+    y = M.conv2d_same(x, kern, bias, acc_dtype=torch.float64)
+    want = M.hdr_log_decompression(torch.relu(M.leaky_relu(y, 0.1) + torch.from_numpy(res).double())).numpy()
+    r = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert r < 2e-3, r
