@@ -255,13 +255,16 @@ da_smallc_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ of
             dys[e] = (x0 + px < w && ff < F) ? __ldg(dy + (((size_t)b * h + i) * w + x0 + px) * F + ff) : 0.f;
         }
         __syncthreads();
-        for (int px = 0; px < SW_THREADS; ++px) {
-            const float d = dys[px * SW_F + f];
-            if (kq == 0) bacc += d;
+        for (int px = 0; px < SW_THREADS; px += 4) {            // four pixels per broadcast 128-bit read of the blended samples
+            const float d0 = dys[px * SW_F + f], d1 = dys[(px + 1) * SW_F + f], d2 = dys[(px + 2) * SW_F + f], d3 = dys[(px + 3) * SW_F + f];
+            if (kq == 0) bacc += (d0 + d1) + (d2 + d3);
 #pragma unroll
             for (int q = 0; q < MAXO; ++q) {
                 const int kc = kq + 4 * q;
-                if (kc < KC) acc[q] = fmaf(pixs[(size_t)kc * SW_THREADS + px], d, acc[q]);
+                if (kc < KC) {
+                    const float4 pv = *reinterpret_cast<const float4 *>(pixs + (size_t)kc * SW_THREADS + px);
+                    acc[q] = fmaf(pv.w, d3, fmaf(pv.z, d2, fmaf(pv.y, d1, fmaf(pv.x, d0, acc[q]))));
+                }
             }
         }
     }

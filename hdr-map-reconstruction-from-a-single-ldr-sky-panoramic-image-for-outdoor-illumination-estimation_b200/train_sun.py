@@ -24,6 +24,21 @@ from .trunk_train import allreduce_flat_
 LEARNING_RATE = 1e-4       # train_sun.py:34
 
 
+def start_tail_allreduce(flat_g, split):
+    """Data-parallel gradient exchange, first half: asynchronously sum flat_g[split:] (the Dense gradients, complete early in the
+    backward pass) over the ranks; returns the work handle, or None in a single-process run."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.all_reduce(flat_g[split:], op=dist.ReduceOp.SUM, async_op=True)
+    return None
+
+
+def finish_allreduce(flat_g, split, work):
+    """Second half: sum flat_g[:split] (conv / norm gradients, complete at the end of the backward pass) and wait for the first."""
+    if work is not None:
+        allreduce_flat_(flat_g[:split])
+        work.wait()
+
+
 class SunTrainer:
     def __init__(self, net, batch_size, im_height=32, im_width=128, lr=LEARNING_RATE, beta1=0.9, beta2=0.999, eps=1e-7):
         self.net = net
@@ -130,9 +145,7 @@ class SunTrainer:
                                        self._g(net.fc1, "bias").data_ptr(), B, flat.shape[1], n_fc, _stream()))
         # data-parallel: the Dense gradients (201 MB at 32x128) are complete here, before any conv gradient — their all-reduce is
         # started now and runs on NCCL's stream under the rest of the backward pass
-        fc_work = None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            fc_work = dist.all_reduce(self.flat_g[self._fc_offset:], op=dist.ReduceOp.SUM, async_op=True)
+        fc_work = start_tail_allreduce(self.flat_g, self._fc_offset)
         g = net.fc1.backward_data(g_z1)
         g = maxpool2d_backward(acts[2], g.view(pool_shape))
         g = self._layer_backward(net.sunlayer3, g, True)
@@ -141,9 +154,7 @@ class SunTrainer:
         g = maxpool2d_backward(acts[0], g)
         self._layer_backward(net.sunlayer1, g, False)
         # ---- optimizer (:258) ----
-        if fc_work is not None:
-            allreduce_flat_(self.flat_g[:self._fc_offset])                        # conv / norm gradients (1 MB)
-            fc_work.wait()
+        finish_allreduce(self.flat_g, self._fc_offset, fc_work)                   # conv / norm gradients (1 MB), then join
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.apply_gradients(world)
         return pred, sungt, cams

@@ -70,6 +70,32 @@ def test_flat_gradient_allreduce_sums_over_ranks():
     assert ret[0] == want and ret[1] == want
 
 
+def _worker_two_buckets(rank, world, port, ret):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ts = importlib.import_module(PKG_NAME).train_sun
+    flat = torch.arange(12, dtype=torch.float32) * (rank + 1)          # [conv / norm gradients | Dense gradients], split at 5
+    work = ts.start_tail_allreduce(flat, 5)                            # Dense part first, asynchronously (SunTrainer.sun_train_step)
+    flat[:5] += 100.0 * (rank + 1)                                     # "the rest of the backward pass" still writes the head
+    ts.finish_allreduce(flat, 5, work)
+    ret[rank] = flat.tolist()
+    dist.destroy_process_group()
+
+
+def test_two_bucket_gradient_allreduce():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_two_buckets, args=(world, port, ret), nprocs=world, join=True)
+        ret = dict(ret)
+    base = torch.arange(12, dtype=torch.float32) * 3
+    base[:5] += 300.0
+    assert ret[0] == base.tolist() and ret[1] == base.tolist()
+
+
 def test_shard_bounds_edge_cases(pkg):
     sb = pkg.sharding.shard_bounds
     assert [sb(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
