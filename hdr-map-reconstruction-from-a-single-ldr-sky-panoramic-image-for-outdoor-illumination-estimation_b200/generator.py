@@ -200,6 +200,7 @@ class model:
         # enhanceSunRadiance (generator.py:88)
         self.sun = sunRadNet(**kw)
         self._gmax = None
+        self._side = None
 
     def encode(self, x, training="training"):
         for stage in self._enc:                       # generator.py:94-106
@@ -254,15 +255,23 @@ class model:
     def generator_inference(self, ldr, sun_model, threshold=0.12):
         """inference.generator_in_step (inference.py:81-112): LDR panorama -> linear HDR panorama."""
         from . import grad_cam
+        # The sky branch (encode -> trunk -> sky_decode) and the sun branch up to the sun radiance (sun-position network -> Grad-CAM ->
+        # sunRadNet) only share the input: the sun branch runs on a side stream (fork / join; also valid inside a CUDA-graph capture)
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            sunpose_cmf, (sunlayer1, sunlayer2, sunlayer3) = sun_model.sunposeEstimation(ldr, training=False)   # :87
+            y_c = sun_model.class_score(sunpose_cmf)                                        # :98
+            sun_cam1 = grad_cam.layer(y_c, sunlayer1)                                       # :100-102
+            sun_cam2 = grad_cam.layer(y_c, sunlayer2)
+            sun_cam3 = grad_cam.layer(y_c, sunlayer3)
+            sun_rad_gamma, _, _ = self.sun_rad_estimation(ldr, sun_cam1, sun_cam2, sun_cam3, sunpose_cmf, training=False,
+                                                          log_compress=True)                # :104-105
         res_out = self.encode(ldr, training=False)                                          # :83
         sky_pred_gamma = self.sky_decode(res_out, ldr, training=False)                      # :84 (:85 is folded into the blend)
-        sunpose_cmf, (sunlayer1, sunlayer2, sunlayer3) = sun_model.sunposeEstimation(ldr, training=False)   # :87
-        y_c = sun_model.class_score(sunpose_cmf)                                            # :98
-        sun_cam1 = grad_cam.layer(y_c, sunlayer1)                                           # :100-102
-        sun_cam2 = grad_cam.layer(y_c, sunlayer2)
-        sun_cam3 = grad_cam.layer(y_c, sunlayer3)
-        sun_rad_gamma, _, _ = self.sun_rad_estimation(ldr, sun_cam1, sun_cam2, sun_cam3, sunpose_cmf, training=False,
-                                                      log_compress=True)                    # :104-105
+        main.wait_stream(self._side)
         return self.sun_decode(res_out, sun_cam1, sun_cam2, sun_cam3, sun_rad_gamma, training=False, blend_with=sky_pred_gamma,
                                threshold=threshold, log_decompress=True)                    # :106-110
 
