@@ -442,6 +442,15 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    # keep warming for at least 0.4 s of wall time: clocks, the caching allocator's per-stream pools (the step uses side streams)
+    # and NCCL's channels reach their steady state only after a few dozen steps; untimed, the same count on every rank
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    extra = int(min(200, max(0, 0.4 / max(time.perf_counter() - t_w, 1e-4))))
+    for _ in range(extra):
+        step_device()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
