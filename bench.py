@@ -449,6 +449,10 @@ def run_ours(args):
     step_device()
     torch.cuda.synchronize()
     extra = int(min(200, max(0, 0.4 / max(time.perf_counter() - t_w, 1e-4))))
+    if world > 1:                                   # the train step contains a collective: every rank must run the same number of steps
+        ex = torch.tensor([extra], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+        extra = int(ex.item())
     for _ in range(extra):
         step_device()
     barrier()
