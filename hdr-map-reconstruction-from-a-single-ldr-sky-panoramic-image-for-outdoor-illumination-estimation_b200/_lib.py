@@ -91,7 +91,7 @@ def load():
 
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
-LAUNCHES_PER_CALL = {"sky_dense_fwd": 2, "sky_dense_bwd_data": 2, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
+LAUNCHES_PER_CALL = {"sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
                      "sky_da_offsets_host": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
                      "sky_debug_band_trace": 0}
 

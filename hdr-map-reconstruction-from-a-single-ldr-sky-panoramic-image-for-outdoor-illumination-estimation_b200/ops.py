@@ -87,7 +87,7 @@ class _PlainConvCore:
         x, dy = _require_cuda(x, "x"), _require_cuda(dy, "dy")
         B, h, w, C = x.shape
         k, F = self.k_h, self.output_channels
-        if self._zero_tab is None or self._zero_tab.shape[0] != h:
+        if self._zero_tab is None or tuple(self._zero_tab.shape) != (h, k * k, 2):
             self._zero_tab = torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         check(LIB.sky_da_conv2d_bwd_data(dy.data_ptr(), self._zero_tab.data_ptr(), self._weight().data_ptr(), dx.data_ptr(),
