@@ -6,13 +6,6 @@ import tensorflow as tf
 _sky = tf.load_op_library("libskydome_tf_ops.so")
 
 
-@tf.RegisterGradient("DaConv2D")
-def _da_conv2d_grad(op, dy):
-    x, offsets, _offsets_host, _packed, _bias = op.inputs
-    kernel = op.get_attr("_kernel_ref") if False else None      # the layer passes the variable through the closure below instead
-    raise NotImplementedError("use DaConv2DLayerMixin.call, which wires the gradient with tf.custom_gradient")
-
-
 class DaConv2DLayerMixin:
     """Drop into `class conv2d(Layer)` of the reference: replaces `call` (distortion_aware_ops.py:50-123)."""
 
