@@ -16,3 +16,4 @@ from . import grad_cam                 # noqa: F401
 from . import inference                # noqa: F401
 from . import tf_utils, discriminator, vgg16, train   # noqa: F401
 from . import train_sun   # noqa: F401
+from . import utils   # noqa: F401

@@ -65,6 +65,7 @@ SIGNATURES = {
     "sky_softmax_bwd_rows": (_i, [_vp] * 4 + [_i, _i, _vp]),
     "sky_dense_bwd_filter": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
     "sky_da_conv2d_smallc_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "sky_rgbe_encode": (_i, [_vp, _vp, ctypes.c_long, _i, _vp]),
     "sky_concat2_pad": (_i, [_vp, _i, _vp, _i, _vp, _i, ctypes.c_long, _vp]),
     "sky_vgg_preprocess": (_i, [_vp, _vp, ctypes.c_long, _f, _f, _f, _vp]),
     "sky_sun_radiance": (_i, [_vp] * 5 + [_i, _i, _f, _vp]),

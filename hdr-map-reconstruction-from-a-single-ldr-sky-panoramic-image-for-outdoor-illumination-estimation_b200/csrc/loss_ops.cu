@@ -316,3 +316,32 @@ extern "C" int sky_vgg_preprocess(const float *x, float *out4, long n, float mea
     SKY_CHECK_CUDA(cudaGetLastError());
     return SKY_OK;
 }
+
+// ---- Radiance RGBE (inference.py:156 / utils.py:83-84: cv2.imwrite("*.hdr")) -----------------------------------------------------
+// Greg Ward's shared-exponent encoding of one pixel: v = max(r, g, b) = m * 2^e with m in [0.5, 1) -> bytes (r, g, b) * 256 m / v, e + 128.
+// Done on the device so the D2H copy of a prediction is 4 bytes per pixel instead of 12.
+__global__ void rgbe_encode_kernel(const float *__restrict__ rgb, uint8_t *__restrict__ out, long npix, int bgr)
+{
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < npix; p += (long)gridDim.x * blockDim.x) {
+        const float c0 = rgb[3 * p], c1 = rgb[3 * p + 1], c2 = rgb[3 * p + 2];
+        const float r = bgr ? c2 : c0, g = c1, b = bgr ? c0 : c2;
+        const float v = fmaxf(r, fmaxf(g, b));
+        uchar4 o = make_uchar4(0, 0, 0, 0);
+        if (v >= 1e-32f) {
+            int e;
+            const float m = frexpf(v, &e);
+            const float s = m * 256.f / v;
+            o = make_uchar4((unsigned char)(int)(fmaxf(r, 0.f) * s), (unsigned char)(int)(fmaxf(g, 0.f) * s),
+                            (unsigned char)(int)(fmaxf(b, 0.f) * s), (unsigned char)(e + 128));
+        }
+        reinterpret_cast<uchar4 *>(out)[p] = o;
+    }
+}
+
+extern "C" int sky_rgbe_encode(const float *rgb, uint8_t *rgbe, long npix, int bgr, void *stream)
+{
+    SKY_REQUIRE(rgb && rgbe && npix > 0 && ((uintptr_t)rgbe & 3) == 0, SKY_ERR_INVALID, "bad arguments");
+    rgbe_encode_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>(rgb, rgbe, npix, bgr);
+    SKY_CHECK_CUDA(cudaGetLastError());
+    return SKY_OK;
+}
