@@ -142,18 +142,13 @@ def make_inference_weights(H, W, seed=0):
 
 
 def make_sunpose_gt(batch, H, W, seed):
-    """sunpose_gt = von Mises-Fisher bump (kappa = 80) over the H*W sky bins (train.py:42-52) at a random sun position."""
+    """sunpose_gt = von Mises-Fisher bump (kappa = 80) over the H*W sky bins (train.py:42-52) at azimuth W/2 - 1
+    (train.py:32) and a random elevation row in [H/8, H/2] — computed by the package's own mirror of train.vMF (dataset.py)."""
+    from __graft_entry__ import load_package
+    D = load_package().dataset
     rng = np.random.default_rng(seed)
-    ii, jj = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    elev = (H - ii - 0.5) * (np.pi / 2) / H
-    azim = (jj + 0.5) * (2 * np.pi) / W - np.pi
-    bins = np.stack([np.cos(elev) * np.sin(azim), np.sin(elev), np.cos(elev) * np.cos(azim)], -1).reshape(-1, 3)
-    out = np.empty((batch, H * W), np.float32)
-    for b in range(batch):
-        c = bins[rng.integers(0, H * W)]
-        p = np.exp(80.0 * (bins @ c - 1.0))
-        out[b] = (p / p.sum()).astype(np.float32)
-    return out
+    bins = D.sunpose_bins(H, W)
+    return np.stack([D.vMF(W * 0.5 - 1, rng.uniform(H / 8, H / 2), H, W, bins=bins) for _ in range(batch)]).astype(np.float32)
 
 
 def make_ldr(batch, H, W, seed):

@@ -17,3 +17,4 @@ from . import inference                # noqa: F401
 from . import tf_utils, discriminator, vgg16, train   # noqa: F401
 from . import train_sun   # noqa: F401
 from . import utils   # noqa: F401
+from . import dataset   # noqa: F401
