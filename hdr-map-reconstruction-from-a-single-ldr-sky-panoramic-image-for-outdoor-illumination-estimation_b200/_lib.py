@@ -19,6 +19,7 @@ _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_
 SIGNATURES = {
     "sky_version": (_i, []),
     "sky_last_error": (ctypes.c_char_p, []),
+    "sky_launch_count": (ctypes.c_long, []),
     "sky_da_offsets_host": (_i, [_i, _i, _i, _i, _i, _vp]),
     "sky_da_offsets_device": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sky_da_sample_debug": (_i, [_i, _i, _i, _vp] + [_vp] * 8 + [_vp]),

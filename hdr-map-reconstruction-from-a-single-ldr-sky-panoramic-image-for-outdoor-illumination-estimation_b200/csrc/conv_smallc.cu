@@ -288,7 +288,7 @@ int launch_fwd_smallf(const FwdArgs &a)
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;          // two resident CTAs per SM
     conv2d_smallf_kernel<<<grid, SF_THREADS, smem, a.stream>>>(a.x, a.packed, a.bias, a.residual, a.aux, a.y, a.B, a.h, a.w, a.C, a.F, f_pad_of(a.F),
                                                                a.k, a.flags, a.slope, a.threshold);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -323,7 +323,7 @@ static int launch_fwd_smallc_da(const FwdArgs &a, const float *kernel)
         default: SKY_LAUNCH_SCDA(4); break;
     }
 #undef SKY_LAUNCH_SCDA
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -360,7 +360,7 @@ extern "C" int sky_conv2d_smallc_fwd(const float *x, const float *kernel, const 
         default: SKY_LAUNCH_SC(4); break;
     }
 #undef SKY_LAUNCH_SC
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 

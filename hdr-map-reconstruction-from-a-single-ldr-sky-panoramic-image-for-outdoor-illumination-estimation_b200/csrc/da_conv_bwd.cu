@@ -368,7 +368,7 @@ extern "C" int sky_da_conv2d_bwd_data(const float *dy, const float *offsets, con
     if (ksplit > p.k2 * p.CC) ksplit = p.k2 * p.CC;
     p.ksplit = ksplit;
     da_conv2d_dgrad_kernel<<<dim3(tiles, ksplit), BWD_THREADS, smem, st>>>(p);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -397,14 +397,14 @@ extern "C" int sky_da_conv2d_bwd_filter(const float *x, const float *dy, const f
     }
     dim3 grid(p.parts, groups, p.CC);
     da_conv2d_wgrad_kernel<<<grid, BWD_THREADS, smem, st>>>(p);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     if (dbias) {
         SKY_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)F * sizeof(float), st));
         int ysplit = (p.M + 31) / 32;
         if (ysplit > 8 * 148) ysplit = 8 * 148;
         dim3 g2((F + 127) / 128, ysplit);
         col_sum_kernel<<<g2, 128, 0, st>>>(dy, dbias, p.M, F);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
     }
     return SKY_OK;
 }

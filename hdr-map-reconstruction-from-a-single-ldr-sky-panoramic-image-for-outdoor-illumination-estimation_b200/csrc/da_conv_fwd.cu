@@ -517,13 +517,13 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
     const int ksplit = (p.KB + p.kb_per_split - 1) / p.kb_per_split;
     if (ksplit > 1) SKY_CHECK_CUDA(cudaMemsetAsync(p.y, 0, (size_t)p.M * p.ldF * sizeof(float), st));
     da_conv2d_fwd_tc_kernel<STAGES, SPLIT3><<<dim3(tiles, ksplit, p.nslices), NUM_THREADS, smem, st>>>(p);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     if (ksplit > 1) {
         const long total4 = (long)p.M * p.ldF / 4;
         int blocks = (int)((total4 + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         conv_finalize_kernel<<<blocks, 256, 0, st>>>(p.y, p.bias, total4, p.ldF / 4, p.flags, p.slope);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
     }
     return SKY_OK;
 }
@@ -565,7 +565,7 @@ extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel + 256 * s, (float *)dst, K, Fs, Fp, KB, planes, C, k * k, F);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
         dst += slice_bytes(C, Fs, k, math_mode);
     }
     return SKY_OK;
@@ -715,7 +715,7 @@ extern "C" int sky_da_conv2d_fwd_simt(const float *x, const float *offsets, cons
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     da_conv2d_fwd_simt_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, offsets, kernel, bias, y, B, h, w, C, F, k);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -729,6 +729,6 @@ extern "C" int sky_resize_bilinear_fwd(const float *x, float *y, int B, int h, i
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (vec) resize_bilinear_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
     else resize_bilinear_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

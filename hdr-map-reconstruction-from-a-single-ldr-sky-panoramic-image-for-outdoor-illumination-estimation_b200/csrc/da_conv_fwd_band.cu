@@ -688,7 +688,7 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
     }
     const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
     da_conv2d_fwd_band_kernel<STAGES, SPLIT3><<<grid, BAND_THREADS, smem, a.stream>>>(p, tmap);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 

@@ -4,11 +4,15 @@
 #include <string.h>
 #include <vector>
 
+#include <atomic>
+
 #include "da_geometry.cuh"
 
 namespace sky {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long> g_launches{ 0 };
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -172,6 +176,7 @@ using namespace sky;
 
 extern "C" int sky_version(void) { return 100; }
 extern "C" const char *sky_last_error(void) { return sky::g_err; }
+extern "C" long sky_launch_count(void) { return sky::g_launches.load(); }
 
 extern "C" int sky_da_offsets_host(int h, int w, int k, int dilation, int skydome, float *out_host)
 {
@@ -196,7 +201,7 @@ extern "C" int sky_da_offsets_device(int h, int w, int k, int dilation, int skyd
     cudaStream_t st = (cudaStream_t)stream;
     SKY_CHECK_CUDA(cudaMemsetAsync(dev_status, 0, sizeof(int), st));
     da_offsets_kernel<<<(h + 63) / 64, 64, 0, st>>>(h, w, k, dilation, skydome, dev_out, dev_status);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -209,6 +214,6 @@ extern "C" int sky_da_sample_debug(int h, int w, int k, const float *dev_offsets
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     da_sample_debug_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h, w, k, dev_offsets, y0, y1, x0, x1, w0, w1, w2, w3);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

@@ -78,6 +78,6 @@ extern "C" int sky_instnorm_apply(const float *x, const double *stats, const flo
     dim3 grid(chunks, B);
     instnorm_apply_kernel<<<grid, IN_THREADS, 2 * F * sizeof(float), (cudaStream_t)stream>>>(
         x, stats, gamma, beta, (flags & SKY_EPI_RESIDUAL) ? residual : nullptr, y, hw, F, eps, flags, slope, pix);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

@@ -245,7 +245,7 @@ extern "C" int sky_ldr_synth(const float *hdr, const float *t, const float *crf,
     SKY_REQUIRE((!noise_s || sigma_s) && (!noise_c || sigma_c), SKY_ERR_INVALID, "noise without its sigma");
     ldr_synth_kernel<<<blocks_for((long)B * hw * C), 256, 0, (cudaStream_t)stream>>>(hdr, t, crf, sigma_s, sigma_c, noise_s, noise_c, hdr_t,
                                                                                      ldr, B, hw, C, K, quantize);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -253,7 +253,7 @@ extern "C" int sky_hdr_log_codec(const float *x, float *y, long n, int decompres
 {
     SKY_REQUIRE(x && y && n > 0, SKY_ERR_INVALID, "bad arguments");
     hdr_log_codec_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(x, y, n, decompress);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -261,7 +261,7 @@ extern "C" int sky_loss_reduce(int kind, const float *a, const float *b, long n,
 {
     SKY_REQUIRE(a && out && n > 0 && kind >= 0 && kind <= 2 && (kind != 0 || b), SKY_ERR_INVALID, "bad arguments");
     loss_reduce_kernel<<<blocks_for(n, 148 * 4), 256, 0, (cudaStream_t)stream>>>(kind, a, b, n, out);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -269,7 +269,7 @@ extern "C" int sky_kl_divergence(const float *y_true, const float *y_pred, long 
 {
     SKY_REQUIRE(y_true && y_pred && out && n > 0, SKY_ERR_INVALID, "bad arguments");
     kl_divergence_kernel<<<blocks_for(n, 148 * 4), 256, 0, (cudaStream_t)stream>>>(y_true, y_pred, n, out);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -277,7 +277,7 @@ extern "C" int sky_dog_base(const float *x, float *base, int B, int h, int w, in
 {
     SKY_REQUIRE(x && base && B > 0 && h > 1 && w > 1 && C > 0, SKY_ERR_INVALID, "bad arguments");
     dog_base_kernel<<<blocks_for((long)B * 4 * h * w * C), 256, 0, (cudaStream_t)stream>>>(x, base, B, h, w, C, 1.2489996f);   // tf_utils.py:61
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -285,7 +285,7 @@ extern "C" int sky_dog_l1(const float *base_a, const float *base_b, int B, int H
 {
     SKY_REQUIRE(base_a && base_b && out4 && B > 0 && H2 > 1 && W2 > 1 && C > 0, SKY_ERR_INVALID, "bad arguments");
     dog_l1_kernel<<<blocks_for((long)B * H2 * W2 * C, 148 * 4), 256, 0, (cudaStream_t)stream>>>(base_a, base_b, B, H2, W2, C, out4);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -297,7 +297,7 @@ extern "C" int sky_adam_step(float *w, float *m, float *v, const float *g, long 
     const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
     SKY_REQUIRE((((uintptr_t)w | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0, SKY_ERR_INVALID, "w, m, v, g must be 16-byte aligned");
     adam_kernel<<<blocks_for((n + 3) / 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(w, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -305,7 +305,7 @@ extern "C" int sky_concat2_pad(const float *a, int Ca, const float *b, int Cb, f
 {
     SKY_REQUIRE(a && b && out && Ca > 0 && Cb > 0 && Cp >= Ca + Cb && n > 0, SKY_ERR_INVALID, "bad arguments");
     concat2_pad_kernel<<<blocks_for(n * Cp), 256, 0, (cudaStream_t)stream>>>(a, Ca, b, Cb, out, Cp, n);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -313,7 +313,7 @@ extern "C" int sky_vgg_preprocess(const float *x, float *out4, long n, float mea
 {
     SKY_REQUIRE(x && out4 && n > 0 && ((uintptr_t)out4 & 15) == 0, SKY_ERR_INVALID, "bad arguments");
     vgg_preprocess_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(x, out4, n, mean0, mean1, mean2);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -342,6 +342,6 @@ extern "C" int sky_rgbe_encode(const float *rgb, uint8_t *rgbe, long npix, int b
 {
     SKY_REQUIRE(rgb && rgbe && npix > 0 && ((uintptr_t)rgbe & 3) == 0, SKY_ERR_INVALID, "bad arguments");
     rgbe_encode_kernel<<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>(rgb, rgbe, npix, bgr);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

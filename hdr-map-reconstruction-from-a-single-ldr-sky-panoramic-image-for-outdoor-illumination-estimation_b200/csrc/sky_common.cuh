@@ -21,6 +21,14 @@ void set_error(const char *fmt, ...);
         }                                                                                             \
     } while (0)
 
+// after every kernel launch: counts it (sky_launch_count) and surfaces launch-configuration errors
+void count_launch();
+#define SKY_CHECK_LAUNCH()                   \
+    do {                                     \
+        sky::count_launch();                 \
+        SKY_CHECK_CUDA(cudaGetLastError());  \
+    } while (0)
+
 #define SKY_REQUIRE(cond, code, ...)     \
     do {                                 \
         if (!(cond)) {                   \

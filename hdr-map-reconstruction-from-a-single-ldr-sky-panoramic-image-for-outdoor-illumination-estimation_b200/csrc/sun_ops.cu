@@ -277,7 +277,7 @@ extern "C" int sky_softmax_max_bwd(const float *sm, const float *act, float *yc,
 {
     SKY_REQUIRE(sm && act && g && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     softmax_max_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, act, nullptr, yc, g, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -285,7 +285,7 @@ extern "C" int sky_transpose(const float *in, float *out, int K, int N, void *st
 {
     SKY_REQUIRE(in && out && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, K, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -298,7 +298,7 @@ extern "C" int sky_dense_bwd_data(const float *dy, const float *Wt, const float 
     if (act) {
         const long total = (long)B * K;
         relu_mask_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dx, act, total);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
     }
     return SKY_OK;
 }
@@ -310,7 +310,7 @@ extern "C" int sky_maxpool2x2_bwd(const float *x, const float *dy, float *dx, in
     const int oh = (h + 1) / 2, ow = (w + 1) / 2;
     const long total = (long)B * oh * ow * (C / 4);
     maxpool2x2_bwd_kernel<<<ew_blocks(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, h, w, C, oh, ow);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -326,10 +326,10 @@ extern "C" int sky_gradcam(const float *grad, const float *A, float *wsum, float
     if (pix < 16) pix = 16;
     chunks = (hw + pix - 1) / pix;
     gradcam_reduce_kernel<<<dim3(chunks, B), 256, 256 * 4 * sizeof(float), st>>>(grad, wsum, hw, C, pix);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     const long threads = (long)B * hw * (C / 4);
     gradcam_apply_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(A, wsum, cam, B, hw, C);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -340,7 +340,7 @@ extern "C" int sky_sunrad_input(const float *ldr, const float *cam1, const float
                 "bad arguments");
     SKY_REQUIRE(Cp >= 6, SKY_ERR_INVALID, "the sunRadNet input has 6 channels (got Cp=%d)", Cp);
     sunrad_input_kernel<<<ew_blocks((long)B * H * W), 256, 0, (cudaStream_t)stream>>>(ldr, cam1, cam2, cam3, out, B, H, W, h2, w2, h3, w3, Cp);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -349,7 +349,7 @@ extern "C" int sky_bn_fold(const float *kernel, const float *gamma, const float 
 {
     SKY_REQUIRE(kernel && gamma && beta && mean && var && kernel_out && bias_out && K > 0 && F > 0, SKY_ERR_INVALID, "bad arguments");
     bn_fold_kernel<<<ew_blocks(K * F), 256, 0, (cudaStream_t)stream>>>(kernel, gamma, beta, mean, var, eps, kernel_out, bias_out, K, F);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -359,7 +359,7 @@ extern "C" int sky_max_nonneg(const float *x, float *out, long n, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     SKY_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
     max_nonneg_kernel<<<ew_blocks(n, 256, 148 * 4), 256, 0, st>>>(x, out, n);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -370,7 +370,7 @@ extern "C" int sky_sun_radiance(const float *sm, const float *gmax, const float 
     // deltafunc_const = tf.sqrt(pi) (sunrad_net.py:35): fp32 sqrt of fp32(pi)
     const float sqrt_pi = sqrtf(3.14159265358979323846f);
     sun_radiance_kernel<<<ew_blocks((long)B * hw), 256, 0, (cudaStream_t)stream>>>(sm, gmax, gb, out3, lin1, B, hw, eps, sqrt_pi);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -428,7 +428,7 @@ extern "C" int sky_softmax_pick_bwd(const float *sm, const float *act, const int
 {
     SKY_REQUIRE(sm && act && pick && g && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     sky::softmax_max_bwd_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, act, pick, yc, g, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -436,7 +436,7 @@ extern "C" int sky_argmax_rows(const float *x, int *idx, int rows, int N, void *
 {
     SKY_REQUIRE(x && idx && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     argmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, idx, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -448,6 +448,6 @@ extern "C" int sky_blend_split(const float *sky_gamma, const float *sun_gamma, f
     if (blocks > 148 * 8) blocks = 148 * 8;
     blend_split_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(sky_gamma, sun_gamma, threshold, y_gamma, y_lin, sky_lin, sun_lin, alpha,
                                                                       npix);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

@@ -292,7 +292,7 @@ extern "C" int sky_kl_divergence_bwd(const float *y_true, const float *y_pred, f
 {
     SKY_REQUIRE(y_true && y_pred && g && n > 0, SKY_ERR_INVALID, "bad arguments");
     kl_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(y_true, y_pred, g, n, scale, accumulate);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -304,7 +304,7 @@ extern "C" int sky_dog_l1_bwd(const float *base_a, const float *base_b, float *d
     const long total = (long)B * H2 * W2 * C;
     SKY_CHECK_CUDA(cudaMemsetAsync(dbase_a, 0, total * sizeof(float), st));
     dog_l1_bwd_kernel<<<ew_grid(total), 256, 0, st>>>(base_a, base_b, dbase_a, B, H2, W2, C, scale);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -314,7 +314,7 @@ extern "C" int sky_dog_base_bwd(const float *dbase, float *dx, int B, int h, int
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * h * w * C * sizeof(float), st));
     dog_base_bwd_kernel<<<ew_grid((long)B * 4 * h * w * C), 256, 0, st>>>(dbase, dx, B, h, w, C, 1.2489996f);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -322,7 +322,7 @@ extern "C" int sky_softmax_bwd_rows(const float *sm, const float *g, const float
 {
     SKY_REQUIRE(sm && g && gz && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     softmax_bwd_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(sm, g, act, gz, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -333,7 +333,7 @@ extern "C" int sky_dense_bwd_filter(const float *x, const float *dy, float *dW, 
                 "Dense weight gradient needs units %% 4 == 0 and 16-byte aligned outputs (N=%d)", N);
     dim3 grid((N + DW_BN - 1) / DW_BN, (K + DW_BK - 1) / DW_BK);
     dense_bwd_filter_kernel<<<grid, DW_THREADS, 0, (cudaStream_t)stream>>>(x, dy, dW, db, B, K, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -369,6 +369,6 @@ extern "C" int sky_da_conv2d_smallc_bwd_filter(const float *x, const float *dy, 
         default: SKY_LAUNCH_SW(4); break;
     }
 #undef SKY_LAUNCH_SW
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

@@ -206,7 +206,7 @@ extern "C" int sky_maxpool2x2_fwd(const float *x, float *y, int B, int h, int w,
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     maxpool2x2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, B, h, w, C, oh, ow);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -217,7 +217,7 @@ static int dense_finish(float *y, const float *bias, int B, int N, int relu, cud
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         dense_finalize_kernel<<<blocks, 256, 0, st>>>(y, bias, total, N, relu);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
     }
     return SKY_OK;
 }
@@ -246,7 +246,7 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
         k_per = (k_per + DS_BK - 1) / DS_BK * DS_BK;
         ksplit = (K + k_per - 1) / k_per;
         dense_stream_kernel<<<dim3(ncta, ksplit, bcta), DS_THREADS, DS_SMEM, st>>>(tmap_w, tmap_x, y, B, K, N, k_per);
-        SKY_CHECK_CUDA(cudaGetLastError());
+        SKY_CHECK_LAUNCH();
         return dense_finish(y, bias, B, N, relu, st);
     }
     const int ncta = (N + DN_THREADS - 1) / DN_THREADS;
@@ -255,7 +255,7 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
     k_per = (k_per + DN_BK - 1) / DN_BK * DN_BK;
     ksplit = (K + k_per - 1) / k_per;
     dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return dense_finish(y, bias, B, N, relu, st);
 }
 
@@ -263,6 +263,6 @@ extern "C" int sky_softmax_rows(const float *x, float *y, int rows, int N, void 
 {
     SKY_REQUIRE(x && y && rows > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
     softmax_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, y, N);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }

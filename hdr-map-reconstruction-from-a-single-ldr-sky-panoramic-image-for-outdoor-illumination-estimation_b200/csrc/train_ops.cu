@@ -177,10 +177,10 @@ extern "C" int sky_instnorm_bwd(const float *x, const double *stats, const float
     dim3 grid(chunks, B);
     instnorm_bwd_reduce_kernel<<<grid, TR_THREADS, (2 * F + TR_THREADS * 8) * sizeof(float), st>>>(x, stats, dy, act, sums, hw, F, eps,
                                                                                                   slope, pix);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     instnorm_bwd_apply_kernel<<<grid, TR_THREADS, 5 * F * sizeof(float), st>>>(x, stats, gamma, dy, act, sums, extra, dx, dgamma, dbeta,
                                                                                hw, F, eps, slope, pix);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -192,7 +192,7 @@ extern "C" int sky_mse_loss(const float *y, const float *target, float *dy, doub
     long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     mse_loss_kernel<<<(int)blocks, 256, 0, st>>>(y, target, dy, loss, n / 4, 1.0f / (float)n);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
 
@@ -203,6 +203,6 @@ extern "C" int sky_rmsprop_step(float *w, float *ms, const float *g, long n, flo
     long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     rmsprop_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, ms, g, n, lr, rho, eps, grad_scale);
-    SKY_CHECK_CUDA(cudaGetLastError());
+    SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
