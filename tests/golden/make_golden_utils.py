@@ -1,0 +1,106 @@
+"""Generate tests/golden/utils_golden.npz by executing the reference's own tf_utils.py (hdr_logCompression / hdr_logDecompression,
+apply_rf / interp_1d / sample_1d, sphere2world, sunpose_init) and the arithmetic tail of sunrad_net.sunRadNet.call, read
+unmodified from /root/reference, over the numpy TensorFlow stand-in of tf_shim.py (extended here with the few extra symbols those
+functions touch).  Run in the build container only:   python tests/golden/make_golden_utils.py
+The committed .npz pins oracle/model_oracle.py, <package>/dataset.py and the GPU kernels' CPU references (tests/test_oracle_model.py)."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import tf_shim  # noqa: E402
+from tf_shim import Tensor, _to_np  # noqa: E402
+
+
+def _f32(fn):
+    def op(x, *a, **k):
+        return Tensor(fn(_to_np(x).astype(np.float32)).astype(np.float32))
+    return op
+
+
+def install():
+    tf = tf_shim.install()
+    tf.math.log, tf.math.exp = _f32(np.log), _f32(np.exp)
+    tf.math.multiply, tf.math.divide, tf.math.subtract = tf.multiply, tf.divide, tf.subtract
+    tf.sqrt = _f32(np.sqrt)
+    tf.pow = lambda x, y: Tensor(np.power(_to_np(x).astype(np.float32), np.float32(_to_np(y))).astype(np.float32))
+    tf.nn.sigmoid = _f32(lambda a: 1.0 / (1.0 + np.exp(-a)))
+    tf.shape = lambda x: list(_to_np(x).shape)
+    tf.scalar_mul = lambda s, x: Tensor(np.float32(s) * _to_np(x))
+    _where3 = tf.where
+    tf.where = lambda c, a, b: Tensor(np.where(_to_np(c), np.float32(_to_np(a)) if np.isscalar(a) else _to_np(a), _to_np(b)).astype(np.float32))
+    tf.function = lambda f=None, **k: (f if f is not None else (lambda g: g))
+    _range = tf.range
+    tf.range = lambda *a, dtype=None, **k: (Tensor(_to_np(_range(*a, **k)).astype(np.int32 if dtype is tf.int32 else np.float32))
+                                            if dtype is not None else _range(*a, **k))
+
+    def gather_nd(params, indices):
+        p, idx = _to_np(params), _to_np(indices).astype(np.int64)
+        return Tensor(p[tuple(idx[..., i] for i in range(idx.shape[-1]))])
+    tf.gather_nd = gather_nd
+    keras = sys.modules["tensorflow.keras"]
+    keras.Model = type("Model", (), {"__init__": lambda self, *a, **k: None})
+    keras.layers.Conv2D = keras.layers.BatchNormalization = keras.layers.LeakyReLU = keras.layers.Flatten = keras.layers.Dense = (
+        lambda *a, **k: None)
+    tf.random_normal_initializer = lambda *a, **k: None
+    for name in ("tensorflow_addons", "utils", "ops", "cv2", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    return tf
+
+
+def load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    install()
+    U = load("/root/reference/tf_utils.py", "ref_tf_utils")
+    S = load("/root/reference/sunrad_net.py", "ref_sunrad_net")
+    rng = np.random.default_rng(0)
+    out = {}
+    # log codec (tf_utils.py:263-280)
+    x = (rng.uniform(0, 1, (2, 4, 8, 3)) ** 4 * 100).astype(np.float32)
+    out["codec_x"] = x
+    out["codec_compressed"] = U.hdr_logCompression(Tensor(x)).numpy()
+    out["codec_roundtrip"] = U.hdr_logDecompression(Tensor(out["codec_compressed"])).numpy()
+    # camera response lookup (tf_utils.py:191-255)
+    K = 1024
+    crf = (np.linspace(0, 1, K)[None, :] ** (1 / rng.uniform(1.5, 3, (3, 1)))).astype(np.float32)
+    xr = rng.uniform(0, 1, (3, 5, 7, 3)).astype(np.float32)
+    xr[0, 0, 0] = [0.0, 1.0, 0.5]
+    out["rf_crf"], out["rf_x"] = crf, xr
+    out["rf_y"] = U.apply_rf(Tensor(xr), Tensor(crf)).numpy()
+    # sun-position bins and directions (tf_utils.py:95-129)
+    h, w = 8, 32
+    out["bins_hw"] = np.array([h, w])
+    out["bins"] = np.stack([U.sunpose_init(Tensor(np.float32(i)), h, w).numpy() for i in range(h * w)])
+    pts = np.array([[15.0, 2.5], [0.0, 0.0], [31.0, 7.9], [7.25, 4.0]], np.float32)
+    out["s2w_pts"] = pts
+    out["s2w"] = np.stack([U.sphere2world((Tensor(p[0]), Tensor(p[1])), h, w, skydome=True).numpy() for p in pts])
+    # arithmetic tail of sunRadNet.call (sunrad_net.py:56-71) with the conv stack replaced by fixed head outputs
+    net = S.sunRadNet()
+    B, H, W = 3, 4, 8
+    heads = rng.standard_normal((B, 2)).astype(np.float32) * 2
+    ident = lambda t, *a: t
+    net.d1 = net.d2 = net.d3 = net.d4 = ident
+    net.flat = ident
+    net.gamma = lambda t: Tensor(heads[:, 0:1])
+    net.beta = lambda t: Tensor(heads[:, 1:2])
+    sm = rng.uniform(0, 1, (B, H, W, 1)).astype(np.float32)
+    sm[0, 0, 0, 0] = 1.0                                     # the normalised maximum: the peak of the radiance function
+    rad, g_in, b_in = net.call(Tensor(sm), Tensor(np.zeros((B, 1), np.float32)), False)
+    out["rad_heads"], out["rad_x"], out["rad_y"] = heads, sm, rad.numpy()
+    out["rad_gamma_in"], out["rad_beta_in"] = g_in.numpy(), b_in.numpy()
+    np.savez_compressed(os.path.join(HERE, "utils_golden.npz"), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

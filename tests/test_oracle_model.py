@@ -89,3 +89,53 @@ def test_generator_inference_oracle_shapes_and_ranges():
     assert abs(float(d["sm"].sum()) - 1) < 1e-5 and float(d["alpha"].min()) >= 0 and float(d["alpha"].max()) <= 1
     assert [tuple(c.shape) for c in d["cams"]] == [(1, H, W, 1), (1, H // 2, W // 2, 1), (1, H // 4, W // 4, 1)]
     assert float(d["sun_rad_gamma"].max()) <= float(M.hdr_log_compression(torch.tensor(30000.0))) + 1e-6          # the 30000 clamp
+
+
+# ---- golden vectors produced by the reference's OWN tf_utils.py / sunrad_net.py over the TF shim (tests/golden/make_golden_utils.py) ----
+def _utils_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "utils_golden.npz"))
+
+
+def test_oracle_matches_reference_tf_utils_vectors(pkg):
+    g = _utils_golden()
+    T = torch.from_numpy
+    # log codec (tf_utils.py:263-280)
+    assert np.allclose(M.hdr_log_compression(T(g["codec_x"])).numpy(), g["codec_compressed"], rtol=2e-6, atol=1e-7)
+    assert np.allclose(M.hdr_log_decompression(T(g["codec_compressed"])).numpy(), g["codec_roundtrip"], rtol=2e-5, atol=1e-6)
+    # camera response lookup (tf_utils.py:191-255): fp32 oracle against the reference's fp32 ops
+    got = M.apply_rf(T(g["rf_x"]), T(g["rf_crf"])).numpy()
+    assert np.abs(got - g["rf_y"]).max() < 2e-6
+    # sun-position bins / directions (tf_utils.py:95-129) as restated in <package>/dataset.py
+    h, w = (int(v) for v in g["bins_hw"])
+    assert np.abs(pkg.dataset.sunpose_bins(h, w) - g["bins"]).max() < 1e-6
+    for p, want in zip(g["s2w_pts"], g["s2w"]):
+        assert np.abs(pkg.dataset.sphere2world((p[0], p[1]), h, w) - want).max() < 1e-6
+
+
+def test_oracle_matches_reference_sunrad_tail():
+    """sunRadNet.call's arithmetic (sunrad_net.py:56-71) executed from the reference source with the conv stack stubbed out: the
+    oracle's radiance function, its epsilon placement and the 30000 clamp."""
+    g = _utils_golden()
+    heads = torch.from_numpy(g["rad_heads"])
+    x = torch.from_numpy(g["rad_x"])
+    gamma_in = torch.sigmoid(heads[:, 0]).reshape(-1, 1, 1, 1)
+    beta_in = torch.sigmoid(heads[:, 1]).reshape(-1, 1, 1, 1)
+    assert np.allclose(gamma_in.numpy(), g["rad_gamma_in"], rtol=1e-6) and np.allclose(beta_in.numpy(), g["rad_beta_in"], rtol=1e-6)
+    eps = 1e-5
+    v = torch.exp(-((1.0 - x) ** 2.0) / (beta_in + eps)) * gamma_in / (beta_in * torch.sqrt(torch.tensor(float(np.float32(np.pi)))) + eps)
+    v = torch.where(v > 30000.0, torch.full_like(v, 30000.0), v)
+    assert np.allclose(v.numpy(), g["rad_y"], rtol=1e-5, atol=1e-7)
+    # and the same through the oracle function the GPU tests use (identity conv stack: weights that produce exactly these head values)
+    w = {"gamma": (np.zeros((1, 1), np.float32), np.zeros(1, np.float32)), "beta": (np.zeros((1, 1), np.float32), np.zeros(1, np.float32))}
+    for b in range(x.shape[0]):
+        wb = dict(w)
+        wb["gamma"] = (np.zeros((4 * 16 * 16, 1), np.float32), g["rad_heads"][b, 0:1])
+        wb["beta"] = (np.zeros((4 * 16 * 16, 1), np.float32), g["rad_heads"][b, 1:2])
+        for name, cin, f in (("d1", 6, 2), ("d2", 2, 2), ("d3", 2, 2), ("d4", 2, 16)):
+            wb[name] = {"kernel": np.zeros((4, 4, cin, f), np.float32)}
+        plz = torch.zeros(1, 32, 128, 6)
+        xb = torch.nn.functional.interpolate(x[b:b + 1].permute(0, 3, 1, 2), size=(32, 128)).permute(0, 2, 3, 1)
+        got = M.sunrad_net(xb, plz, wb)
+        want = torch.nn.functional.interpolate(torch.from_numpy(g["rad_y"][b:b + 1]).permute(0, 3, 1, 2), size=(32, 128)).permute(0, 2, 3, 1)
+        assert np.allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
