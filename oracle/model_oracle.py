@@ -11,8 +11,8 @@ wired in as the commented lines generator.py:14,18 do:
 and of the rest of the path (sun branch, train / test tail, sun pre-train step) further down.
 
 Pinning: the distortion-aware sampling against tests/golden/da_golden.npz (the reference's own distortion_aware_ops.py executed over a
-numpy TensorFlow shim); hdr_log_*, apply_rf and the sunRadNet radiance tail against tests/golden/utils_golden.npz (the reference's own
-tf_utils.py / sunrad_net.py over the same shim); the Keras / TFA semantics that are not in /root/reference (instance norm, batch norm,
+numpy TensorFlow shim); hdr_log_*, apply_rf, ldr_synth and the sunRadNet radiance tail against tests/golden/utils_golden.npz (the
+reference's own tf_utils.py / sunrad_net.py / train.py over the same shim); the Keras / TFA semantics that are not in /root/reference (instance norm, batch norm,
 SAME padding, max-pool routing, KLDivergence, gaussian_filter2d) against numpy / scipy / closed forms in tests/test_oracle_model.py.
 With respect to a real TensorFlow run parity remains unpinned (TensorFlow cannot be installed in the build container).
 """

@@ -59,6 +59,53 @@ def load(path, name):
     return mod
 
 
+def train_vectors():
+    """train.vMF (train.py:42-52) and train._preprocessing (train.py:54-94) executed from the reference's own train.py.  Its sibling
+    model modules are stubbed (they are not touched by these two functions); tf_utils is the real one.  The random draws of
+    _preprocessing are replaced by recorded arrays and the JPEG round trip (a CPU codec) by the identity, as SURVEY 8(d) states."""
+    tf = sys.modules["tensorflow"]
+    tf.config = types.SimpleNamespace(experimental=types.SimpleNamespace(list_physical_devices=lambda kind: [], set_visible_devices=None))
+    tf.data = types.SimpleNamespace(AUTOTUNE=-1)
+    tf.uint8 = np.uint8
+    tf.einsum = lambda eq, a, b: Tensor(np.einsum(eq.replace(" ", ""), _to_np(a), _to_np(b)).astype(np.float32))
+    tf.reduce_sum = lambda x, *a, **k: Tensor(np.float32(_to_np(x).sum(dtype=np.float32)))
+    tf.reduce_mean = lambda x, *a, **k: Tensor(np.float32(_to_np(x).mean(dtype=np.float32)))
+    tf.nn.relu = lambda x: Tensor(np.maximum(_to_np(x), np.float32(0)))
+    tf.round = lambda x: Tensor(np.rint(_to_np(x)))
+    _cast = tf.cast
+    tf.cast = lambda x, dt: (Tensor(_to_np(x).astype(np.uint8)) if dt is np.uint8 else
+                             (Tensor(_to_np(x).astype(np.float32)) if _to_np(x).dtype == np.uint8 else _cast(x, dt)))
+    tf.image.adjust_jpeg_quality = lambda img, q: img
+    draws = {}
+    tf.random = types.SimpleNamespace(
+        uniform=lambda shape, minval=0.0, maxval=1.0, dtype=None, seed=None: Tensor(draws["uniform"].pop(0)),
+        normal=lambda shape, seed=None: Tensor(draws["normal"].pop(0)))
+    for name in ("generator", "discriminator", "sunpose_net", "grad_cam", "vgg16"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["vgg16"].Vgg16 = object
+    sys.modules["tf_utils"] = load("/root/reference/tf_utils.py", "tf_utils")
+    T = load("/root/reference/train.py", "ref_train")
+    out = {}
+    H, W = T.IMSHAPE[0], T.IMSHAPE[1]
+    pts = np.array([[T.AZIMUTH_gt, 8.0], [T.AZIMUTH_gt, 20.5], [10.0, 3.0]], np.float32)
+    out["vmf_pts"] = pts
+    out["vmf"] = np.stack([T.vMF(float(p[0]), float(p[1]), H, W).numpy() for p in pts])
+    rng = np.random.default_rng(7)
+    b, K = 4, 1024
+    hdr = (rng.uniform(0, 1, (b, 8, 16, 3)) ** 3 * 4).astype(np.float32)
+    crf_src = (np.linspace(0, 1, K)[None, :] ** (1 / rng.uniform(1.5, 3, (6, 1)))).astype(np.float32)
+    t_src = (2 ** np.linspace(-3, 3, 9)).astype(np.float32)
+    picks = iter([3, 0, 5, 1, 8, 2, 2, 7])                       # crf rows for the 4 samples, then exposures
+    T.randint = lambda lo, hi: next(picks)
+    u_s, u_c = (rng.uniform(0, 1, (b, 1, 1, 3)).astype(np.float32) for _ in range(2))
+    n_s, n_c = (rng.standard_normal(hdr.shape).astype(np.float32) for _ in range(2))
+    draws["uniform"], draws["normal"] = [u_s, u_c], [n_s, n_c]
+    hdr_t, ldr = T._preprocessing(Tensor(hdr), crf_src, t_src)
+    out.update(pre_hdr=hdr, pre_crf=crf_src[[3, 0, 5, 1]], pre_t=t_src[[8, 2, 2, 7]], pre_u_s=u_s, pre_u_c=u_c, pre_n_s=n_s, pre_n_c=n_c,
+               pre_hdr_t=hdr_t.numpy(), pre_ldr=ldr.numpy())
+    return out
+
+
 def main():
     install()
     U = load("/root/reference/tf_utils.py", "ref_tf_utils")
@@ -98,6 +145,7 @@ def main():
     rad, g_in, b_in = net.call(Tensor(sm), Tensor(np.zeros((B, 1), np.float32)), False)
     out["rad_heads"], out["rad_x"], out["rad_y"] = heads, sm, rad.numpy()
     out["rad_gamma_in"], out["rad_beta_in"] = g_in.numpy(), b_in.numpy()
+    out.update(train_vectors())
     np.savez_compressed(os.path.join(HERE, "utils_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

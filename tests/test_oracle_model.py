@@ -139,3 +139,23 @@ def test_oracle_matches_reference_sunrad_tail():
         got = M.sunrad_net(xb, plz, wb)
         want = torch.nn.functional.interpolate(torch.from_numpy(g["rad_y"][b:b + 1]).permute(0, 3, 1, 2), size=(32, 128)).permute(0, 2, 3, 1)
         assert np.allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_oracle_matches_reference_train_vectors(pkg):
+    """train.vMF and train._preprocessing executed from the reference's own train.py (random draws recorded, JPEG = identity)."""
+    g = _utils_golden()
+    T = torch.from_numpy
+    H, W = 32, 128
+    bins = pkg.dataset.sunpose_bins(H, W)
+    for p, want in zip(g["vmf_pts"], g["vmf"]):
+        got = pkg.dataset.vMF(float(p[0]), float(p[1]), H, W, bins=bins)
+        assert np.abs(got - want).max() <= 2e-5 * want.max() and abs(float(got.sum()) - 1) < 1e-5
+        assert int(got.argmax()) == int(want.argmax())
+    sigma_s = (np.float32(0.08 / 6) * g["pre_u_s"]).reshape(4, 3)          # train.py:67
+    sigma_c = (np.float32(0.005) * g["pre_u_c"]).reshape(4, 3)             # train.py:69
+    hdr_t, ldr = M.ldr_synth(T(g["pre_hdr"]), T(g["pre_t"]), T(g["pre_crf"]), T(sigma_s), T(sigma_c), T(g["pre_n_s"]), T(g["pre_n_c"]),
+                             quantize=True)
+    assert np.allclose(hdr_t.numpy(), g["pre_hdr_t"], rtol=2e-6, atol=1e-7)
+    code_got, code_want = np.round(ldr.numpy() * 255), np.round(g["pre_ldr"] * 255)
+    assert (code_got != code_want).mean() < 1e-3                            # 8-bit codes: identical except ties at x.5 under fp32 reordering
+    assert np.abs(code_got - code_want).max() <= 1
