@@ -106,6 +106,50 @@ def train_vectors():
     return out
 
 
+def generator_vectors():
+    """The non-conv glue of generator.model executed from the reference's own generator.py with every layer replaced by a recording
+    stand-in: sky_decode / sun_decode tails (generator.py:120-124, 150-155), sun_rad_estimation's normalisation, resize and concat
+    order (:160-167) and blending (:171-175)."""
+    tf = sys.modules["tensorflow"]
+    tf.nn.leaky_relu = lambda x, a: Tensor(np.where(_to_np(x) > 0, _to_np(x), np.float32(a) * _to_np(x)).astype(np.float32))
+    tf.reduce_max = lambda x, *a, **k: Tensor(np.float32(_to_np(x).max()))
+    tf.concat = lambda vals, axis=-1: Tensor(np.concatenate([_to_np(v) for v in vals], axis=axis))
+    for name in ("ops", "distortion_aware_ops", "sunrad_net"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["sunrad_net"].sunRadNet = object
+    sys.modules["tensorflow_addons"].layers = types.SimpleNamespace(InstanceNormalization=lambda *a, **k: None)
+    G = load("/root/reference/generator.py", "ref_generator")
+    rng = np.random.default_rng(11)
+    B, H, W = 2, 8, 16
+    m = object.__new__(G.model)
+    m.im_height, m.im_width = H, W
+    conv_out = rng.standard_normal((B, H, W, 3)).astype(np.float32)
+    ident = lambda t, *a, **k: t
+    for name in ("conv3_f", "norm3_f", "conv2_f", "norm2_f", "conv3_u", "norm3_u", "conv2_u", "norm2_u"):
+        setattr(m, name, ident)
+    m.conv1_f = m.conv1_u = lambda t: Tensor(conv_out)
+    inp = rng.uniform(0, 1, (B, H, W, 3)).astype(np.float32)
+    out = {"gen_conv_out": conv_out, "gen_input": inp}
+    out["gen_sky_decode"] = G.model.sky_decode(m, Tensor(np.zeros((B, 2, 4, 8), np.float32)), Tensor(inp)).numpy()
+    out["gen_sun_decode"] = G.model.sun_decode(m, Tensor(np.zeros((B, 2, 4, 8), np.float32)), None, None, None, Tensor(inp)).numpy()
+    seen = {}
+
+    def sun_stub(x, plz, training):
+        seen["x"], seen["plz"] = x.numpy(), plz.numpy()
+        return Tensor(x.numpy() * np.float32(2.0)), None, None
+    m.sun = sun_stub
+    ldr = rng.uniform(0, 1, (B, H, W, 3)).astype(np.float32)
+    cam1 = rng.uniform(0, 1, (B, H, W, 1)).astype(np.float32)
+    cam2 = rng.uniform(0, 1, (B, H // 2, W // 2, 1)).astype(np.float32)
+    cam3 = rng.uniform(0, 1, (B, H // 4, W // 4, 1)).astype(np.float32)
+    pred = rng.uniform(0, 0.01, (B, H, W, 1)).astype(np.float32)
+    rad_t, _, _ = G.model.sun_rad_estimation(m, Tensor(ldr), Tensor(cam1), Tensor(cam2), Tensor(cam3), Tensor(pred), False)
+    out.update(sre_ldr=ldr, sre_cam1=cam1, sre_cam2=cam2, sre_cam3=cam3, sre_pred=pred, sre_x=seen["x"], sre_plz=seen["plz"],
+               sre_out=rad_t.numpy())
+    out["gen_blend"] = G.model.blending(m, Tensor(conv_out), Tensor(inp)).numpy()
+    return out
+
+
 def main():
     install()
     U = load("/root/reference/tf_utils.py", "ref_tf_utils")
@@ -146,6 +190,7 @@ def main():
     out["rad_heads"], out["rad_x"], out["rad_y"] = heads, sm, rad.numpy()
     out["rad_gamma_in"], out["rad_beta_in"] = g_in.numpy(), b_in.numpy()
     out.update(train_vectors())
+    out.update(generator_vectors())
     np.savez_compressed(os.path.join(HERE, "utils_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

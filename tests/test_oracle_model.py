@@ -159,3 +159,21 @@ def test_oracle_matches_reference_train_vectors(pkg):
     code_got, code_want = np.round(ldr.numpy() * 255), np.round(g["pre_ldr"] * 255)
     assert (code_got != code_want).mean() < 1e-3                            # 8-bit codes: identical except ties at x.5 under fp32 reordering
     assert np.abs(code_got - code_want).max() <= 1
+
+
+def test_oracle_matches_reference_generator_glue():
+    """The non-conv glue of generator.model (decoder tails, sun_rad_estimation's normalisation / resize / concat order, blending)
+    executed from the reference's own generator.py with recording stand-ins for the layers."""
+    g = _utils_golden()
+    T = torch.from_numpy
+    conv, inp = T(g["gen_conv_out"]), T(g["gen_input"])
+    want_tail = torch.relu(inp + M.leaky_relu(conv, 0.1)).numpy()                      # what decode_branch computes after conv1_*
+    assert np.allclose(g["gen_sky_decode"], want_tail, atol=1e-7) and np.allclose(g["gen_sun_decode"], want_tail, atol=1e-7)
+    assert np.allclose(g["gen_blend"], (conv + inp).numpy(), atol=1e-7)
+    # sun_rad_estimation: x = pred / max(pred) over the WHOLE batch; plz = [ldr, cam1, resize(cam2), resize(cam3)]; output tiled x3
+    pred = T(g["sre_pred"])
+    assert np.allclose(g["sre_x"], (pred / pred.max()).numpy(), rtol=1e-6)
+    H, W = g["sre_ldr"].shape[1:3]
+    plz = torch.cat([T(g["sre_ldr"]), T(g["sre_cam1"]), M.O.resize_bilinear(T(g["sre_cam2"]), H, W), M.O.resize_bilinear(T(g["sre_cam3"]), H, W)], -1)
+    assert np.allclose(g["sre_plz"], plz.numpy(), atol=1e-6)
+    assert g["sre_out"].shape[-1] == 3 and np.allclose(g["sre_out"], np.repeat(g["sre_x"] * 2, 3, axis=-1), rtol=1e-6)
