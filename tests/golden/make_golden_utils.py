@@ -150,6 +150,20 @@ def generator_vectors():
     return out
 
 
+def gradcam_vectors():
+    """grad_cam.layer (grad_cam.py:29-45) from the reference's own file, with tf.gradients replaced by a recorded gradient."""
+    tf = sys.modules["tensorflow"]
+    rng = np.random.default_rng(13)
+    A = np.maximum(rng.standard_normal((2, 4, 6, 5)), 0).astype(np.float32)
+    grad = rng.standard_normal(A.shape).astype(np.float32)
+    tf.gradients = lambda y, x: [Tensor(grad)]
+    tf.reduce_mean = lambda x, axis=None, **k: Tensor(_to_np(x).mean(axis=axis, dtype=np.float32).astype(np.float32))
+    tf.einsum = lambda eq, a, b: Tensor(np.einsum(eq.replace(" ", ""), _to_np(a), _to_np(b)).astype(np.float32))
+    C = load("/root/reference/grad_cam.py", "ref_grad_cam")
+    cam = C.layer(Tensor(np.zeros(2, np.float32)), Tensor(A)).numpy()
+    return {"cam_A": A, "cam_grad": grad, "cam_out": cam}
+
+
 def main():
     install()
     U = load("/root/reference/tf_utils.py", "ref_tf_utils")
@@ -191,6 +205,7 @@ def main():
     out["rad_gamma_in"], out["rad_beta_in"] = g_in.numpy(), b_in.numpy()
     out.update(train_vectors())
     out.update(generator_vectors())
+    out.update(gradcam_vectors())
     np.savez_compressed(os.path.join(HERE, "utils_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -177,3 +177,15 @@ def test_oracle_matches_reference_generator_glue():
     plz = torch.cat([T(g["sre_ldr"]), T(g["sre_cam1"]), M.O.resize_bilinear(T(g["sre_cam2"]), H, W), M.O.resize_bilinear(T(g["sre_cam3"]), H, W)], -1)
     assert np.allclose(g["sre_plz"], plz.numpy(), atol=1e-6)
     assert g["sre_out"].shape[-1] == 3 and np.allclose(g["sre_out"], np.repeat(g["sre_x"] * 2, 3, axis=-1), rtol=1e-6)
+
+
+def test_oracle_matches_reference_grad_cam_arithmetic():
+    """grad_cam.layer executed from the reference's own grad_cam.py with a recorded gradient in place of tf.gradients: channel mean
+    over (h, w), einsum over channels, ReLU, trailing axis — the arithmetic of sky_gradcam and of the oracle's grad_cam_layer."""
+    g = _utils_golden()
+    A, grad = g["cam_A"].astype(np.float64), g["cam_grad"].astype(np.float64)
+    want = np.maximum(np.einsum("bc,bhwc->bhw", grad.mean(axis=(1, 2)), A), 0)[..., None]
+    assert g["cam_out"].shape == want.shape and np.allclose(g["cam_out"], want, rtol=1e-5, atol=1e-7)
+    At = torch.from_numpy(g["cam_A"]).double().requires_grad_(True)
+    y_c = (At * torch.from_numpy(g["cam_grad"]).double()).sum(dim=(1, 2, 3))          # d y_c / dA == the recorded gradient
+    assert np.allclose(M.grad_cam_layer(y_c, At).detach().numpy(), g["cam_out"], rtol=1e-5, atol=1e-7)
