@@ -164,6 +164,36 @@ def gradcam_vectors():
     return {"cam_A": A, "cam_grad": grad, "cam_out": cam}
 
 
+def sunpose_order():
+    """Call order of sunpose_net.model.sunposeEstimation (sunpose_net.py:54-72) from the reference's own file: every layer is a
+    stand-in that appends its name to a log and tags the tensor, so the golden records the wiring (which tensors are returned as
+    activation maps, where the pools sit, flatten -> fc1 -> relu -> fc2 -> relu -> softmax)."""
+    tf = sys.modules["tensorflow"]
+    log = []
+
+    def stage(name):
+        def f(x, *a, **k):
+            log.append(name)
+            return x
+        return f
+    tf.nn.softmax = lambda x: (log.append("softmax"), x)[1]
+    ops = types.ModuleType("ops")
+    ops.conv2d = ops.relu = ops.maxpool2d = lambda *a, **k: None
+    sys.modules["ops"] = ops
+    sys.modules["distortion_aware_ops"] = types.ModuleType("distortion_aware_ops")
+    P = load("/root/reference/sunpose_net.py", "ref_sunpose_net")
+    m = object.__new__(P.model)
+    for name in ("sunlayer1", "pool1_s", "sunlayer2", "pool2_s", "sunlayer3", "pool3_s", "flat", "fc1", "actv1_s", "fc2", "actv2_s"):
+        setattr(m, name, stage(name))
+    x = Tensor(np.zeros((1, 2, 2, 1), np.float32))
+    sm, acts = P.model.sunposeEstimation(m, x, False)
+    lay = object.__new__(P.sunposeLayer)
+    for name in ("conv1", "norm1", "actv1", "conv2", "norm2", "actv2"):
+        setattr(lay, name, stage("layer." + name))
+    P.sunposeLayer.call(lay, x, False)
+    return {"sunpose_call_order": np.array(log), "sunpose_n_acts": np.array([len(acts)])}
+
+
 def main():
     install()
     U = load("/root/reference/tf_utils.py", "ref_tf_utils")
@@ -206,6 +236,7 @@ def main():
     out.update(train_vectors())
     out.update(generator_vectors())
     out.update(gradcam_vectors())
+    out.update(sunpose_order())
     np.savez_compressed(os.path.join(HERE, "utils_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

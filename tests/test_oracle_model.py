@@ -189,3 +189,13 @@ def test_oracle_matches_reference_grad_cam_arithmetic():
     At = torch.from_numpy(g["cam_A"]).double().requires_grad_(True)
     y_c = (At * torch.from_numpy(g["cam_grad"]).double()).sum(dim=(1, 2, 3))          # d y_c / dA == the recorded gradient
     assert np.allclose(M.grad_cam_layer(y_c, At).detach().numpy(), g["cam_out"], rtol=1e-5, atol=1e-7)
+
+
+def test_sunpose_wiring_matches_reference_call_order():
+    """The reference's own sunpose_net.py run with logging stand-ins for every layer (tests/golden/make_golden_utils.py) against the
+    order the oracle (and the package mirror) apply them in."""
+    g = _utils_golden()
+    order = [str(v) for v in g["sunpose_call_order"]]
+    assert order == ["sunlayer1", "pool1_s", "sunlayer2", "pool2_s", "sunlayer3", "pool3_s", "flat", "fc1", "actv1_s", "fc2", "actv2_s",
+                     "softmax", "layer.conv1", "layer.norm1", "layer.actv1", "layer.conv2", "layer.norm2", "layer.actv2"]
+    assert int(g["sunpose_n_acts"][0]) == 3
