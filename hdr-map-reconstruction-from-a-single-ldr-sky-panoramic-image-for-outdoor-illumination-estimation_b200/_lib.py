@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libskydome_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
-EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_SUN_BLEND, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 16, 256
+EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_SUN_BLEND, EPI_MASK, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 16, 32, 256
 MATH_TF32, MATH_3XTF32 = 0, 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -70,6 +70,21 @@ SIGNATURES = {
     "sky_concat2_pad": (_i, [_vp, _i, _vp, _i, _vp, _i, ctypes.c_long, _vp]),
     "sky_vgg_preprocess": (_i, [_vp, _vp, ctypes.c_long, _f, _f, _f, _vp]),
     "sky_sun_radiance": (_i, [_vp] * 5 + [_i, _i, _f, _vp]),
+    "sky_conv2d_transpose_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sky_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 8 + [_f, _i, _vp]),
+    "sky_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 9 + [_vp]),
+    "sky_bn_train_stats": (_i, [_vp] * 5 + [_i, _i, _i, _i, _f, _vp]),
+    "sky_bn_train_apply": (_i, [_vp] * 5 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
+    "sky_bn_train_bwd": (_i, [_vp] * 9 + [_i, _i, _i, _i, _f, _f, _vp]),
+    "sky_resize_bilinear_bwd": (_i, [_vp, _vp] + [_i] * 7 + [_vp]),
+    "sky_sun_radiance_bwd": (_i, [_vp] * 7 + [_i, _i, _f, _vp]),
+    "sky_maxnorm_bwd": (_i, [_vp] * 5 + [ctypes.c_long, _i, _vp]),
+    "sky_sunrad_heads_bwd": (_i, [_vp] * 6 + [_i, _i, _vp]),
+    "sky_train_tail_fwd": (_i, [_vp] * 5 + [_f, _f] + [_vp] * 6 + [ctypes.c_long, _vp]),
+    "sky_train_tail_bwd": (_i, [_vp] * 10 + [_f, _f, _f] + [_vp] * 3 + [ctypes.c_long, _vp]),
+    "sky_lsgan_bwd": (_i, [_vp] * 3 + [_i] * 7 + [_f, _f, _vp]),
+    "sky_l1_bwd": (_i, [_vp] * 4 + [ctypes.c_long, _f, _i, _vp]),
+    "sky_maxpool2x2_bwd_relu": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
 }
 
 
@@ -93,7 +108,7 @@ def load():
 
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
-LAUNCHES_PER_CALL = {"sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
+LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
                      "sky_da_offsets_host": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
                      "sky_debug_band_trace": 0}
 

@@ -20,7 +20,7 @@ __device__ __forceinline__ void smallc_epilogue(float (&acc)[SC_FMAX], const flo
     const bool ok = j < w;
 #pragma unroll
     for (int f = 0; f < SC_FMAX; ++f) {
-        float v = acc[f] + (f < F ? __ldg(bias + f) : 0.f);
+        float v = acc[f] + ((bias && f < F) ? __ldg(bias + f) : 0.f);
         if (flags & SKY_EPI_LEAKY_RELU) v = v > 0.f ? v : v * slope;
         acc[f] = v;
     }
@@ -253,7 +253,7 @@ conv2d_smallf_kernel(const float *__restrict__ x, const float *__restrict__ pack
         for (int f = 0; f < 4; ++f) {
             float val = acc[half][f];
             if (f < F) {
-                val += __ldg(bias + f);
+                if (bias) val += __ldg(bias + f);
                 if (flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * slope;
                 if (flags & SKY_EPI_RESIDUAL) val += __ldg(residual + m * F + f);
                 if (flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
@@ -275,7 +275,7 @@ conv2d_smallf_kernel(const float *__restrict__ x, const float *__restrict__ pack
 int launch_fwd_smallf(const FwdArgs &a)
 {
     if (a.F > 4 || a.C % 4 != 0 || a.k % 2 == 0 || a.plain_stride != 1 || a.stats != nullptr || a.math_mode != SKY_MATH_TF32 ||
-        (a.flags & SKY_EPI_FORCE_DIRECT) || a.ldF > 0)
+        (a.flags & (SKY_EPI_FORCE_DIRECT | SKY_EPI_MASK)) || a.ldF > 0 || a.transposed)
         return SKY_ERR_UNSUPPORTED;
     const size_t smem = ((size_t)a.k * a.k * a.C * 4 + (size_t)(SF_TH + a.k - 1) * (SF_TW + a.k - 1) * (a.C + 4)) * sizeof(float);
     if (smem > 110 * 1024) return SKY_ERR_UNSUPPORTED;
@@ -334,7 +334,7 @@ using namespace sky;
 extern "C" int sky_conv2d_smallc_fwd(const float *x, const float *kernel, const float *bias, float *y, double *stats, int B, int h,
                                      int w, int C, int F, int k, int epilogue_flags, float slope, void *stream)
 {
-    SKY_REQUIRE(x && kernel && bias && y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(x && kernel && y, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0, SKY_ERR_INVALID, "non-positive dimension");
     SKY_REQUIRE(C >= 1 && C <= 4 && F >= 1 && F <= SC_FMAX && k % 2 == 1 && k <= 11, SKY_ERR_UNSUPPORTED,
                 "small-C conv covers C <= 4, F <= 32, odd k <= 11 (got C=%d F=%d k=%d)", C, F, k);

@@ -30,6 +30,10 @@ struct FwdArgs {
     float slope;
     int math_mode;
     int plain_stride;           // 0: distortion-aware sampling; 1 or 2: plain SAME conv with that stride (direct kernel only)
+    // transposed != 0 (direct kernel only): the data gradient of a plain conv of stride `plain_stride` run as a forward pass over dy
+    // (x = dy [B,h,w,C]) with the flipped, transposed kernel: output pixel (i, j) of the out_h x out_w gradient map reads tap (a, b) at
+    // ((i + a - tp_ph0) / stride, (j + b - tp_pw0) / stride) when both divisions are exact and land inside dy
+    int transposed = 0, out_h = 0, out_w = 0, tp_ph0 = 0, tp_pw0 = 0;
     cudaStream_t stream;
 };
 
@@ -53,6 +57,8 @@ __device__ __forceinline__ void sun_blend3(float v[3], const float *__restrict__
 
 // direct-gather kernel (any C): corners read straight from global/L2
 int launch_fwd_direct(const FwdArgs &a);
+// the dispatch behind sky_conv2d_fwd (plain SAME conv: small-filter / band-staged / direct kernel, filter slices)
+int conv2d_plain_entry(FwdArgs a, int stride);
 // halo of input pixels (relative to an output pixel) the taps of a distortion-aware layer touch (da_conv_fwd_band.cu)
 void compute_halo(const float *off, int h, int w, int k, int *hy_lo, int *hy_hi, int *hx_lo, int *hx_hi);
 // fp32 CUDA-core kernel for plain stride-1 layers with F <= 4 filters (conv_smallc.cu); SKY_ERR_UNSUPPORTED when it does not apply

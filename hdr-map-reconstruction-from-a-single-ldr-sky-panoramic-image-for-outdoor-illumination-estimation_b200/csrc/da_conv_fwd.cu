@@ -130,8 +130,16 @@ __device__ __forceinline__ CornerRef sample_corners(const FwdParams &p, int b_im
 {
     if (p.plain) {
         CornerRef r;
-        const int yy = i * p.stride + t / p.k - p.ph0, xx = j * p.stride + t % p.k - p.pw0;
-        const bool ok = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+        int yy = i * p.stride + t / p.k - p.ph0, xx = j * p.stride + t % p.k - p.pw0;
+        bool ok = true;
+        if (p.plain == 2) {
+            // transposed sampler (data gradient of a strided conv): x is dy, (i, j) a pixel of the gradient map; the tap lands on a
+            // dy pixel only when (i + a - ph0, j + b - pw0) is a multiple of the stride
+            yy = i + t / p.k - p.ph0; xx = j + t % p.k - p.pw0;
+            ok = yy >= 0 && xx >= 0 && (yy % p.stride) == 0 && (xx % p.stride) == 0;
+            yy /= p.stride; xx /= p.stride;
+        }
+        ok = ok && yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
         r.off[0] = ok ? ((b_img * p.h + yy) * p.w + xx) * p.C : -1;
         r.w[0] = 1.f;
         r.off[1] = r.off[2] = r.off[3] = -1;
@@ -319,9 +327,10 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
                     const int f = c0 + q;
                     float val = __uint_as_float(r[q]);
                     if (f < p.F) {
-                        val += __ldg(p.bias + f_slice + f);
+                        if (p.bias) val += __ldg(p.bias + f_slice + f);
                         if (p.flags & SKY_EPI_LEAKY_RELU) val = val > 0.f ? val : val * p.slope;
                         if (p.flags & SKY_EPI_RESIDUAL) val += __ldg(p.residual + (size_t)m * p.ldF + f_slice + f);
+                        if (p.flags & SKY_EPI_MASK) val *= __ldg(p.residual + (size_t)m * p.ldF + f_slice + f) > 0.f ? 1.f : p.slope;
                         if (p.flags & SKY_EPI_RELU) val = fmaxf(val, 0.f);
                     }
                     o[q] = val;
@@ -478,13 +487,21 @@ __global__ void resize_bilinear_kernel(const float *__restrict__ x, float *__res
     }
 }
 
-// y = act(y + bias) after a split-K launch (flags: SKY_EPI_LEAKY_RELU only)
-__global__ void conv_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total4, int F4, int flags, float slope)
+// y = act(y + bias) after a split-K launch (flags: SKY_EPI_LEAKY_RELU, or SKY_EPI_MASK with its mask source)
+__global__ void conv_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, const float *__restrict__ mask, long total4,
+                                     int F4, int flags, float slope)
 {
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total4; e += (long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<float4 *>(y)[e];
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(e % F4));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(e % F4));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (flags & SKY_EPI_MASK) {
+            const float4 mk = __ldg(reinterpret_cast<const float4 *>(mask) + e);
+            v.x *= mk.x > 0.f ? 1.f : slope; v.y *= mk.y > 0.f ? 1.f : slope;
+            v.z *= mk.z > 0.f ? 1.f : slope; v.w *= mk.w > 0.f ? 1.f : slope;
+        }
         if (flags & SKY_EPI_LEAKY_RELU) {
             v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
             v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
@@ -522,7 +539,7 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
         const long total4 = (long)p.M * p.ldF / 4;
         int blocks = (int)((total4 + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        conv_finalize_kernel<<<blocks, 256, 0, st>>>(p.y, p.bias, total4, p.ldF / 4, p.flags, p.slope);
+        conv_finalize_kernel<<<blocks, 256, 0, st>>>(p.y, p.bias, p.residual, total4, p.ldF / 4, p.flags, p.slope);
         SKY_CHECK_LAUNCH();
     }
     return SKY_OK;
@@ -590,6 +607,9 @@ int sky::launch_fwd_direct(const FwdArgs &a)
         int th = (p.oh - 1) * p.stride + a.k - a.h, tw = (p.ow - 1) * p.stride + a.k - a.w;
         p.ph0 = (th > 0 ? th : 0) / 2; p.pw0 = (tw > 0 ? tw : 0) / 2;
     }
+    if (a.transposed) {
+        p.plain = 2; p.stride = a.plain_stride; p.oh = a.out_h; p.ow = a.out_w; p.ph0 = a.tp_ph0; p.pw0 = a.tp_pw0;
+    }
     p.M = a.B * p.oh * p.ow;
     p.flags = a.flags; p.slope = a.slope;
     p.nslices = a.nslices > 0 ? a.nslices : 1;
@@ -599,7 +619,8 @@ int sky::launch_fwd_direct(const FwdArgs &a)
         // Few output tiles and a long K (sunRadNet d3 / d4: 16 tiles, 64 / 128 k-blocks): split K over blockIdx.y so the SMs are
         // used; the partial sums meet in y through vector reductions and conv_finalize_kernel applies bias + LeakyReLU.
         const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M * p.nslices;
-        const bool simple_epilogue = !(a.flags & ~(SKY_EPI_LEAKY_RELU | SKY_EPI_FORCE_DIRECT)) && a.stats == nullptr;
+        const bool simple_epilogue = !(a.flags & ~(SKY_EPI_LEAKY_RELU | SKY_EPI_MASK | SKY_EPI_FORCE_DIRECT)) && a.stats == nullptr &&
+                                     (a.flags & (SKY_EPI_LEAKY_RELU | SKY_EPI_MASK)) != (SKY_EPI_LEAKY_RELU | SKY_EPI_MASK);
         if (simple_epilogue && tiles * 2 <= 148 && p.KB >= 16 && (p.ldF % 4) == 0 && (a.F % 4) == 0 && (a.ldF == 0 || a.nslices > 0)) {
             int ksplit = 148 / tiles;
             if (ksplit > p.KB / 4) ksplit = p.KB / 4;
@@ -642,8 +663,10 @@ static int conv2d_plain(FwdArgs a, int stride)
     SKY_REQUIRE(a.B > 0 && a.h > 0 && a.w > 0 && a.C > 0 && a.F > 0, SKY_ERR_INVALID, "non-positive dimension");
     SKY_REQUIRE(a.k >= 1 && a.k <= 15, SKY_ERR_UNSUPPORTED, "kernel size %d outside 1..15", a.k);
     SKY_REQUIRE(stride == 1 || stride == 2, SKY_ERR_UNSUPPORTED, "stride %d not supported (the path uses 1 and 2)", stride);
-    SKY_REQUIRE(a.x && a.packed && a.bias && a.y, SKY_ERR_INVALID, "NULL pointer");
-    SKY_REQUIRE(!(a.flags & SKY_EPI_RESIDUAL) || a.residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL without a residual pointer");
+    SKY_REQUIRE(a.x && a.packed && a.y, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(!(a.flags & (SKY_EPI_RESIDUAL | SKY_EPI_MASK)) || a.residual, SKY_ERR_INVALID, "SKY_EPI_RESIDUAL / SKY_EPI_MASK without its tensor");
+    SKY_REQUIRE((a.flags & (SKY_EPI_RESIDUAL | SKY_EPI_MASK)) != (SKY_EPI_RESIDUAL | SKY_EPI_MASK), SKY_ERR_INVALID,
+                "SKY_EPI_RESIDUAL and SKY_EPI_MASK share one tensor argument");
     SKY_REQUIRE(!(a.flags & SKY_EPI_SUN_BLEND) || (a.aux && a.F == 3 && a.threshold > 0.f), SKY_ERR_INVALID,
                 "SKY_EPI_SUN_BLEND needs the sky prediction, 3 filters and a positive threshold");
     SKY_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.y & 15) == 0 && ((uintptr_t)a.packed & 15) == 0, SKY_ERR_INVALID, "x, y and packed must be 16-byte aligned");
@@ -680,6 +703,8 @@ static int conv2d_plain(FwdArgs a, int stride)
     }
     return SKY_OK;
 }
+
+int sky::conv2d_plain_entry(FwdArgs a, int stride) { return conv2d_plain(a, stride); }
 
 extern "C" int sky_conv2d_fwd(const float *x, const void *packed, const float *bias, float *y, const float *residual, double *stats,
                               int B, int h, int w, int C, int F, int k, int stride, int epilogue_flags, float slope,

@@ -405,7 +405,7 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                     float bv[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (f + u < p.F) bv[u] = __ldg(p.bias + f + u);
+                        if (p.bias && f + u < p.F) bv[u] = __ldg(p.bias + f + u);
                     float s1[4] = { 0.f, 0.f, 0.f, 0.f }, s2[4] = { 0.f, 0.f, 0.f, 0.f };
                     if (f < p.F) {
                         for (int row = row0; row < BLOCK_M; row += rstep) {
@@ -425,6 +425,16 @@ da_conv2d_fwd_band_kernel(const BandParams p, const __grid_constant__ CUtensorMa
                                 } else {
                                     for (int u = 0; u < 4; ++u)
                                         if (f + u < p.F) v[u] += __ldg(p.residual + go + u);
+                                }
+                            }
+                            if (p.flags & SKY_EPI_MASK) {   // activation gradient of the layer below (mask source in `residual`)
+                                if (vec_ok) {
+                                    const float4 mk = __ldg(reinterpret_cast<const float4 *>(p.residual + go));
+                                    v[0] *= mk.x > 0.f ? 1.f : p.slope; v[1] *= mk.y > 0.f ? 1.f : p.slope;
+                                    v[2] *= mk.z > 0.f ? 1.f : p.slope; v[3] *= mk.w > 0.f ? 1.f : p.slope;
+                                } else {
+                                    for (int u = 0; u < 4; ++u)
+                                        if (f + u < p.F) v[u] *= __ldg(p.residual + go + u) > 0.f ? 1.f : p.slope;
                                 }
                             }
                             if (p.flags & SKY_EPI_RELU) {

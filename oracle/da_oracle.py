@@ -27,6 +27,8 @@ import subprocess
 import numpy as np
 import torch
 
+from . import tf32_emu as _emu
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
@@ -124,7 +126,7 @@ def _as_t(a, dtype=torch.float32):
     return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
 
 
-def conv2d_forward(x, kernel, bias, k, dilation=1, skydome=True, off=None, acc_dtype=torch.float32):
+def conv2d_forward(x, kernel, bias, k, dilation=1, skydome=True, off=None, acc_dtype=torch.float32, tf32=None):
     """x [B,h,w,C] NHWC, kernel [k*k*C, F], bias [F] -> [B,h,w,F].  Materialises the same intermediates the reference
     does.  acc_dtype=float64 gives the tolerance anchor (same fp32 indices/weights, fp64 blend and contraction)."""
     x, kernel, bias = _as_t(x), _as_t(kernel), _as_t(bias)
@@ -144,7 +146,9 @@ def conv2d_forward(x, kernel, bias, k, dilation=1, skydome=True, off=None, acc_d
         term = p * torch.from_numpy(s[ww].reshape(-1)).to(acc_dtype)[None, :, None]   # :112
         pix = term if pix is None else pix + term                               # add_n, left to right
     pix = pix.reshape(B, h * w, k * k * C)                                      # :115
-    out = torch.matmul(pix, kernel.to(acc_dtype)) + bias.to(acc_dtype)          # :117-119
+    if tf32 is None:
+        tf32 = C > 4
+    out = _emu.matmul(pix, kernel.to(acc_dtype), tf32=tf32) + bias.to(acc_dtype)   # :117-119
     return out.reshape(B, h, w, -1)
 
 

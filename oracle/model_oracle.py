@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import da_oracle as O
+from . import tf32_emu as emu
 
 
 def instance_norm(x, gamma, beta, eps=1e-3):
@@ -52,7 +53,7 @@ def res_layer(x, blocks, k=3, dilation=1, acc_dtype=torch.float32):
     return x
 
 
-def conv2d_same(x, w4, b, stride=1, acc_dtype=torch.float32):
+def conv2d_same(x, w4, b, stride=1, acc_dtype=torch.float32, tf32=None):
     """tf.nn.conv2d(x, w, strides, 'SAME') + bias_add (ops.py:41-42) on NHWC input, HWIO kernel.  TensorFlow SAME padding:
     out = ceil(n/s), total = max((out-1)*s + k - n, 0), floor(total/2) in front, the rest behind."""
     x, w4, b = O._as_t(x).to(acc_dtype), O._as_t(w4).to(acc_dtype), O._as_t(b).to(acc_dtype)
@@ -64,7 +65,9 @@ def conv2d_same(x, w4, b, stride=1, acc_dtype=torch.float32):
         total = max((out - 1) * stride + k - n, 0)
         pads.append((total // 2, total - total // 2))
     xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
-    y = torch.nn.functional.conv2d(xp, w4.permute(3, 2, 0, 1), bias=b, stride=stride)
+    if tf32 is None:      # layers the library runs on the fp32 pipes: image-like inputs (conv1_d) and 3-filter outputs (conv1_f / conv1_u)
+        tf32 = not ((C <= 4 and w4.shape[3] <= 32 and stride == 1 and k % 2 == 1) or w4.shape[3] <= 4)
+    y = emu.conv2d(xp, w4.permute(3, 2, 0, 1), stride=stride, tf32=tf32) + b.reshape(1, -1, 1, 1)
     return y.permute(0, 2, 3, 1).contiguous()
 
 
@@ -228,18 +231,46 @@ def batch_norm_inference(x, gamma, beta, mean, var, eps=1e-3):
     return x * inv + (beta - mean * inv)
 
 
-def sunrad_net(x, actv_map, w, eps=1e-5, acc_dtype=torch.float32, return_heads=False):
-    """sunRadNet.call (sunrad_net.py:46-71), inference mode.  w: d1..d4 -> dict(kernel [4,4,C,F] (, gamma, beta, moving_mean,
-    moving_variance)), gamma / beta -> (kernel [flat, 1], bias [1])."""
-    dt = acc_dtype
-    h = actv_map.to(dt)
+def batch_norm_train(x, gamma, beta, eps=1e-3):
+    """Keras BatchNormalization with training=True (sunrad_net.py:25, discriminator.py:24): batch statistics over (N, H, W), biased
+    variance to normalise.  Returns (y, batch mean, biased batch variance)."""
+    mean = x.mean(dim=(0, 1, 2))
+    var = ((x - mean) ** 2).mean(dim=(0, 1, 2))
+    inv = gamma * torch.rsqrt(var + eps)
+    return x * inv + (beta - mean * inv), mean.detach(), var.detach()
+
+
+def bn_moving_update(moving_mean, moving_var, mean, var_biased, count, momentum=0.99):
+    """The moving-statistics assignment of a training-mode call (Keras BatchNormalization on the fused path, momentum 0.99):
+    TensorFlow's FusedBatchNormV3 hands back the Bessel-corrected batch variance for the running average (restated from the
+    published kernel, not in /root/reference)."""
+    unbiased = var_biased * (count / max(count - 1, 1))
+    return moving_mean * momentum + mean * (1 - momentum), moving_var * momentum + unbiased * (1 - momentum)
+
+
+def down_blocks(h, w, dt, training=False, bn_stats=None):
+    """d1..d4 of sunrad_net.sunRadNet / discriminator.model: Conv2D(4x4, SAME, no bias) -> BatchNormalization -> LeakyReLU(0.3).
+    training=True: batch statistics; bn_stats (dict) then receives name -> (mean, biased variance, element count per channel)."""
     for name, stride in (("d1", 2), ("d2", 2), ("d3", 2), ("d4", 1)):
         d = w[name]
         kern = O._as_t(d["kernel"]).to(dt)
         h = conv2d_same(h, kern, torch.zeros(kern.shape[-1], dtype=dt), stride=stride, acc_dtype=dt)     # use_bias=False
         if "gamma" in d:
-            h = batch_norm_inference(h, *(O._as_t(d[k]).to(dt) for k in ("gamma", "beta", "moving_mean", "moving_variance")))
+            if training:
+                h, mean, var = batch_norm_train(h, O._as_t(d["gamma"]).to(dt), O._as_t(d["beta"]).to(dt))
+                if bn_stats is not None:
+                    bn_stats[name] = (mean, var, h.shape[0] * h.shape[1] * h.shape[2])
+            else:
+                h = batch_norm_inference(h, *(O._as_t(d[k]).to(dt) for k in ("gamma", "beta", "moving_mean", "moving_variance")))
         h = leaky_relu(h, 0.3)                                              # Keras LeakyReLU() default alpha
+    return h
+
+
+def sunrad_net(x, actv_map, w, eps=1e-5, acc_dtype=torch.float32, return_heads=False, training=False, bn_stats=None):
+    """sunRadNet.call (sunrad_net.py:46-71).  w: d1..d4 -> dict(kernel [4,4,C,F] (, gamma, beta, moving_mean,
+    moving_variance)), gamma / beta -> (kernel [flat, 1], bias [1])."""
+    dt = acc_dtype
+    h = down_blocks(actv_map.to(dt), w, dt, training, bn_stats)
     flat = h.reshape(h.shape[0], -1)
     gamma = flat @ O._as_t(w["gamma"][0]).to(dt) + O._as_t(w["gamma"][1]).to(dt)
     beta = flat @ O._as_t(w["beta"][0]).to(dt) + O._as_t(w["beta"][1]).to(dt)
@@ -435,19 +466,12 @@ def vgg16_pools(bgr, data_dict, mean=(103.939, 116.779, 123.68), acc_dtype=torch
     return p1, p2, p3
 
 
-def discriminator(ldr, hdr, w, acc_dtype=torch.float32):
-    """discriminator.model.call (discriminator.py:41-50), BatchNormalization in inference mode; Conv2D(1, 4) is VALID."""
+def discriminator(ldr, hdr, w, acc_dtype=torch.float32, training=False, bn_stats=None):
+    """discriminator.model.call (discriminator.py:41-50); Conv2D(1, 4) is VALID.  training: see down_blocks."""
     dt = acc_dtype
-    h = torch.cat([ldr.to(dt), hdr.to(dt)], dim=-1)
-    for name, stride in (("d1", 2), ("d2", 2), ("d3", 2), ("d4", 1)):
-        d = w[name]
-        kern = O._as_t(d["kernel"]).to(dt)
-        h = conv2d_same(h, kern, torch.zeros(kern.shape[-1], dtype=dt), stride=stride, acc_dtype=dt)
-        if "gamma" in d:
-            h = batch_norm_inference(h, *(O._as_t(d[k]).to(dt) for k in ("gamma", "beta", "moving_mean", "moving_variance")))
-        h = leaky_relu(h, 0.3)
+    h = down_blocks(torch.cat([ldr.to(dt), hdr.to(dt)], dim=-1), w, dt, training, bn_stats)
     kern, bias = O._as_t(w["out"][0]).to(dt), O._as_t(w["out"][1]).to(dt)
-    y = torch.nn.functional.conv2d(h.permute(0, 3, 1, 2), kern.permute(3, 2, 0, 1), bias=bias)
+    y = emu.conv2d(h.permute(0, 3, 1, 2), kern.permute(3, 2, 0, 1)) + bias.reshape(1, -1, 1, 1)
     return y.permute(0, 2, 3, 1)
 
 
@@ -537,3 +561,103 @@ def sun_train_step_grads(ldr, sunpose_gt, ws, acc_dtype=torch.float64, with_grad
     for n in ("fc1", "fc2"):
         out[n] = (next(it), next(it))
     return loss.detach(), out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full train step (train.py:382-415): both tapes
+# ---------------------------------------------------------------------------------------------------------------------
+def _leafify(obj, dt):
+    """Nested dict / list / tuple of arrays -> the same nesting of fp leaves that require grad."""
+    if isinstance(obj, dict):
+        return {k: _leafify(v, dt) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_leafify(v, dt) for v in obj)
+    return O._as_t(obj).to(dt).clone().requires_grad_(True)
+
+
+def _flatten(obj, out, prefix=""):
+    if isinstance(obj, dict):
+        for k in obj:
+            _flatten(obj[k], out, f"{prefix}{k}.")
+    elif isinstance(obj, (list, tuple)):
+        for i, v in enumerate(obj):
+            _flatten(v, out, f"{prefix}{i}.")
+    else:
+        out.append((prefix[:-1], obj))
+    return out
+
+
+def generator_train_forward(inp, hdr_t, gt, wg, ws, wd, vgg_dict, k=3, threshold=0.12, dt=torch.float64, distortion_aware_sunpose=True,
+                            bn_stats=None):
+    """train.generator_in_step(training=True) (train.py:239-349) on autograd leaves: alpha and the Grad-CAM maps are computed under
+    gen_tape.stop_recording() (:256-271) and are constants; sunRadNet runs with batch statistics (sun_rad_estimation passes `training`
+    through, generator.py:165); the discriminator call inside the generator step uses its moving statistics (train.py:300)."""
+    B, H, W, _ = inp.shape
+
+    def norm_act(y, name):
+        return leaky_relu(instance_norm(y, wg[name][0], wg[name][1]), 0.1)
+
+    x = norm_act(conv2d_same(inp, *wg["conv1_d"], stride=1, acc_dtype=dt), "norm1_d")
+    x = norm_act(conv2d_same(x, *wg["conv2_d"], stride=2, acc_dtype=dt), "norm2_d")
+    x = norm_act(conv2d_same(x, *wg["conv3_d"], stride=2, acc_dtype=dt), "norm3_d")
+    res_out = res_layer(x, wg["res"], k, acc_dtype=dt)
+    sky_gamma = decode_branch(res_out, inp, wg, ("conv3_f", "norm3_f", "conv2_f", "norm2_f", "conv1_f"), dt)
+    sky_lin = hdr_log_decompression(sky_gamma)
+    sm, acts = sunpose_estimation(inp, ws, distortion_aware=distortion_aware_sunpose, acc_dtype=dt)
+    pred = sm.reshape(B, H, W, 1)
+    with torch.no_grad():
+        alpha = torch.clamp((sky_lin.amax(dim=3) - 1.0 + threshold).clamp(min=0.0) / threshold, max=1.0).unsqueeze(-1)
+    y_c = torch.gather(sm, 1, gt.argmax(dim=1, keepdim=True))[:, 0]                     # train.py:263-265
+    cams = [grad_cam_layer(y_c, a).detach() for a in acts]                                # :267-269, outside the tape
+    plz = torch.cat([inp, cams[0], O.resize_bilinear(cams[1], H, W), O.resize_bilinear(cams[2], H, W)], dim=-1)
+    normed = pred / pred.max()                                                            # generator.py:160 (differentiable, max included)
+    sun_rad, gamma_in, beta_in = sunrad_net(normed, plz, wg["sun"], acc_dtype=dt, return_heads=True, training=True, bn_stats=bn_stats)
+    sun_rad_gamma = hdr_log_compression(sun_rad.expand(B, H, W, 3))
+    sun_gamma = decode_branch(res_out, sun_rad_gamma, wg, ("conv3_u", "norm3_u", "conv2_u", "norm2_u", "conv1_u"), dt)
+    sky_s, sun_s = (1.0 - alpha) * sky_gamma, alpha * sun_gamma
+    y_gamma = sky_s + sun_s
+    y_lin = hdr_log_decompression(y_gamma)
+    out = dict(y_final_gamma=y_gamma, y_final_lin=y_lin, sky_pred_lin=hdr_log_decompression(sky_s), sun_pred_lin=hdr_log_decompression(sun_s),
+               alpha=alpha, sm=sm, cams=cams, sun_rad_lin=sun_rad, gamma=gamma_in, beta=beta_in)
+    out["kl"] = kl_divergence(gt, sm)
+    pa = vgg16_pools(y_gamma, vgg_dict, acc_dtype=dt)
+    with torch.no_grad():
+        pb = vgg16_pools(hdr_log_compression(hdr_t), vgg_dict, acc_dtype=dt)
+    out["perceptual"] = sum((a - b).abs().mean() for a, b in zip(pa, pb))
+    out["dog"] = dog_l1(y_lin, hdr_t)
+    out["l1"] = (y_lin - hdr_t).abs().mean()
+    d_fake = discriminator(inp, y_lin, wd, dt, training=False)
+    out["gen"] = ((d_fake - 1.0) ** 2).mean()
+    out["total"] = out["kl"] + 1000.0 * out["dog"] + out["gen"] + 10.0 * out["l1"] + 0.01 * out["perceptual"]
+    return out
+
+
+def train_step(ldr, hdr_t, sunpose_gt, wg, ws, wd, vgg_dict, k=3, threshold=0.12, acc_dtype=torch.float64, distortion_aware_sunpose=True):
+    """train.train_step (train.py:382-415) up to the optimizer: total_gen_loss differentiated w.r.t. every variable of _gen and _sun
+    (:402), total_disc_loss (discriminator_in_step, :351-380, BatchNormalization with batch statistics, one set per call) w.r.t. every
+    variable of _dis (:405).  Returns dict(losses..., outputs..., grads_gen, grads_sun, grads_dis (nested like the weight dicts, None for
+    the non-trainable moving statistics), bn=dict(sun / dis_real / dis_fake -> name -> (mean, biased var, count)))."""
+    dt = acc_dtype
+    Lg, Ls, Ld = _leafify(wg, dt), _leafify(ws, dt), _leafify(wd, dt)
+    inp, hdr_t, gt = O._as_t(ldr).to(dt), O._as_t(hdr_t).to(dt), O._as_t(sunpose_gt).to(dt)
+    bn = dict(sun={}, dis_real={}, dis_fake={})
+    out = generator_train_forward(inp, hdr_t, gt, Lg, Ls, Ld, vgg_dict, k, threshold, dt, distortion_aware_sunpose, bn["sun"])
+    y_lin = out["y_final_lin"].detach()                                                   # D's tape never reaches the generator variables
+    d_real = discriminator(inp, hdr_t, Ld, dt, training=True, bn_stats=bn["dis_real"])    # train.py:360
+    d_fake = discriminator(inp, y_lin, Ld, dt, training=True, bn_stats=bn["dis_fake"])    # :361
+    out["disc"] = 0.5 * ((d_fake ** 2).mean() + ((d_real - 1.0) ** 2).mean())             # :364-368
+    gen_leaves = _flatten(Lg, []) + [("sun." + n, t) for n, t in _flatten(Ls, [])]
+    g = torch.autograd.grad(out["total"], [t for _, t in gen_leaves], retain_graph=True, allow_unused=True)
+    dis_leaves = _flatten(Ld, [])
+    gd = torch.autograd.grad(out["disc"], [t for _, t in dis_leaves], allow_unused=True)
+    res = {kk: (v.detach() if isinstance(v, torch.Tensor) else [c.detach() for c in v]) for kk, v in out.items()}
+    res["grads_gen"] = {n: gg for (n, _), gg in zip(gen_leaves, g)}
+    res["grads_dis"] = {n: gg for (n, _), gg in zip(dis_leaves, gd)}
+    res["bn"] = bn
+    return res
+
+
+def rmsprop_step(w, ms, g, lr=1e-4, rho=0.9, eps=1e-7):
+    """Keras RMSprop (train.py:201-202): ms = rho ms + (1 - rho) g^2; w -= lr g / (sqrt(ms) + eps)."""
+    ms = rho * ms + (1.0 - rho) * g * g
+    return w - lr * g / (np.sqrt(ms) + eps), ms
