@@ -85,6 +85,7 @@ SIGNATURES = {
     "sky_lsgan_bwd": (_i, [_vp] * 3 + [_i] * 7 + [_f, _f, _vp]),
     "sky_l1_bwd": (_i, [_vp] * 4 + [ctypes.c_long, _f, _i, _vp]),
     "sky_maxpool2x2_bwd_relu": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "sky_zero": (_i, [_vp, _sz, _vp]),
 }
 
 
@@ -109,7 +110,7 @@ def load():
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
 LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
-                     "sky_da_offsets_host": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
+                     "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
                      "sky_debug_band_trace": 0}
 
 

@@ -312,14 +312,17 @@ static void same_pad(int n, int k, int s, int *out, int *front)
     *front = (total > 0 ? total : 0) / 2;
 }
 
-extern "C" int sky_conv2d_bwd_data(const float *dy, const void *packed_t, float *dx, const float *mask_src, int B, int h, int w, int C,
+extern "C" int sky_conv2d_bwd_data(const float *dy, const void *packed_t, float *dx, const float *aux, int B, int h, int w, int C,
                                    int F, int k, int stride, int epilogue_flags, float slope, int math_mode, void *stream)
 {
+    const float *mask_src = aux;
     SKY_REQUIRE(dy && packed_t && dx, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension");
     SKY_REQUIRE(k >= 1 && k <= 15 && (stride == 1 || stride == 2), SKY_ERR_UNSUPPORTED, "kernel size %d / stride %d not supported", k, stride);
-    SKY_REQUIRE(!(epilogue_flags & ~SKY_EPI_MASK), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK only");
-    SKY_REQUIRE(!(epilogue_flags & SKY_EPI_MASK) || mask_src, SKY_ERR_INVALID, "SKY_EPI_MASK without a mask source");
+    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_MASK | SKY_EPI_RESIDUAL)), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK or SKY_EPI_RESIDUAL only");
+    SKY_REQUIRE((epilogue_flags & (SKY_EPI_MASK | SKY_EPI_RESIDUAL)) != (SKY_EPI_MASK | SKY_EPI_RESIDUAL), SKY_ERR_INVALID,
+                "SKY_EPI_MASK and SKY_EPI_RESIDUAL share the aux tensor");
+    SKY_REQUIRE(!(epilogue_flags & (SKY_EPI_MASK | SKY_EPI_RESIDUAL)) || aux, SKY_ERR_INVALID, "SKY_EPI_MASK / SKY_EPI_RESIDUAL without the aux tensor");
     int oh, ow, ph0, pw0;
     same_pad(h, k, stride, &oh, &ph0);
     same_pad(w, k, stride, &ow, &pw0);

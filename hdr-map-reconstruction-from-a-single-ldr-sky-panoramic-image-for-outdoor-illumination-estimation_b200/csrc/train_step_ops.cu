@@ -455,6 +455,13 @@ __global__ void maxpool2x2_bwd_relu_kernel(const float *__restrict__ x, const fl
 
 using namespace sky;
 
+extern "C" int sky_zero(void *p, size_t bytes, void *stream)
+{
+    SKY_REQUIRE(p != nullptr || bytes == 0, SKY_ERR_INVALID, "NULL pointer");
+    if (bytes) SKY_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+    return SKY_OK;
+}
+
 extern "C" int sky_bn_train_stats(const float *x, double *sums, float *mean_var, float *moving_mean, float *moving_var, int B, int hw, int F,
                                   int groups, float momentum, void *stream)
 {

@@ -1,11 +1,16 @@
-"""Host-side mirror of the residual trunk of the reference's generator.py: the same class names and constructor
-signatures (``resBlock(filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1)``,
-``resLayer(filters, filter_in, k_h, k_w, strides=1, dilation_rate=1)``) wired the way the commented lines
-generator.py:14,18 wire them: distortion-aware convolutions inside every res-block.
+"""Host-side mirror of the reference's generator.py: the same class names and constructor signatures
+(``resBlock(filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1)``,
+``resLayer(filters, filter_in, k_h, k_w, strides=1, dilation_rate=1)``, ``model(batch_size, im_height, im_width, da_kernel_size,
+dilation_rate)``).  ``distortion_aware=True`` (default) wires every res-block conv the way the commented lines generator.py:14,18 do
+(``distortion_aware_ops.conv2d``: the north-star path); ``distortion_aware=False`` gives the plain ``ops.conv2d`` wiring that is live
+in the reference as committed (generator.py:13,17) — same variables ([k,k,C,F] kernels), so a reference SKY checkpoint maps onto it.
 
-    resBlock.call  (generator.py:26-35):  x + IN(conv2(leaky_relu_0.1(IN(conv1(x)))))
+    resBlock.call  (generator.py:26-35):  identity(x) + IN(conv2(leaky_relu_0.1(IN(conv1(x)))))
 
 Launches per res-block: conv1 (+ fused IN moments) -> IN apply + LeakyReLU -> conv2 (+ moments) -> IN apply + residual.
+Training direction (train.train_step): ``model.train_forward`` keeps every intermediate, ``model.train_backward`` walks the graph in
+reverse — instance-norm backward fused with the LeakyReLU masks, data gradients as gathers, pipelined tcgen05 weight gradients —
+writing every gradient into the flat buffer of ``_flat.FlatVars``.
 """
 from __future__ import annotations
 
@@ -14,8 +19,44 @@ import torch
 from . import _lib
 from ._lib import LIB, check
 from . import ops
-from .distortion_aware_ops import _require_cuda, _stream, conv2d as da_conv2d
+from .distortion_aware_ops import _require_cuda, _stream, conv2d as da_conv2d, conv2d_backward, zero_
 from .sunrad_net import sunRadNet
+
+
+def _kernel_attr(conv):
+    """Name of the kernel / bias attributes of the three conv flavours (reference variable names)."""
+    if isinstance(conv, da_conv2d):
+        return "kernel", "bias"
+    return ("kernel" if isinstance(conv, ops.deconv2d) else "w"), "biases"
+
+
+def conv_owner_list(conv):
+    k, b = _kernel_attr(conv)
+    return [(conv, k), (conv, b)]
+
+
+def instnorm_backward(norm, z, stats, dy, act, slope, fv, extra=None):
+    """tfa InstanceNormalization backward fused with the LeakyReLU mask (act = the activation that followed, or None)."""
+    B, h, w, F = z.shape
+    dz = torch.empty_like(z)
+    sums = torch.empty(B, F, 2, dtype=torch.float64, device=z.device)
+    check(LIB.sky_instnorm_bwd(z.data_ptr(), stats.data_ptr(), norm.gamma.data_ptr(), dy.data_ptr(), None if act is None else act.data_ptr(),
+                               None if extra is None else extra.data_ptr(), sums.data_ptr(), dz.data_ptr(), fv.grad(norm, "gamma").data_ptr(),
+                               fv.grad(norm, "beta").data_ptr(), B, h, w, F, norm.epsilon, float(slope), _stream()))
+    return dz
+
+
+def conv_backward(conv, x, dy, fv, need_dx=True, residual=None):
+    """Weight / bias gradients into the flat buffer and (optionally) the data gradient (+ residual) of either conv flavour."""
+    kname, bname = _kernel_attr(conv)
+    dk, db = fv.grad(conv, kname), fv.grad(conv, bname)
+    if isinstance(conv, da_conv2d):
+        dx = None
+        if need_dx and residual is not None:
+            dx = residual.clone()
+        return conv2d_backward(conv, x, dy, need_dx=need_dx, dx_out=dx, dk_out=dk, db_out=db, accumulate_dx=residual is not None)[0]
+    conv.backward_filter(x, dy, dk, db)
+    return conv.backward_data(x, dy, residual=residual) if need_dx else None
 
 
 class InstanceNormalization:
@@ -56,92 +97,135 @@ class InstanceNormalization:
 
 
 class resBlock:
-    def __init__(self, filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1, *, math_mode=None, device="cuda"):
+    def __init__(self, filter_in, filter_out, k_h=3, k_w=3, strides=1, dilation_rate=1, *, distortion_aware=True, math_mode=None,
+                 device="cuda"):
         if k_h != k_w:
             raise ValueError("the distortion-aware conv takes one kernel_size (generator.py:14)")
-        self.conv1 = da_conv2d(filter_out, kernel_size=k_h, strides=strides, dilation_rate=dilation_rate,
-                               math_mode=math_mode, device=device)            # generator.py:14
+
+        def conv():
+            if distortion_aware:                                                # generator.py:14,18
+                return da_conv2d(filter_out, kernel_size=k_h, strides=strides, dilation_rate=dilation_rate, math_mode=math_mode,
+                                 device=device)
+            return ops.conv2d(filter_out, strides=strides, k_h=k_h, k_w=k_w, math_mode=math_mode, device=device)   # :13,17
+        self.distortion_aware = bool(distortion_aware)
+        self.filter_out = filter_out
+        self.conv1 = conv()
         self.norm1 = InstanceNormalization(device=device)                       # :15
-        self.conv2 = da_conv2d(filter_out, kernel_size=k_h, strides=strides, dilation_rate=dilation_rate,
-                               math_mode=math_mode, device=device)            # :18
+        self.conv2 = conv()
         self.norm2 = InstanceNormalization(device=device)                       # :19
-        if filter_in != filter_out:                                             # :21-24 (never taken: the trunk is 128 -> 128)
-            raise NotImplementedError("1x1 projection shortcut (generator.py:24) is outside the hot path: every "
-                                      "res-block of the reference model has filter_in == filter_out == 128")
+        self.identity = None                                                    # :21-22 `lambda x: x`
+        if filter_in != filter_out:                                             # :23-24 1x1 projection shortcut
+            self.identity = ops.conv2d(filter_out, strides=1, k_h=1, k_w=1, math_mode=math_mode, device=device)
         self._stats = None
 
     def _moments(self, B, C, device):
         if self._stats is None or self._stats.shape[1] != B or self._stats.shape[2] != C:
-            self._stats = torch.zeros(2, B, C, 2, dtype=torch.float64, device=device)
-        else:
-            self._stats.zero_()
+            self._stats = torch.empty(2, B, C, 2, dtype=torch.float64, device=device)
+        zero_(self._stats)
         return self._stats[0], self._stats[1]
 
     @property
     def trainable_variables(self):
         return (self.conv1.trainable_variables + self.norm1.trainable_variables + self.conv2.trainable_variables
-                + self.norm2.trainable_variables)
+                + self.norm2.trainable_variables + (self.identity.trainable_variables if self.identity is not None else []))
+
+    def owner_list(self):
+        """(object, attribute) of every trainable variable, in trainable_variables order."""
+        out = []
+        for conv, norm in ((self.conv1, self.norm1), (self.conv2, self.norm2)):
+            out += conv_owner_list(conv) + [(norm, "gamma"), (norm, "beta")]
+        if self.identity is not None:
+            out += conv_owner_list(self.identity)
+        return out
 
     def build(self, input_shape):
+        if self.identity is not None and not self.identity.built:
+            self.identity.build(tuple(input_shape))
         for conv, norm in ((self.conv1, self.norm1), (self.conv2, self.norm2)):
             if not conv.built:
                 conv.build(tuple(input_shape))
-            shape = tuple(input_shape[:3]) + (conv.filters,)
+            shape = tuple(input_shape[:3]) + (self.filter_out,)
             if norm.gamma is None:
                 norm.build(shape)
             input_shape = shape
 
     def set_weights(self, w):
         """w: dict conv{1,2}_kernel / conv{1,2}_bias / norm{1,2}_gamma / norm{1,2}_beta (numpy or torch), the reference's
-        variable names under each res-block."""
+        variable names under each res-block; kernels as [k*k*C, F] (either wiring; the plain variable is the same memory as [k,k,C,F])."""
         for i, (conv, norm) in enumerate(((self.conv1, self.norm1), (self.conv2, self.norm2)), start=1):
-            conv.kernel.copy_(torch.as_tensor(w[f"conv{i}_kernel"]))
-            conv.bias.copy_(torch.as_tensor(w[f"conv{i}_bias"]))
+            kname, bname = _kernel_attr(conv)
+            kv = getattr(conv, kname)
+            kv.copy_(torch.as_tensor(w[f"conv{i}_kernel"]).reshape(kv.shape))
+            getattr(conv, bname).copy_(torch.as_tensor(w[f"conv{i}_bias"]))
             norm.gamma.copy_(torch.as_tensor(w[f"norm{i}_gamma"]))
             norm.beta.copy_(torch.as_tensor(w[f"norm{i}_beta"]))
+        if self.identity is not None and "identity_kernel" in w:
+            self.identity.w.copy_(torch.as_tensor(w["identity_kernel"]).reshape(self.identity.w.shape))
+            self.identity.biases.copy_(torch.as_tensor(w["identity_bias"]))
 
-    def call(self, x):
+    def call(self, x, save=False):
         x = _require_cuda(x, "inputs")
         if not self.conv1.built:
-            self.conv1.build(tuple(x.shape))
+            self.build(tuple(x.shape))
         B = x.shape[0]
-        s1, s2 = self._moments(B, self.conv1.filters, x.device)
+        s1, s2 = self._moments(B, self.filter_out, x.device)
         conv1 = self.conv1.call(x, stats=s1)                                    # :28
         actv1 = self.norm1.apply(conv1, s1, leaky_slope=0.1)                    # :29-30
-        if not self.conv2.built:
-            self.conv2.build(tuple(actv1.shape))
         conv2 = self.conv2.call(actv1, stats=s2)                                # :32
-        return self.norm2.apply(conv2, s2, residual=x)                          # :33-35
+        ident = x if self.identity is None else self.identity.call(x)           # :21-24
+        out = self.norm2.apply(conv2, s2, residual=ident)                       # :33-35
+        if save:
+            self._saved = (x, conv1, actv1, conv2, s1, s2)
+        return out
 
     __call__ = call
 
+    def backward(self, dout, fv):
+        """Gradient w.r.t. the block input; every variable gradient goes to fv (dgamma / dbeta accumulate: fv.flat_g zeroed per step)."""
+        x, c1, a1, c2, s1, s2 = self._saved
+        dc2 = instnorm_backward(self.norm2, c2, s2, dout, None, 0.1, fv)                         # IN2 (:33)
+        da1 = conv_backward(self.conv2, a1, dc2, fv)                                             # conv2 (:32)
+        dc1 = instnorm_backward(self.norm1, c1, s1, da1, a1, 0.1, fv)                            # lrelu (:30) + IN1 (:29)
+        if self.identity is None:
+            return conv_backward(self.conv1, x, dc1, fv, residual=dout)                          # conv1 (:28) + identity branch (:35)
+        dx = conv_backward(self.identity, x, dout, fv)                                           # 1x1 projection (:24)
+        return conv_backward(self.conv1, x, dc1, fv, residual=dx)
+
 
 class resLayer:
-    def __init__(self, filters, filter_in, k_h, k_w, strides=1, dilation_rate=1, *, math_mode=None, device="cuda"):
+    def __init__(self, filters, filter_in, k_h, k_w, strides=1, dilation_rate=1, *, distortion_aware=True, math_mode=None, device="cuda"):
         self.sequence = list()
         for f_in, f_out in zip([filter_in] + list(filters), filters):           # generator.py:43-44
             self.sequence.append(resBlock(f_in, f_out, k_h=k_h, k_w=k_w, strides=strides, dilation_rate=dilation_rate,
-                                          math_mode=math_mode, device=device))
+                                          distortion_aware=distortion_aware, math_mode=math_mode, device=device))
 
     @property
     def trainable_variables(self):
         return [v for unit in self.sequence for v in unit.trainable_variables]
 
+    def owner_list(self):
+        return [o for unit in self.sequence for o in unit.owner_list()]
+
     def build(self, input_shape):
         for unit in self.sequence:
             unit.build(input_shape)
-            input_shape = tuple(input_shape[:3]) + (unit.conv2.filters,)
+            input_shape = tuple(input_shape[:3]) + (unit.filter_out,)
 
     def set_weights(self, blocks):
         for unit, w in zip(self.sequence, blocks):
             unit.set_weights(w)
 
-    def call(self, x):
+    def call(self, x, save=False):
         for unit in self.sequence:                                              # :46-49
-            x = unit(x)
+            x = unit(x, save=save)
         return x
 
     __call__ = call
+
+    def backward(self, dout, fv):
+        for unit in reversed(self.sequence):
+            dout = unit.backward(dout, fv)
+        return dout
 
 
 class _NormAct:
@@ -153,15 +237,38 @@ class _NormAct:
         self.norm = InstanceNormalization(device=device)
         self._stats = None
 
-    def __call__(self, x):
+    def __call__(self, x, save=False):
         B = x.shape[0]
         F = self.conv.output_channels
         if self._stats is None or self._stats.shape[0] != B:
-            self._stats = torch.zeros(B, F, 2, dtype=torch.float64, device=x.device)
-        else:
-            self._stats.zero_()
+            self._stats = torch.empty(B, F, 2, dtype=torch.float64, device=x.device)
+        zero_(self._stats)
         y = self.conv(x, stats=self._stats)
-        return self.norm.apply(y, self._stats, leaky_slope=0.1)
+        a = self.norm.apply(y, self._stats, leaky_slope=0.1)
+        if save:
+            # the conv's own input: for ops.deconv2d that is the resized tensor (ops.py:122)
+            xin = self.conv._last_resized if isinstance(self.conv, ops.deconv2d) else x
+            self._saved = (x, xin, y, a)
+        return a
+
+    def owner_list(self):
+        return conv_owner_list(self.conv) + [(self.norm, "gamma"), (self.norm, "beta")]
+
+    def backward(self, da, fv, need_dx=True, dx_out=None, dx_accumulate=False):
+        """da: gradient w.r.t. the stage output (after the LeakyReLU).  Returns the gradient w.r.t. the stage input; deconv stages can
+        write it into dx_out, or (dx_accumulate) add it to what dx_out holds."""
+        x, xin, z, a = self._saved
+        dz = instnorm_backward(self.norm, z, self._stats, da, a, 0.1, fv)
+        dxin = conv_backward(self.conv, xin, dz, fv, need_dx=need_dx)
+        if not need_dx:
+            return None
+        if not isinstance(self.conv, ops.deconv2d):
+            return dxin
+        B, h, w, C = x.shape
+        dx = dx_out if dx_out is not None else torch.empty_like(x)
+        check(LIB.sky_resize_bilinear_bwd(dxin.data_ptr(), dx.data_ptr(), B, h, w, C, xin.shape[1], xin.shape[2],
+                                          int(bool(dx_accumulate)), _stream()))                          # adjoint of ops.py:122
+        return dx
 
 
 class model:
@@ -169,8 +276,8 @@ class model:
     (sun_decode / sun_rad_estimation / blending, :127-175) depends on sunpose_net, Grad-CAM and sunRadNet, which are not
     part of this round."""
 
-    def __init__(self, batch_size=32, im_height=32, im_width=128, da_kernel_size=3, dilation_rate=1, *, math_mode=None,
-                 device="cuda"):
+    def __init__(self, batch_size=32, im_height=32, im_width=128, da_kernel_size=3, dilation_rate=1, *, distortion_aware=True,
+                 math_mode=None, device="cuda"):
         self.fc_dim = int(im_height * im_width)
         self.im_height, self.im_width = im_height, im_width
         kw = dict(math_mode=math_mode, device=device)
@@ -180,7 +287,8 @@ class model:
         self.conv3_d = ops.conv2d(output_channels=128, k_h=3, k_w=3, strides=2, **kw)
         self._enc = [_NormAct(c, device) for c in (self.conv1_d, self.conv2_d, self.conv3_d)]
         self.norm1_d, self.norm2_d, self.norm3_d = (e.norm for e in self._enc)
-        self.res = resLayer((128,) * 6, 128, k_h=da_kernel_size, k_w=da_kernel_size, strides=1, dilation_rate=dilation_rate, **kw)
+        self.res = resLayer((128,) * 6, 128, k_h=da_kernel_size, k_w=da_kernel_size, strides=1, dilation_rate=dilation_rate,
+                            distortion_aware=distortion_aware, **kw)
         # sky_decode (generator.py:69-76)
         self.conv3_f = ops.deconv2d(output_channels=64, output_imshape=[int(im_height / 2), int(im_width / 2)], k_h=3, k_w=3,
                                     method='resize', **kw)
@@ -202,10 +310,46 @@ class model:
         self._gmax = None
         self._side = None
 
-    def encode(self, x, training="training"):
+    def encode(self, x, training="training", save=False):
         for stage in self._enc:                       # generator.py:94-106
-            x = stage(x)
-        return self.res(x)                            # :108
+            x = stage(x, save=save)
+        return self.res(x, save=save)                 # :108
+
+    # ---- training direction (train.generator_in_step with training=True, train.py:239-349) ----------------------------------------
+    def owner_list(self):
+        """(object, attribute) of every trainable variable of the generator (order of the flat buffer)."""
+        out = []
+        for st in self._enc:
+            out += st.owner_list()
+        out += self.res.owner_list()
+        for st in self._dec:
+            out += st.owner_list()
+        out += conv_owner_list(self.conv1_f)
+        for st in self._dec_u:
+            out += st.owner_list()
+        out += conv_owner_list(self.conv1_u)
+        for d in (self.sun.d1, self.sun.d2, self.sun.d3, self.sun.d4):
+            out += [(d, "kernel")] + ([(d, "gamma"), (d, "beta")] if d.apply_norm else [])
+        out += [(self.sun, "gb_kernel"), (self.sun, "gb_bias")]
+        return out
+
+    def decode_train(self, x, stages, last):
+        """Decoder up to the raw output of its 7x7 conv (bias included, no activation): the tail kernel applies the rest."""
+        for stage in stages:
+            x = stage(x, save=True)
+        return last(x), x
+
+    def decode_backward(self, dc, stages, last, last_in, fv, dres, accumulate):
+        """dc: gradient w.r.t. the raw 7x7 conv output; writes (accumulate=False) or adds the gradient w.r.t. the trunk output into dres."""
+        g = conv_backward(last, last_in, dc, fv)                              # conv1_f / conv1_u (generator.py:120, 150)
+        g = stages[1].backward(g, fv)                                         # conv2_* + IN + lrelu (+ resize adjoint)
+        stages[0].backward(g, fv, dx_out=dres, dx_accumulate=accumulate)      # conv3_*
+
+    def encode_backward(self, dres, fv):
+        g = self.res.backward(dres, fv)
+        g = self._enc[2].backward(g, fv)
+        g = self._enc[1].backward(g, fv)
+        self._enc[0].backward(g, fv, need_dx=False)
 
     def sky_decode(self, x, _input, training="training", log_decompress=False):
         for stage in self._dec:                       # generator.py:112-118

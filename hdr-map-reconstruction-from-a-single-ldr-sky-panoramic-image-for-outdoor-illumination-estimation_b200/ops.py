@@ -34,6 +34,69 @@ def _epilogue_flags(leaky_slope, residual, relu, log_decompress):
     return flags
 
 
+class TransposedPack:
+    """Cache of the flipped, transposed kernel of a plain conv layer — unpacked [k*k*F, C] (`scratch`) and packed for the tensor-core
+    kernels — which turns the layer's data gradient into a forward pass over dy (sky_conv2d_bwd_data)."""
+
+    def __init__(self, k, C, F, math_mode, device):
+        self.k, self.C, self.F, self.mode = k, C, F, _MATH[math_mode]
+        self.scratch = torch.empty(k * k * F * C, dtype=torch.float32, device=device)
+        self.packed = torch.empty(LIB.sky_da_packed_weight_bytes(F, C, k, self.mode), dtype=torch.uint8, device=device)
+        self.key = None
+
+    def get(self, w):
+        key = (w.data_ptr(), w._version)
+        if self.key != key:
+            check(LIB.sky_conv2d_transpose_weights(w.data_ptr(), self.scratch.data_ptr(), self.C, self.F, self.k, 1, _stream()))
+            check(LIB.sky_da_pack_weights(self.scratch.data_ptr(), self.packed.data_ptr(), self.F, self.C, self.k, self.mode, _stream()))
+            self.key = key
+        return self.packed
+
+
+def conv_backward_data(tp: TransposedPack, w, in_shape, dy, stride=1, mask_src=None, slope=0.0, residual=None):
+    """dx [in_shape] of a plain SAME conv with kernel `w` ([k,k,C,F]) for the upstream gradient dy; mask_src: the activation tensor
+    that fed the conv (its LeakyReLU / ReLU gradient is applied in the epilogue); residual: a gradient to add (identity branch)."""
+    B, h, w_, C = in_shape
+    dy = _require_cuda(dy, "dy")
+    dx = torch.empty(in_shape, dtype=torch.float32, device=dy.device)
+    k, F = tp.k, tp.F
+    packed = tp.get(w)
+    if F <= 4 and C <= 32 and stride == 1 and k % 2 == 1 and k <= 11 and mask_src is None and residual is None:
+        # 3-filter layers (conv1_f / conv1_u): the transposed conv has a 3-channel input -> the fp32 small-C kernel on the unpacked kernel
+        check(LIB.sky_conv2d_smallc_fwd(dy.data_ptr(), tp.scratch.data_ptr(), None, dx.data_ptr(), None, B, h, w_, F, C, k, 0, 0.0, _stream()))
+        return dx
+    if mask_src is not None and residual is not None:
+        raise ValueError("mask_src and residual share one epilogue slot")
+    flags = _lib.EPI_MASK if mask_src is not None else (_lib.EPI_RESIDUAL if residual is not None else 0)
+    aux = mask_src if mask_src is not None else residual
+    check(LIB.sky_conv2d_bwd_data(dy.data_ptr(), packed.data_ptr(), dx.data_ptr(), _ptr(aux), B, h, w_, C, F, k, int(stride), flags,
+                                  float(slope), tp.mode, _stream()))
+    return dx
+
+
+_ZERO_TABLES = {}
+
+
+def conv_backward_filter(x, dy, k, stride, dk_out, db_out=None, accumulate=False, C_store=None):
+    """dkernel [k*k*C_store, F] (+ dbias) of a plain SAME conv at input x for the upstream gradient dy."""
+    x, dy = _require_cuda(x, "x"), _require_cuda(dy, "dy")
+    B, h, w_, C = x.shape
+    F = dy.shape[-1]
+    if C <= 4:
+        # image-like input (conv1_d): the small-C distortion-aware weight-gradient kernel through an all-zero offset table (every tap on
+        # a grid point == the plain SAME conv for odd k, stride 1)
+        if stride != 1 or k % 2 == 0 or accumulate:
+            raise NotImplementedError("small-C weight gradient: stride 1, odd kernel, overwrite")
+        key = (h, k, str(x.device))
+        if key not in _ZERO_TABLES:
+            _ZERO_TABLES[key] = torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device)
+        check(LIB.sky_da_conv2d_smallc_bwd_filter(x.data_ptr(), dy.data_ptr(), _ZERO_TABLES[key].data_ptr(), dk_out.data_ptr(),
+                                                  _ptr(db_out), B, h, w_, C, F, k, _stream()))
+        return
+    check(LIB.sky_conv2d_bwd_filter(x.data_ptr(), dy.data_ptr(), None, dk_out.data_ptr(), _ptr(db_out), B, h, w_, C, int(C_store or C), F, k,
+                                    int(stride), int(bool(accumulate)), _stream()))
+
+
 class _PlainConvCore:
     """Shared by conv2d and deconv2d: weight packing and the two launch routes."""
 
@@ -49,7 +112,7 @@ class _PlainConvCore:
         self.built = False
         self._packed = None
         self._packed_key = None
-        self._zero_tab = None
+        self._tpack = None
 
     def _build_weights(self, channels_in):
         k, F = self.k_h, self.output_channels
@@ -79,20 +142,21 @@ class _PlainConvCore:
             self._packed_key = key
         return self._packed
 
-    def backward_data(self, x, dy):
-        """Gradient of a stride-1, odd-k SAME conv w.r.t. its input: the distortion-aware data-gradient kernel with an all-zero
-        offset table (every tap lands on a grid point, so the bilinear scatter degenerates to the transposed conv)."""
-        if self.stride != 1 or self.k_h % 2 == 0:
-            raise NotImplementedError("data gradient is built for the stride-1 odd-kernel layers of sunpose_net.py")
-        x, dy = _require_cuda(x, "x"), _require_cuda(dy, "dy")
-        B, h, w, C = x.shape
-        k, F = self.k_h, self.output_channels
-        if self._zero_tab is None or tuple(self._zero_tab.shape) != (h, k * k, 2):
-            self._zero_tab = torch.zeros((h, k * k, 2), dtype=torch.float32, device=x.device)
-        dx = torch.empty_like(x)
-        check(LIB.sky_da_conv2d_bwd_data(dy.data_ptr(), self._zero_tab.data_ptr(), self._weight().data_ptr(), dx.data_ptr(),
-                                         B, h, w, C, F, k, 0, _stream()))
-        return dx
+    def _invalidate(self):
+        self._packed_key = None
+        if self._tpack is not None:
+            self._tpack.key = None
+
+    def backward_data(self, x, dy, mask_src=None, slope=0.0, residual=None):
+        """Gradient of the SAME conv (stride 1 or 2, any kernel size) w.r.t. its input `x` (only its shape is used): a forward pass
+        over dy with the flipped, transposed kernel (csrc/conv_bwd.cu) — a gather, no atomics."""
+        if self._tpack is None:
+            self._tpack = TransposedPack(self.k_h, self._channels_in, self.output_channels, self.math_mode, self.device)
+        return conv_backward_data(self._tpack, self._weight(), tuple(x.shape), dy, self.stride, mask_src, slope, residual)
+
+    def backward_filter(self, x, dy, dk_out, db_out=None, accumulate=False):
+        """Weight / bias gradient of the SAME conv at input x (for deconv2d: the resized input)."""
+        conv_backward_filter(x, dy, self.k_h, self.stride, dk_out.view(-1, self.output_channels), db_out, accumulate)
 
     def _conv(self, x, leaky_slope=None, residual=None, relu=False, log_decompress=False, stats=None, blend=None):
         B, h, w, C = x.shape
@@ -188,6 +252,7 @@ class deconv2d(_PlainConvCore):
         if not self.built:
             self.build(tuple(x.shape))
         im_resized = resize_bilinear(x, self.output_imshape[0], self.output_imshape[1])   # ops.py:122
+        self._last_resized = im_resized                                                    # the conv's input: its weight gradient needs it
         return self._conv(im_resized, **epilogue)                                          # ops.py:124
 
     __call__ = call

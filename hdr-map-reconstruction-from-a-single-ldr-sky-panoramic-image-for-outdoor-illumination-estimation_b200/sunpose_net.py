@@ -12,7 +12,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import LIB, check
-from .distortion_aware_ops import _initializer, _require_cuda, _stream, conv2d as da_conv2d, conv2d_backward
+from .distortion_aware_ops import _initializer, _require_cuda, _stream, conv2d as da_conv2d, conv2d_backward, zero_
 from .generator import InstanceNormalization
 
 
@@ -40,6 +40,9 @@ class Dense:
         k = int(input_shape[-1])
         self.kernel = _initializer("glorot_uniform", (k, self.units), k, self.units, self.device)
         self.bias = torch.zeros(self.units, dtype=torch.float32, device=self.device)
+
+    def _invalidate(self):
+        self._kernel_t_key = None
 
     def kernel_transposed(self):
         """W^T [units, in], rebuilt only when the variable changes: the backward streams it like the forward streams W."""
@@ -117,9 +120,8 @@ class sunposeLayer:
         x = _require_cuda(x, "x")
         B = x.shape[0]
         if self._stats is None or self._stats.shape[1] != B:
-            self._stats = torch.zeros(2, B, self.filter_out, 2, dtype=torch.float64, device=x.device)
-        else:
-            self._stats.zero_()
+            self._stats = torch.empty(2, B, self.filter_out, 2, dtype=torch.float64, device=x.device)
+        zero_(self._stats)
         conv1 = self.conv1(x, stats=self._stats[0])                                  # :21
         actv1 = self.norm1.apply(conv1, self._stats[0], leaky_slope=0.0)             # :22-23  relu == leaky_relu(0)
         conv2 = self.conv2(actv1, stats=self._stats[1])                              # :25

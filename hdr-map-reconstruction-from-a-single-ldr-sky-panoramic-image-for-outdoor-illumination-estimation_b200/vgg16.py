@@ -50,3 +50,50 @@ class Vgg16:
         return pool1, pool2, pool3
 
     __call__ = call
+
+    # ---- perceptual-loss direction (train.py:306-312): features of [prediction; target] in one batch, data gradient for the first half ----
+    def forward_saved(self, bgr):
+        x = _require_cuda(bgr, "bgr")
+        B, H, W, _ = x.shape
+        pre = torch.empty((B, H, W, 4), dtype=torch.float32, device=x.device)
+        check(LIB.sky_vgg_preprocess(x.data_ptr(), pre.data_ptr(), B * H * W, *[float(m) for m in self.VGG_MEAN], _stream()))
+        relu = dict(relu=True)
+        c11 = self.conv1_1(pre, **relu); c12 = self.conv1_2(c11, **relu); p1 = maxpool2d(c12)
+        c21 = self.conv2_1(p1, **relu); c22 = self.conv2_2(c21, **relu); p2 = maxpool2d(c22)
+        c31 = self.conv3_1(p2, **relu); c32 = self.conv3_2(c31, **relu); c33 = self.conv3_3(c32, **relu); p3 = maxpool2d(c33)
+        self._saved = (pre, c11, c12, p1, c21, c22, p2, c31, c32, c33, p3)
+        return p1, p2, p3
+
+    def perceptual_backward(self, n_pred, scale, acc3):
+        """The saved batch holds n_pred predictions followed by n_pred targets.  acc3 (3 zeroed fp64) receives sum |pool_i(pred) -
+        pool_i(target)|; returns d(scale * sum_i mean |.|) / d(preprocessed prediction) [n_pred,H,W,4] (vgg16.py is frozen: data
+        gradients only, each conv's ReLU mask in the epilogue of the data gradient above it)."""
+        pre, c11, c12, p1, c21, c22, p2, c31, c32, c33, p3 = self._saved
+        n = n_pred
+        st = _stream()
+
+        def l1(pool, g, i, accumulate):
+            a, b = pool[:n], pool[n:2 * n]
+            check(LIB.sky_l1_bwd(a.data_ptr(), b.data_ptr(), g.data_ptr(), acc3[i:i + 1].data_ptr(), a.numel(), float(scale) / a.numel(),
+                                 int(accumulate), st))
+
+        def pool_bwd(x, dy):
+            B, h, w, C = x.shape
+            dx = torch.empty_like(x)
+            check(LIB.sky_maxpool2x2_bwd_relu(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), B, h, w, C, 1, st))
+            return dx
+
+        g = torch.empty_like(p3[:n])
+        l1(p3, g, 2, False)
+        g = pool_bwd(c33[:n], g)
+        g = self.conv3_3.backward_data(c32[:n], g, mask_src=c32[:n], slope=0.0)
+        g = self.conv3_2.backward_data(c31[:n], g, mask_src=c31[:n], slope=0.0)
+        g = self.conv3_1.backward_data(p2[:n], g)
+        l1(p2, g, 1, True)
+        g = pool_bwd(c22[:n], g)
+        g = self.conv2_2.backward_data(c21[:n], g, mask_src=c21[:n], slope=0.0)
+        g = self.conv2_1.backward_data(p1[:n], g)
+        l1(p1, g, 0, True)
+        g = pool_bwd(c12[:n], g)
+        g = self.conv1_2.backward_data(c11[:n], g, mask_src=c11[:n], slope=0.0)
+        return self.conv1_1.backward_data(pre[:n], g)

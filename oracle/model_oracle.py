@@ -66,7 +66,10 @@ def conv2d_same(x, w4, b, stride=1, acc_dtype=torch.float32, tf32=None):
         pads.append((total // 2, total - total // 2))
     xp = torch.nn.functional.pad(x.permute(0, 3, 1, 2), (pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
     if tf32 is None:      # layers the library runs on the fp32 pipes: image-like inputs (conv1_d) and 3-filter outputs (conv1_f / conv1_u)
-        tf32 = not ((C <= 4 and w4.shape[3] <= 32 and stride == 1 and k % 2 == 1) or w4.shape[3] <= 4)
+        F = w4.shape[3]
+        tf32 = not (C <= 4 and F <= 32 and stride == 1 and k % 2 == 1)
+        if F <= 4 and stride == 1 and k % 2 == 1:
+            tf32 = "weights"
     y = emu.conv2d(xp, w4.permute(3, 2, 0, 1), stride=stride, tf32=tf32) + b.reshape(1, -1, 1, 1)
     return y.permute(0, 2, 3, 1).contiguous()
 

@@ -82,6 +82,11 @@ def matmul(a, b, tf32=True):
 
 
 def conv2d(xp, w, stride=1, tf32=True):
+    """tf32 = True: both operands rounded, forward and backward; "weights": the small-filter kernel of the library (3-filter layers
+    conv1_f / conv1_u) multiplies fp32 activations with the TF32-rounded packed kernel on the fp32 pipes — forward only, its backward
+    passes use the unrounded variable."""
+    if ENABLED and tf32 == "weights":
+        return torch.nn.functional.conv2d(xp.contiguous(), (w + (round_tf32(w) - w).detach()).contiguous(), stride=stride)
     if ENABLED and tf32:
         return _Conv2dTF32.apply(xp, w, stride)
     return torch.nn.functional.conv2d(xp.contiguous(), w.contiguous(), stride=stride)

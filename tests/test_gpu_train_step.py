@@ -1,0 +1,427 @@
+"""GPU parity of the full GAN train step (train.train_step, train.py:382-415) and of the backward kernels it is made of, against
+autograd through the fp64 oracle (oracle/model_oracle.py) — every call goes through the C ABI.
+
+Tolerances (relative L2 unless stated):
+  plain-conv data / weight gradients (TF32 operands, fp32 accumulate in TMEM) vs fp64 autograd       2e-3   (measured ~3e-4)
+  BatchNormalization forward / backward, resize adjoint, tail, radiance head, LSGAN / L1 adjoints     1e-5   (fp32 elementwise / fp64 sums)
+  whole step, `3xtf32` forward convs vs the fp64 oracle: losses 2e-3, every gradient of G u Sun and D  5e-2  (TF32 backward convs; conv
+      biases in front of a norm have exactly-zero gradients and are compared absolutely)
+  whole step, `tf32` vs the TF32-EMULATING oracle (operands rounded to 10 mantissa bits, what TensorFlow computes on any Ampere-or-newer
+      GPU): losses 5e-3, gradients 5e-2; vs the fp64 oracle the same run is only held to 3e-1 (ReLU-mask / arg-max flips).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import da_oracle as O
+from oracle import model_oracle as M
+from oracle import tf32_emu
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# convolution backward kernels
+# --------------------------------------------------------------------------------------------------------------------------------
+CONV_CASES = [  # (B, h, w, C, F, k, stride)
+    (2, 16, 32, 32, 64, 3, 2),      # conv2_d
+    (2, 8, 16, 64, 128, 3, 2),      # conv3_d
+    (2, 16, 32, 8, 64, 4, 2),       # d1 (6 -> 8 channel-padded input)
+    (2, 8, 16, 64, 128, 4, 2),      # d2
+    (2, 4, 16, 256, 512, 4, 1),     # d4: even kernel at stride 1, 512 filters (two slices)
+    (3, 4, 16, 512, 1, 4, 1),       # the discriminator's output conv as its SAME map
+    (2, 16, 32, 32, 3, 7, 1),       # conv1_f / conv1_u: 3 filters
+    (2, 16, 32, 64, 32, 3, 1),      # conv2_f on the resized map (band-staged kernel)
+    (2, 8, 16, 128, 64, 3, 1),      # conv3_f
+    (2, 8, 16, 4, 64, 3, 1),        # VGG conv1_1 on the 4-channel preprocessed image (small-filter kernel in the transposed pass)
+    (2, 8, 16, 128, 256, 3, 1),     # VGG conv3_1
+    (2, 4, 8, 256, 256, 3, 1),      # VGG conv3_2 / 3_3
+    (2, 9, 15, 32, 64, 3, 2),       # odd map sizes under stride 2 (asymmetric SAME padding)
+    (2, 7, 9, 32, 32, 1, 1),        # 1x1 projection shortcut (generator.py:24)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "B%d_%dx%d_C%d_F%d_k%d_s%d" % c)
+def test_plain_conv_backward(pkg, case):
+    B, h, w, C, F, k, s = case
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    w4 = (rng.standard_normal((k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    xt = T(x).double().requires_grad_(True)
+    wt = T(w4).double().requires_grad_(True)
+    bt = torch.zeros(F, dtype=torch.float64, requires_grad=True)
+    y = M.conv2d_same(xt, wt, bt, stride=s, acc_dtype=torch.float64)
+    dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+    y.backward(T(dy).double())
+    ops, LIB, check = pkg.ops, pkg._lib.LIB, pkg._lib.check
+    wd, xd, dyd = T(w4).cuda(), T(x).cuda(), T(dy).cuda()
+    # data gradient, then the same with the LeakyReLU mask of the layer below in the epilogue
+    tp = ops.TransposedPack(k, C, F, "tf32", "cuda")
+    dx = ops.conv_backward_data(tp, wd, (B, h, w, C), dyd, s)
+    assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 2e-3, rel(dx.cpu().numpy(), xt.grad.numpy())
+    mask_src = T(rng.standard_normal((B, h, w, C)).astype(np.float32)).cuda()
+    dxm = ops.conv_backward_data(tp, wd, (B, h, w, C), dyd, s, mask_src=mask_src, slope=0.3)
+    want = xt.grad.numpy() * np.where(mask_src.cpu().numpy() > 0, 1.0, 0.3)
+    assert rel(dxm.cpu().numpy(), want) < 2e-3
+    if s == 1 and C <= 256:
+        res = T(rng.standard_normal((B, h, w, C)).astype(np.float32)).cuda()
+        dxr = ops.conv_backward_data(tp, wd, (B, h, w, C), dyd, s, residual=res)
+        assert rel(dxr.cpu().numpy(), xt.grad.numpy() + res.cpu().numpy()) < 2e-3
+    # weight / bias gradient (overwrite, then accumulate on top)
+    if C % 4 == 0 and C > 4:
+        dk = torch.full((k * k * C, F), 7.0, device="cuda")
+        db = torch.full((F,), 7.0, device="cuda")
+        ops.conv_backward_filter(xd, dyd, k, s, dk, db)
+        assert rel(dk.cpu().numpy(), wt.grad.numpy().reshape(k * k * C, F)) < 2e-3, rel(dk.cpu().numpy(), wt.grad.numpy().reshape(k * k * C, F))
+        assert rel(db.cpu().numpy(), bt.grad.numpy()) < 1e-4
+        ops.conv_backward_filter(xd, dyd, k, s, dk, db, accumulate=True)
+        assert rel(dk.cpu().numpy(), 2 * wt.grad.numpy().reshape(k * k * C, F)) < 2e-3
+    if C == 8:      # channel padding: rows of channels 6, 7 are not stored (sunrad_net.py:37 on the 6-channel input)
+        dk6 = torch.zeros((k * k * 6, F), device="cuda")
+        ops.conv_backward_filter(xd, dyd, k, s, dk6, None, C_store=6)
+        assert rel(dk6.cpu().numpy(), wt.grad.numpy()[:, :, :6, :].reshape(k * k * 6, F)) < 2e-3
+
+
+@pytest.mark.parametrize("B,h,w,C,F,k", [(2, 8, 32, 128, 128, 3), (2, 16, 64, 64, 64, 3), (2, 32, 128, 32, 32, 7), (3, 8, 32, 64, 128, 3)])
+def test_da_weight_gradient_pipelined(pkg, B, h, w, C, F, k):
+    """The pipelined weight-gradient kernel with the distortion-aware sampler vs autograd through the materialised oracle."""
+    rng = np.random.default_rng(B * 1000 + C + k)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    kern = (rng.standard_normal((k * k * C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    bias = np.zeros(F, np.float32)
+    dy = rng.standard_normal((B, h, w, F)).astype(np.float32)
+    _, want_dk, want_db = (g.numpy() for g in O.conv2d_backward(x, kern, bias, dy, k, acc_dtype=torch.float64))
+    layer = pkg.conv2d(F, kernel_size=k, kernel_initializer=kern, bias_initializer=bias)
+    layer.build((B, h, w, C))
+    xd, dyd = T(x).cuda(), T(dy).cuda()
+    dk, db = torch.empty((k * k * C, F), device="cuda"), torch.empty(F, device="cuda")
+    pkg._lib.check(pkg._lib.LIB.sky_conv2d_bwd_filter(xd.data_ptr(), dyd.data_ptr(), layer.offset_table.data_ptr(), dk.data_ptr(), db.data_ptr(),
+                                                      B, h, w, C, C, F, k, 1, 0, st()))
+    assert rel(dk.cpu().numpy(), want_dk) < 2e-3, rel(dk.cpu().numpy(), want_dk)
+    assert rel(db.cpu().numpy(), want_db) < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# elementwise / reduction kernels of the train step
+# --------------------------------------------------------------------------------------------------------------------------------
+def test_batch_norm_train_kernels(pkg):
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(0)
+    for (B, hw, F, groups) in ((4, 48, 128, 2), (6, 20, 512, 1), (2, 130, 256, 2)):
+        x = (rng.standard_normal((B, hw, F)) * 2 + 0.5).astype(np.float32)
+        gamma, beta = (1 + 0.2 * rng.standard_normal(F)).astype(np.float32), (0.2 * rng.standard_normal(F)).astype(np.float32)
+        up = rng.standard_normal((B, hw, F)).astype(np.float32)
+        mm0, mv0 = rng.standard_normal(F).astype(np.float32), rng.uniform(0.5, 2, F).astype(np.float32)
+        xt, gt_, bt_ = T(x).double().requires_grad_(True), T(gamma).double().requires_grad_(True), T(beta).double().requires_grad_(True)
+        halves, mm, mv = [], mm0.astype(np.float64), mv0.astype(np.float64)
+        per = B // groups
+        for g in range(groups):
+            y, mean, var = M.batch_norm_train(xt[g * per:(g + 1) * per].reshape(per, hw, 1, F), gt_, bt_)
+            halves.append(M.leaky_relu(y.reshape(per, hw, F), 0.3))
+            mm, mv = M.bn_moving_update(mm, mv, mean.numpy(), var.numpy(), per * hw)
+        act = torch.cat(halves, 0)
+        (act * T(up).double()).sum().backward()
+        xd, gd, bd, upd = T(x).cuda(), T(gamma).cuda(), T(beta).cuda(), T(up).cuda()
+        sums = torch.empty((groups, F, 2), dtype=torch.float64, device="cuda")
+        mean_var = torch.empty((groups, F, 2), device="cuda")
+        mmd, mvd = T(mm0).cuda(), T(mv0).cuda()
+        check(LIB.sky_bn_train_stats(xd.data_ptr(), sums.data_ptr(), mean_var.data_ptr(), mmd.data_ptr(), mvd.data_ptr(), B, hw, F, groups, 0.99, st()))
+        a = torch.empty_like(xd)
+        check(LIB.sky_bn_train_apply(xd.data_ptr(), mean_var.data_ptr(), gd.data_ptr(), bd.data_ptr(), a.data_ptr(), B, hw, F, groups, 1e-3, 1, 0.3, st()))
+        assert rel(a.cpu().numpy(), act.detach().numpy()) < 1e-5
+        assert rel(mmd.cpu().numpy(), mm) < 1e-5 and rel(mvd.cpu().numpy(), mv) < 1e-5
+        dx = torch.empty_like(xd)
+        dgamma, dbeta = torch.zeros(F, device="cuda"), torch.zeros(F, device="cuda")
+        check(LIB.sky_bn_train_bwd(xd.data_ptr(), mean_var.data_ptr(), gd.data_ptr(), upd.data_ptr(), a.data_ptr(), sums.data_ptr(), dx.data_ptr(),
+                                   dgamma.data_ptr(), dbeta.data_ptr(), B, hw, F, groups, 1e-3, 0.3, st()))
+        assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 2e-5, rel(dx.cpu().numpy(), xt.grad.numpy())
+        assert rel(dgamma.cpu().numpy(), gt_.grad.numpy()) < 2e-5 and rel(dbeta.cpu().numpy(), bt_.grad.numpy()) < 2e-5
+
+
+def test_resize_adjoint(pkg):
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(1)
+    for (B, h, w, C, oh, ow) in ((2, 8, 32, 128, 16, 64), (2, 16, 64, 64, 32, 128), (1, 5, 7, 4, 10, 14)):
+        x = T(rng.standard_normal((B, h, w, C)).astype(np.float32)).double().requires_grad_(True)
+        y = O.resize_bilinear(x, oh, ow)
+        dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        y.backward(T(dy).double())
+        dyd = T(dy).cuda()
+        dx = torch.empty((B, h, w, C), device="cuda")
+        check(LIB.sky_resize_bilinear_bwd(dyd.data_ptr(), dx.data_ptr(), B, h, w, C, oh, ow, 0, st()))
+        assert rel(dx.cpu().numpy(), x.grad.numpy()) < 1e-5
+        check(LIB.sky_resize_bilinear_bwd(dyd.data_ptr(), dx.data_ptr(), B, h, w, C, oh, ow, 1, st()))
+        assert rel(dx.cpu().numpy(), 2 * x.grad.numpy()) < 1e-5
+
+
+def test_sun_radiance_head_backward(pkg):
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(2)
+    B, H, W, K = 3, 8, 16, 256
+    hw = H * W
+    sm0 = torch.softmax(T(rng.standard_normal((B, hw)).astype(np.float32) * 3), -1)
+    flat0 = rng.standard_normal((B, K)).astype(np.float32)
+    W0, b0 = (rng.standard_normal((K, 2)) * 0.1).astype(np.float32), np.array([6.0, -1.0], np.float32)   # large gamma: part of the map clamps
+    up = rng.standard_normal((B, hw, 3)).astype(np.float32)
+    sm, flat, Wt, bt = sm0.double().requires_grad_(True), T(flat0).double().requires_grad_(True), T(W0).double().requires_grad_(True), T(b0).double().requires_grad_(True)
+    gb = flat @ Wt + bt
+    gam, bet = torch.sigmoid(gb[:, 0:1]), torch.sigmoid(gb[:, 1:2])
+    x = sm / sm.max()
+    v = torch.exp(-((1 - x) ** 2) / (bet + 1e-5)) * gam / (bet * float(np.sqrt(np.float32(np.pi))) + 1e-5)
+    vc = torch.where(v > 30000.0, torch.full_like(v, 30000.0), v)
+    out3 = (torch.log(1 + 10 * vc) / np.log(11.0)).unsqueeze(-1).expand(B, hw, 3)
+    (out3 * T(up).double()).sum().backward()
+    smd, flatd, Wd, bd, upd = sm0.cuda(), T(flat0).cuda(), T(W0).cuda(), T(b0).cuda(), T(up).cuda()
+    gbd = torch.empty((B, 2), device="cuda")
+    check(LIB.sky_dense_fwd(flatd.data_ptr(), Wd.data_ptr(), bd.data_ptr(), gbd.data_ptr(), B, K, 2, 0, st()))
+    gmax = torch.zeros(1, device="cuda")
+    check(LIB.sky_max_nonneg(smd.data_ptr(), gmax.data_ptr(), smd.numel(), st()))
+    o3 = torch.empty((B, hw, 3), device="cuda")
+    check(LIB.sky_sun_radiance(smd.data_ptr(), gmax.data_ptr(), gbd.data_ptr(), o3.data_ptr(), None, B, hw, 1e-5, st()))
+    assert rel(o3.cpu().numpy(), out3.detach().numpy()) < 1e-5
+    dnorm = torch.empty((B, hw), device="cuda")
+    dgb64, red2 = torch.empty((B, 2), dtype=torch.float64, device="cuda"), torch.empty(2, dtype=torch.float64, device="cuda")
+    check(LIB.sky_sun_radiance_bwd(smd.data_ptr(), gmax.data_ptr(), gbd.data_ptr(), upd.data_ptr(), dnorm.data_ptr(), dgb64.data_ptr(), red2.data_ptr(),
+                                   B, hw, 1e-5, st()))
+    dsm = torch.ones((B, hw), device="cuda")
+    check(LIB.sky_maxnorm_bwd(smd.data_ptr(), gmax.data_ptr(), dnorm.data_ptr(), red2.data_ptr(), dsm.data_ptr(), smd.numel(), 1, st()))
+    assert rel(dsm.cpu().numpy() - 1.0, sm.grad.numpy()) < 1e-4, rel(dsm.cpu().numpy() - 1.0, sm.grad.numpy())
+    dW, db, dflat = torch.empty((K, 2), device="cuda"), torch.empty(2, device="cuda"), torch.empty((B, K), device="cuda")
+    check(LIB.sky_sunrad_heads_bwd(flatd.data_ptr(), Wd.data_ptr(), dgb64.data_ptr(), dW.data_ptr(), db.data_ptr(), dflat.data_ptr(), B, K, st()))
+    assert rel(dW.cpu().numpy(), Wt.grad.numpy()) < 1e-4 and rel(db.cpu().numpy(), bt.grad.numpy()) < 1e-4
+    assert rel(dflat.cpu().numpy(), flat.grad.numpy()) < 1e-4
+
+
+def test_train_tail_kernels(pkg):
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(3)
+    n, thr, slope = 4096, 0.12, 0.1
+    arrs = dict(c_sky=rng.standard_normal((n, 3)) * 0.5, c_sun=rng.standard_normal((n, 3)) * 0.5, srg=rng.uniform(0, 1.5, (n, 3)),
+                ldr=rng.uniform(0, 1, (n, 3)), hdr_t=rng.uniform(0, 3, (n, 3)), g_dog=rng.standard_normal((n, 3)),
+                g_dis8=rng.standard_normal((n, 8)), g_vgg4=rng.standard_normal((n, 4)))
+    arrs = {k: v.astype(np.float32) for k, v in arrs.items()}
+    c_sky, c_sun, srg = (T(arrs[k]).double().requires_grad_(True) for k in ("c_sky", "c_sun", "srg"))
+    ldr, hdr_t, g_dog, g_dis8, g_vgg4 = (T(arrs[k]).double() for k in ("ldr", "hdr_t", "g_dog", "g_dis8", "g_vgg4"))
+    s = torch.relu(ldr + M.leaky_relu(c_sky, slope))
+    u = torch.relu(srg + M.leaky_relu(c_sun, slope))
+    with torch.no_grad():
+        alpha = torch.clamp((M.hdr_log_decompression(s).amax(1, keepdim=True) - 1 + thr).clamp(min=0) / thr, max=1)
+    y_gamma = (1 - alpha) * s + alpha * u
+    y_lin = M.hdr_log_decompression(y_gamma)
+    w_l1, w_vgg = 0.37, 255.0
+    ((y_lin * (g_dog + g_dis8[:, 3:6])).sum() + w_l1 * (y_lin - hdr_t).abs().sum() + w_vgg * (y_gamma * g_vgg4[:, :3]).sum()).backward()
+    d = {k: T(v).cuda() for k, v in arrs.items()}
+    outs = [torch.empty((n, 3), device="cuda") for _ in range(4)]
+    al = torch.empty(n, device="cuda")
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    check(LIB.sky_train_tail_fwd(d["c_sky"].data_ptr(), d["c_sun"].data_ptr(), d["ldr"].data_ptr(), d["srg"].data_ptr(), d["hdr_t"].data_ptr(), thr, slope,
+                                 outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), al.data_ptr(), acc.data_ptr(), n, st()))
+    assert rel(outs[0].cpu().numpy(), y_gamma.detach().numpy()) < 1e-5 and rel(outs[1].cpu().numpy(), y_lin.detach().numpy()) < 1e-5
+    assert rel(outs[2].cpu().numpy(), M.hdr_log_decompression((1 - alpha) * s).detach().numpy()) < 1e-5
+    assert rel(outs[3].cpu().numpy(), M.hdr_log_decompression(alpha * u).detach().numpy()) < 1e-5
+    assert np.abs(al.cpu().numpy() - alpha.numpy()[:, 0]).max() < 1e-4
+    assert abs(float(acc) / float((y_lin - hdr_t).abs().sum()) - 1) < 1e-5
+    dcs, dcu, dsr = (torch.empty((n, 3), device="cuda") for _ in range(3))
+    check(LIB.sky_train_tail_bwd(d["c_sky"].data_ptr(), d["c_sun"].data_ptr(), d["ldr"].data_ptr(), d["srg"].data_ptr(), al.data_ptr(), outs[1].data_ptr(),
+                                 d["hdr_t"].data_ptr(), d["g_dog"].data_ptr(), d["g_dis8"].data_ptr(), d["g_vgg4"].data_ptr(), w_l1, w_vgg, slope,
+                                 dcs.data_ptr(), dcu.data_ptr(), dsr.data_ptr(), n, st()))
+    # a pixel whose fp32 alpha sits exactly on a clamp edge can differ from the fp64 alpha by rounding: compare with a small absolute slack
+    for got, want in ((dcs, c_sky.grad), (dcu, c_sun.grad), (dsr, srg.grad)):
+        assert rel(got.cpu().numpy(), want.numpy()) < 1e-3, rel(got.cpu().numpy(), want.numpy())
+
+
+def test_lsgan_l1_and_pool_adjoints(pkg):
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(4)
+    B, hh, ww = 3, 4, 16
+    dmap = rng.standard_normal((B, hh, ww)).astype(np.float32)
+    dd = T(dmap).cuda()
+    g = torch.empty_like(dd)
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    check(LIB.sky_lsgan_bwd(dd.data_ptr(), g.data_ptr(), acc.data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 1.0, 0.25, st()))
+    want = np.zeros_like(dmap)
+    want[:, 1:hh - 2, 1:ww - 2] = 0.25 * 2 * (dmap[:, 1:hh - 2, 1:ww - 2] - 1)
+    assert np.abs(g.cpu().numpy() - want).max() < 1e-6
+    assert abs(float(acc) - float(((dmap[:, 1:hh - 2, 1:ww - 2].astype(np.float64) - 1) ** 2).sum())) < 1e-4
+    a, b = rng.standard_normal(5000).astype(np.float32), rng.standard_normal(5000).astype(np.float32)
+    b[:50] = a[:50]
+    ga = torch.ones(5000, device="cuda")
+    acc.zero_()
+    ad, bd = T(a).cuda(), T(b).cuda()
+    check(LIB.sky_l1_bwd(ad.data_ptr(), bd.data_ptr(), ga.data_ptr(), acc.data_ptr(), 5000, 0.5, 1, st()))
+    assert np.abs(ga.cpu().numpy() - (1 + 0.5 * np.sign(a - b))).max() < 1e-6
+    assert abs(float(acc) / float(np.abs(a.astype(np.float64) - b).sum()) - 1) < 1e-5
+    # max-pool gradient with the ReLU mask of the layer below
+    x = np.maximum(rng.standard_normal((2, 7, 9, 8)), 0).astype(np.float32)
+    xt = T(x).double().requires_grad_(True)
+    pre = xt.clone()
+    y = M.maxpool2x2_same(torch.relu(pre))
+    dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+    y.backward(T(dy).double())
+    xd, dyd = T(x).cuda(), T(dy).cuda()
+    dx = torch.empty_like(xd)
+    check(LIB.sky_maxpool2x2_bwd_relu(xd.data_ptr(), dyd.data_ptr(), dx.data_ptr(), 2, 7, 9, 8, 1, st()))
+    # windows whose maximum is 0 route nothing with the mask (relu'(0) = 0), like autograd through relu
+    assert np.abs(dx.cpu().numpy() - xt.grad.numpy()).max() < 1e-6
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# the whole step
+# --------------------------------------------------------------------------------------------------------------------------------
+def _inputs(B, H, W, seed=5):
+    rng = np.random.default_rng(seed)
+    ldr = (np.round(255 * rng.uniform(0, 1, (B, H, W, 3))) / 255).astype(np.float32)
+    hdr_t = (rng.uniform(0, 1, (B, H, W, 3)) ** 3 * 3).astype(np.float32)
+    gt = torch.softmax(T(rng.standard_normal((B, H * W)).astype(np.float32) * 4), -1).numpy()
+    return ldr, hdr_t, gt
+
+
+def _gpu_grads(step):
+    """Gradients of the last train_step keyed like the oracle's flattened names."""
+    gen, sun, dis, fv, fvd = step._gen, step._sun, step._dis, step.fv_gen, step.fv_dis
+    g, d = {}, {}
+    for name in ("conv1_d", "conv2_d", "conv3_d", "conv1_f", "conv1_u"):
+        layer = getattr(gen, name)
+        g[name + ".0"], g[name + ".1"] = fv.grad(layer, "w"), fv.grad(layer, "biases")
+    for name in ("conv3_f", "conv2_f", "conv3_u", "conv2_u"):
+        layer = getattr(gen, name)
+        g[name + ".0"], g[name + ".1"] = fv.grad(layer, "kernel"), fv.grad(layer, "biases")
+    for name in ("norm1_d", "norm2_d", "norm3_d", "norm3_f", "norm2_f", "norm3_u", "norm2_u"):
+        norm = getattr(gen, name)
+        g[name + ".0"], g[name + ".1"] = fv.grad(norm, "gamma"), fv.grad(norm, "beta")
+    for i, unit in enumerate(gen.res.sequence):
+        for j, (conv, norm) in enumerate(((unit.conv1, unit.norm1), (unit.conv2, unit.norm2)), start=1):
+            g[f"res.{i}.conv{j}_kernel"], g[f"res.{i}.conv{j}_bias"] = fv.grad(conv, "kernel"), fv.grad(conv, "bias")
+            g[f"res.{i}.norm{j}_gamma"], g[f"res.{i}.norm{j}_beta"] = fv.grad(norm, "gamma"), fv.grad(norm, "beta")
+    for name in ("d1", "d2", "d3", "d4"):
+        for owner, fvx, out, prefix in ((getattr(gen.sun, name), fv, g, "sun."), (getattr(dis, name), fvd, d, "")):
+            out[f"{prefix}{name}.kernel"] = fvx.grad(owner, "kernel")
+            if owner.apply_norm:
+                out[f"{prefix}{name}.gamma"], out[f"{prefix}{name}.beta"] = fvx.grad(owner, "gamma"), fvx.grad(owner, "beta")
+    gbk, gbb = fv.grad(gen.sun, "gb_kernel"), fv.grad(gen.sun, "gb_bias")
+    g["sun.gamma.0"], g["sun.gamma.1"], g["sun.beta.0"], g["sun.beta.1"] = gbk[:, 0:1], gbb[0:1], gbk[:, 1:2], gbb[1:2]
+    for name in ("sunlayer1", "sunlayer2", "sunlayer3"):
+        layer = getattr(sun, name)
+        for j, (conv, norm) in enumerate(((layer.conv1, layer.norm1), (layer.conv2, layer.norm2)), start=1):
+            g[f"sun.{name}.conv{j}_kernel"], g[f"sun.{name}.conv{j}_bias"] = fv.grad(conv, "kernel"), fv.grad(conv, "bias")
+            g[f"sun.{name}.norm{j}_gamma"], g[f"sun.{name}.norm{j}_beta"] = fv.grad(norm, "gamma"), fv.grad(norm, "beta")
+    for name in ("fc1", "fc2"):
+        g[f"sun.{name}.0"], g[f"sun.{name}.1"] = fv.grad(getattr(sun, name), "kernel"), fv.grad(getattr(sun, name), "bias")
+    d["out.0"], d["out.1"] = fvd.grad(dis, "out_kernel"), fvd.grad(dis, "out_bias")
+    return g, d
+
+
+def _zero_grad_bias(name):
+    """Conv biases in front of an instance norm (and nothing else) have exactly-zero gradients: only noise on both sides."""
+    return (name.endswith("_bias") and ("res." in name or "sunlayer" in name)) or (name.endswith(".1") and name.split(".")[0] in
+                                                                                   ("conv1_d", "conv2_d", "conv3_d", "conv3_f", "conv2_f", "conv3_u", "conv2_u"))
+
+
+@pytest.mark.parametrize("mode,emulate,tol_loss,tol_y,tol_grad", [("3xtf32", False, 2e-3, 1e-3, 5e-2), ("tf32", True, 5e-3, 2e-3, 5e-2),
+                                                                  ("tf32", False, 2e-2, 1e-2, 3e-1)])
+def test_train_step_vs_autograd(pkg, mode, emulate, tol_loss, tol_y, tol_grad):
+    B, H, W = 2, 32, 128
+    ldr, hdr_t, gt = _inputs(B, H, W)
+    wg, ws, wd = M.random_full_generator_weights(3, H, W), M.random_sunpose_weights(5, H, W), M.random_discriminator_weights(4)
+    dd = pkg.vgg16.random_data_dict(1)
+    with tf32_emu.emulate(emulate):
+        want = M.train_step(ldr, hdr_t, gt, wg, ws, wd, dd)
+    step = pkg.train.Step(batch_size=B, im_height=H, im_width=W, vgg_data_dict=dd, math_mode=mode)
+    x = T(ldr).cuda()
+    step.init_training(B)
+    step._gen.set_weights(wg)
+    step._sun.set_weights(ws)
+    step._dis.set_weights(wd)
+    w_gen0, w_dis0 = step.fv_gen.flat_w.clone(), step.fv_dis.flat_w.clone()
+    outs = step.train_step([T(hdr_t).cuda(), x], T(gt).cuda())
+    torch.cuda.synchronize()
+    got = {k: float(v) for k, v in step.last_losses.items()}
+    report = {"loss." + k: abs(got[k] / float(want[k]) - 1) for k in ("kl", "perceptual", "dog", "l1", "gen", "total", "disc")}
+    logl = lambda y: np.log1p(10 * np.asarray(y, np.float64)) / np.log(11.0)
+    report["y_final_lin"] = rel(logl(outs[0].cpu().numpy()), logl(want["y_final_lin"].numpy()))
+    g, d = _gpu_grads(step)
+    absolute = {}
+    for name, ref in list(want["grads_gen"].items()) + [("dis." + n, v) for n, v in want["grads_dis"].items()]:
+        if ref is None:
+            continue
+        t = d[name[4:]] if name.startswith("dis.") else g[name]
+        arr = t.cpu().numpy().reshape(ref.shape)
+        if _zero_grad_bias(name):
+            absolute[name] = float(np.abs(arr).max())
+        else:
+            report[name] = rel(arr, ref.numpy())
+    os.makedirs("gpurun_out", exist_ok=True)
+    tag = mode + ("_vs_tf32_oracle" if emulate else "_vs_fp64_oracle")
+    json.dump({"relative": {k: round(v, 6) for k, v in report.items()}, "absolute_zero_grad_biases": absolute},
+              open(f"gpurun_out/train_step_parity_{tag}.json", "w"), indent=1)
+    for k, v in report.items():
+        assert v <= (tol_loss if k.startswith("loss.") else (tol_y if k == "y_final_lin" else tol_grad)), (k, v)
+    for k, v in absolute.items():
+        assert v < 1e-3, (k, v)
+    # RMSprop moved every weight by at most lr / sqrt(0.1) (first step: ms = 0.1 g^2) in the direction of -g
+    for fvx, w0 in ((step.fv_gen, w_gen0), (step.fv_dis, w_dis0)):
+        delta = (fvx.flat_w - w0)
+        assert float(delta.abs().max()) <= 1e-4 / np.sqrt(0.1) * 1.01
+        gsel = fvx.flat_g.abs() > 1e-6
+        assert bool(((delta[gsel] * fvx.flat_g[gsel]) < 0).all())
+        want_delta = -1e-4 * fvx.flat_g / (torch.sqrt(0.1 * fvx.flat_g ** 2) + 1e-7)
+        assert rel(delta.cpu().numpy(), want_delta.cpu().numpy()) < 1e-3
+    # moving statistics of the three BatchNormalization layers of sunRadNet (one call) and of the discriminator (two calls)
+    for owner, src, calls in ((step._gen.sun, wg["sun"], [want["bn"]["sun"]]), (step._dis, wd, [want["bn"]["dis_real"], want["bn"]["dis_fake"]])):
+        for name in ("d2", "d3", "d4"):
+            mm, mv = src[name]["moving_mean"].astype(np.float64), src[name]["moving_variance"].astype(np.float64)
+            for call in calls:
+                mean, var, cnt = call[name]
+                mm, mv = M.bn_moving_update(mm, mv, mean.numpy(), var.numpy(), cnt)
+            layer = getattr(owner, name)
+            assert rel(layer.moving_mean.cpu().numpy(), mm) < 2e-2 and rel(layer.moving_variance.cpu().numpy(), mv) < 2e-2
+
+
+def test_train_step_full_batch_runs_and_descends(pkg):
+    """B = 32 (BASELINE configs[2]): two steps on the same batch; finite losses, every gradient finite, the generator loss goes down."""
+    B, H, W = 32, 32, 128
+    ldr, hdr_t, gt = _inputs(B, H, W, seed=11)
+    step = pkg.train.Step(batch_size=B, im_height=H, im_width=W)
+    ds = [T(hdr_t).cuda(), T(ldr).cuda()]
+    gtd = T(gt).cuda()
+    step.train_step(ds, gtd)
+    first = {k: float(v) for k, v in step.last_losses.items()}
+    assert all(np.isfinite(v) for v in first.values()), first
+    assert bool(torch.isfinite(step.fv_gen.flat_g).all()) and bool(torch.isfinite(step.fv_dis.flat_g).all())
+    for _ in range(3):
+        step.train_step(ds, gtd)
+    last = {k: float(v) for k, v in step.last_losses.items()}
+    assert all(np.isfinite(v) for v in last.values()), last
+    assert last["total"] < first["total"], (first, last)
+
+
+def test_plain_wiring_train_step(pkg):
+    """The as-committed wiring (plain ops.conv2d in the res-blocks and sunposeLayers, generator.py:13,17, sunpose_net.py:10,15) trains too."""
+    B, H, W = 2, 32, 128
+    ldr, hdr_t, gt = _inputs(B, H, W, seed=7)
+    step = pkg.train.Step(batch_size=B, im_height=H, im_width=W, distortion_aware=False, distortion_aware_sunpose=False)
+    step.train_step([T(hdr_t).cuda(), T(ldr).cuda()], T(gt).cuda())
+    vals = {k: float(v) for k, v in step.last_losses.items()}
+    assert all(np.isfinite(v) for v in vals.values()), vals
+    assert bool(torch.isfinite(step.fv_gen.flat_g).all()) and float(step.fv_gen.flat_g.abs().max()) > 0
+    # res-block 0 conv1 weight gradient vs a finite-difference free check: the plain trunk's first block against autograd of the oracle's
+    # plain conv on the saved activations
+    unit = step._gen.res.sequence[0]
+    xin, c1, a1, c2, s1, s2 = unit._saved
+    assert tuple(step.fv_gen.grad(unit.conv1, "w").shape) == (3, 3, 128, 128)
