@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native distortion-aware convolution path.
 
-Workload (config.workload, default `sun_train`): BASELINE.json configs[1], the sun pre-train step at batch 32, 32x128 =
-train_sun.sun_train_step (train_sun.py:220-264): sun-position network forward (distortion-aware wiring of sunpose_net.py:11,16) ->
-Grad-CAM x3 at the ground-truth class -> KLDivergence + DoG L1 -> backward through every layer -> (world > 1: gradient all-reduce,
-the 201 MB Dense part overlapped with the conv backward) -> Adam.  At N = 1 the same line carries `inference`: BASELINE configs[0],
-"generator inference, random-init weights, synthetic 32x128 LDR sky-dome panoramas, batch 32" = inference.generator_in_step
-(inference.py:81-112), which `--workload inference` also times on its own (with its own e2e / roofline keys).
-`--workload sky` times the sky branch alone (inference.py:84-86), `--workload trunk` the DA residual trunk alone,
-`--workload trunk_train` the data-parallel train step of the trunk.
+Workload (config.workload, default `train`): BASELINE.json configs[2], the full train step at batch 32, 32x128 = train._preprocessing
+(DoRF LDR synthesis, train.py:54-94) + train.train_step (train.py:382-415): generator (encoder, distortion-aware residual trunk, sky and
+sun decoders, sunRadNet), sun-position network with Grad-CAM, VGG16 perceptual / DoG / L1 / LSGAN / KL losses, both backward passes
+(generator + sun-position variables; discriminator variables with batch statistics), gradient all-reduce (world > 1) and two RMSprop
+updates.  At N = 1 the same line carries `inference` (BASELINE configs[0]: inference.generator_in_step, batch 32) and `modes`: the
+train step and the inference in BOTH arithmetic modes — `3xtf32` (split TF32 operands, fp32-class results: the mode that meets the
+1e-3 log-luminance tolerance against the fp32/fp64 oracle; the headline) and `tf32` (what TensorFlow itself computes on an Ampere-or-newer
+GPU; parity 3e-3 whole-path, 2e-5 per layer against the TF32-emulating oracle).
+
+Other workloads: `sun_train` (configs[1]: train_sun.sun_train_step), `inference`, `sky`, `trunk`, `trunk_train`, and `sweep`
+(configs[3]: distortion-aware conv layer sweep at 32x128 / 64x256 / 128x512, batch 64, forward + data gradient + weight gradient).
+configs[4] is `--workload train --height 64 --width 256 --batch 32` under torchrun on 8 GPUs (global batch 256).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, one process per GPU under torchrun)
-    python bench.py --impl reference [--steps K] [--warmup W]      reference arm: the oracle's CPU restatement of the
-                                                                   same path on the host cores (TensorFlow itself is
-                                                                   not installable here)
+    python bench.py --impl reference [--steps K] [--warmup W]      reference arm: the oracle's CPU restatement of the same step on
+                                                                   the host cores (TensorFlow is not installable here)
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -33,13 +36,21 @@ sys.path.insert(0, ROOT)
 
 N_BLOCKS, C, K_SIZE = 6, 128, 3
 UNIT = "panoramas/s"
-METRICS = {"trunk_train": "panoramas/sec (32x128, data-parallel train step of the DA residual trunk: fwd + L2 loss + bwd + 1 NCCL all-reduce + RMSprop)",
+METRICS = {"train": "panoramas/sec (32x128, full train step: train._preprocessing + train.train_step = generator + discriminator + VGG16 perceptual loss + DoRF, fwd + both bwd + RMSprop x2)",
+           "trunk_train": "panoramas/sec (32x128, data-parallel train step of the DA residual trunk: fwd + L2 loss + bwd + 1 NCCL all-reduce + RMSprop)",
            "sun_train": "panoramas/sec (32x128, sun-position network pre-train step: train_sun.sun_train_step, fwd + Grad-CAM + KL/DoG loss + bwd + Adam)",
            "inference": "panoramas/sec (32x128, generator inference: inference.generator_in_step, sky + sun branch)",
            "sky": "panoramas/sec (32x128, generator inference, sky branch: encode -> DA res-trunk -> sky_decode -> log-decompress)",
-           "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)"}
+           "trunk": "panoramas/sec (32x128, inference: DA residual trunk forward)",
+           "sweep": "distortion-aware conv layer sweep (fwd + dgrad + wgrad), TFLOP/s per layer"}
+DTYPE = {"tf32": "tf32", "3xtf32": "f32(3xtf32)"}
+VGG_LAYERS = (("conv1_1", 3, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("conv2_2", 128, 128), ("conv3_1", 128, 256),
+              ("conv3_2", 256, 256), ("conv3_3", 256, 256))
 
 
+# ------------------------------------------------------------------------------------------------------------------------------------
+# synthetic inputs and weights — numpy only, shared by both arms
+# ------------------------------------------------------------------------------------------------------------------------------------
 def make_weights(seed=0):
     """numpy-seeded weights with the reference's initialiser distributions (glorot_uniform, zero bias, gamma 1, beta 0)."""
     rng = np.random.default_rng(seed)
@@ -62,27 +73,6 @@ def make_input(batch, h, w, seed):
     return np.where(x > 0, x, 0.1 * x).astype(np.float32)
 
 
-def workload_name(batch, H, W, workload="sky"):
-    if workload == "sun_train":
-        return (f"sun_train_step (train_sun.py:220-264): LDR [{batch},{H},{W},3] -> sunpose_net (distortion-aware convs, 2 Dense {H * W}) -> "
-                f"Grad-CAM x3 at the ground-truth class -> KLDivergence + DoG L1 -> backward through every layer -> gradient all-reduce "
-                f"(world > 1) -> Adam; random-init weights, B={batch}/GPU")
-    if workload == "inference":
-        return (f"generator_inference (inference.py:81-112): LDR [{batch},{H},{W},3] -> encode + 6 DA resBlocks -> sky_decode; "
-                f"sunpose_net (DA convs, 2 Dense {H * W}) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun_decode -> alpha blend -> "
-                f"hdr_logDecompression; random-init weights, B={batch}/GPU")
-    if workload == "trunk_train":
-        return (f"res_trunk_train_step: 6 resBlocks with distortion-aware convs, forward + synthetic L2 objective + backward "
-                f"(IN/LeakyReLU bwd, DA dgrad/wgrad/dbias) + one all-reduce of the flat gradient buffer (7.1 MB) + fused Keras RMSprop, "
-                f"B={batch}/GPU on the {H // 4}x{W // 4}x{C} trunk map of {H}x{W} panoramas")
-    if workload == "trunk":
-        return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3, TF32) + 12 instance norms, "
-                f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
-    return (f"generator_sky_inference (inference.py:84-86): LDR [{batch},{H},{W},3] -> encode (7x7/32, 3x3s2/64, 3x3s2/128, IN, lrelu) "
-            f"-> 6 resBlocks with distortion-aware convs (generator.py:14,18) -> sky_decode (2 resize-deconv, 7x7/3, +LDR, relu) "
-            f"-> hdr_logDecompression; random-init weights, B={batch}/GPU")
-
-
 def make_generator_weights(seed=0):
     """Sky-branch weights with the reference's initialiser distributions (Keras glorot_uniform, zero bias, gamma 1, beta 0)."""
     rng = np.random.default_rng(seed)
@@ -100,6 +90,19 @@ def make_generator_weights(seed=0):
     return w
 
 
+def _down_weights(rng, with_out=False):
+    d4, cin = {}, 6
+    for name, f, norm in (("d1", 64, False), ("d2", 128, True), ("d3", 256, True), ("d4", 512, True)):
+        d = {"kernel": (0.02 * rng.standard_normal((4, 4, cin, f))).astype(np.float32)}
+        if norm:
+            d.update(gamma=np.ones(f, np.float32), beta=np.zeros(f, np.float32), moving_mean=np.zeros(f, np.float32),
+                     moving_variance=np.ones(f, np.float32))
+        d4[name], cin = d, f
+    if with_out:
+        d4["out"] = ((0.02 * rng.standard_normal((4, 4, 512, 1))).astype(np.float32), np.zeros(1, np.float32))
+    return d4
+
+
 def make_inference_weights(H, W, seed=0):
     """Full generator (sky + sun decoder + sunRadNet) and sun-position weights with the reference's initialiser distributions:
     glorot_uniform kernels and zero biases, gamma 1 / beta 0 norms, N(0, 0.02) sunRadNet convs with fresh BatchNormalization."""
@@ -112,13 +115,7 @@ def make_inference_weights(H, W, seed=0):
 
     wg["conv3_u"], wg["conv2_u"], wg["conv1_u"] = conv(3, 128, 64), conv(3, 64, 32), conv(7, 32, 3)
     wg["norm3_u"], wg["norm2_u"] = (np.ones(64, np.float32), np.zeros(64, np.float32)), (np.ones(32, np.float32), np.zeros(32, np.float32))
-    sun, cin = {}, 6
-    for name, f, norm in (("d1", 64, False), ("d2", 128, True), ("d3", 256, True), ("d4", 512, True)):
-        d = {"kernel": (0.02 * rng.standard_normal((4, 4, cin, f))).astype(np.float32)}
-        if norm:
-            d.update(gamma=np.ones(f, np.float32), beta=np.zeros(f, np.float32), moving_mean=np.zeros(f, np.float32),
-                     moving_variance=np.ones(f, np.float32))
-        sun[name], cin = d, f
+    sun = _down_weights(rng)
     flat = (H // 8) * (W // 8) * 512
     lim = (6.0 / (flat + 1)) ** 0.5
     for head in ("gamma", "beta"):
@@ -141,14 +138,36 @@ def make_inference_weights(H, W, seed=0):
     return wg, ws
 
 
+def make_train_weights(H, W, seed=0):
+    """(generator, sun-position, discriminator, VGG16) weights for the full train step; vgg16.npy is not part of the repository, so the
+    frozen VGG16 gets He-normal kernels."""
+    wg, ws = make_inference_weights(H, W, seed)
+    wd = _down_weights(np.random.default_rng(seed + 70), with_out=True)
+    rng = np.random.default_rng(seed + 90)
+    vgg = {n: ((rng.standard_normal((3, 3, c, f)) * np.sqrt(2.0 / (9 * c))).astype(np.float32), np.zeros(f, np.float32)) for n, c, f in VGG_LAYERS}
+    return wg, ws, wd, vgg
+
+
 def make_sunpose_gt(batch, H, W, seed):
-    """sunpose_gt = von Mises-Fisher bump (kappa = 80) over the H*W sky bins (train.py:42-52) at azimuth W/2 - 1
-    (train.py:32) and a random elevation row in [H/8, H/2] — computed by the package's own mirror of train.vMF (dataset.py)."""
-    from __graft_entry__ import load_package
-    D = load_package().dataset
+    """sunpose_gt = von Mises-Fisher bump (kappa = 80) over the H*W sky bins (train.py:42-52, tf_utils.py:95-129) at azimuth
+    W/2 - 1 (train.py:32) and a random elevation row in [H/8, H/2].  Pure numpy: synthetic-input generation, shared by both arms."""
     rng = np.random.default_rng(seed)
-    bins = D.sunpose_bins(H, W)
-    return np.stack([D.vMF(W * 0.5 - 1, rng.uniform(H / 8, H / 2), H, W, bins=bins) for _ in range(batch)]).astype(np.float32)
+    f32, pi = np.float32, np.float32(np.pi)
+    i = np.arange(H * W, dtype=np.float32)
+    row = np.floor(i / f32(W))
+    xdeg = ((i + f32(1)) - row * f32(W) - f32(1)) * f32(360.0 / W) + f32(360.0 / (W * 2.0))
+    ydeg = row * f32(90.0 / H) + f32(90.0 / (2.0 * H))
+    phi, theta = ydeg * (pi / f32(180)), (xdeg - f32(180)) * (pi / f32(180))
+    bins = np.stack([np.cos(phi) * np.cos(theta), np.sin(phi), np.cos(phi) * np.sin(theta)], 1).astype(np.float32)
+    out = []
+    for _ in range(batch):
+        x, y = f32(W * 0.5 - 1), f32(rng.uniform(H / 8, H / 2))
+        unit_w, unit_h = f32(2) * pi / f32(W), pi / f32(2 * H)                         # tf_utils.sphere2world, skydome
+        th, ph = x * unit_w - pi, pi / f32(2) - y * unit_h
+        v = np.array([np.cos(ph) * np.cos(th), np.sin(ph), np.cos(ph) * np.sin(th)], np.float32)
+        pdf = np.exp(f32(80.0) * (bins @ v)).astype(np.float32)
+        out.append(pdf / pdf.sum(dtype=np.float32))
+    return np.stack(out).astype(np.float32)
 
 
 def make_ldr(batch, H, W, seed):
@@ -156,14 +175,93 @@ def make_ldr(batch, H, W, seed):
     return (np.round(255 * np.random.default_rng(seed).uniform(0, 1, (batch, H, W, 3))) / 255).astype(np.float32)
 
 
+def make_hdr_batch(batch, H, W, seed):
+    """SURVEY 8d inputs of train._preprocessing: HDR = sky-like image with a 3x3 sun blob of radiance U(1e2, 3e4) in rows H/8..H/2,
+    normalised 0.5 x / mean (train.py:109-110); exposure t = 2^U(-3,3) (utils.get_T); CRF LUT [B,1024] = linspace^(1/gamma), gamma ~
+    U(1.5, 3) (the DoRF file is not in the repository); shot / read noise levels of train.py:67-75."""
+    rng = np.random.default_rng(seed)
+    hdr = rng.uniform(0, 1, (batch, H, W, 3)).astype(np.float32) ** 2
+    for b in range(batch):
+        r, c = int(rng.integers(H // 8, H // 2)), int(rng.integers(1, W - 2))
+        hdr[b, r - 1:r + 2, c - 1:c + 2, :] = rng.uniform(1e2, 3e4)
+        hdr[b] *= 0.5 / (hdr[b].mean() + 1e-6)
+    t = (2.0 ** rng.uniform(-3, 3, batch)).astype(np.float32)
+    crf = (np.linspace(0, 1, 1024)[None, :] ** (1.0 / rng.uniform(1.5, 3.0, (batch, 1)))).astype(np.float32)
+    sigma_s = (0.08 / 6 * rng.uniform(0, 1, (batch, 3))).astype(np.float32)
+    sigma_c = (0.005 * rng.uniform(0, 1, (batch, 3))).astype(np.float32)
+    noise_s, noise_c = (rng.standard_normal((batch, H, W, 3)).astype(np.float32) for _ in range(2))
+    return dict(hdr=hdr, t=t, crf=crf, sigma_s=sigma_s, sigma_c=sigma_c, noise_s=noise_s, noise_c=noise_c)
+
+
+def workload_name(batch, H, W, workload="train"):
+    if workload == "train":
+        return (f"train._preprocessing + train.train_step (train.py:54-94, 382-415): HDR [{batch},{H},{W},3] -> LDR synthesis (exposure, noise, DoRF "
+                f"CRF, quantise) -> generator (encoder, 6 DA resBlocks, sky + sun decoders, sunRadNet) + sunpose_net (DA convs, 2 Dense {H * W}) + "
+                f"Grad-CAM x3 -> KL + VGG16 perceptual + DoG + L1 + LSGAN -> both backward passes (discriminator with batch statistics) -> "
+                f"gradient all-reduce (world > 1) -> RMSprop x2; random-init weights, B={batch}/GPU")
+    if workload == "sun_train":
+        return (f"sun_train_step (train_sun.py:220-264): LDR [{batch},{H},{W},3] -> sunpose_net (distortion-aware convs, 2 Dense {H * W}) -> "
+                f"Grad-CAM x3 at the ground-truth class -> KLDivergence + DoG L1 -> backward through every layer -> gradient all-reduce "
+                f"(world > 1) -> Adam; random-init weights, B={batch}/GPU")
+    if workload == "inference":
+        return (f"generator_inference (inference.py:81-112): LDR [{batch},{H},{W},3] -> encode + 6 DA resBlocks -> sky_decode; "
+                f"sunpose_net (DA convs, 2 Dense {H * W}) -> Grad-CAM x3 (backward sweep) -> sunRadNet -> sun_decode -> alpha blend -> "
+                f"hdr_logDecompression; random-init weights, B={batch}/GPU")
+    if workload == "trunk_train":
+        return (f"res_trunk_train_step: 6 resBlocks with distortion-aware convs, forward + synthetic L2 objective + backward "
+                f"(IN/LeakyReLU bwd, DA dgrad/wgrad/dbias) + one all-reduce of the flat gradient buffer (7.1 MB) + fused Keras RMSprop, "
+                f"B={batch}/GPU on the {H // 4}x{W // 4}x{C} trunk map of {H}x{W} panoramas")
+    if workload == "trunk":
+        return (f"res_trunk_fwd: 6 resBlocks = 12 distortion-aware conv2d (128->128, k=3) + 12 instance norms, "
+                f"B={batch}/GPU, {H}x{W} panoramas -> trunk map {H // 4}x{W // 4}x{C}")
+    if workload == "sweep":
+        return "distortion-aware conv layer sweep, batch 64, 32x128 / 64x256 / 128x512, fwd + dgrad + wgrad (BASELINE configs[3])"
+    return (f"generator_sky_inference (inference.py:84-86): LDR [{batch},{H},{W},3] -> encode (7x7/32, 3x3s2/64, 3x3s2/128, IN, lrelu) "
+            f"-> 6 resBlocks with distortion-aware convs (generator.py:14,18) -> sky_decode (2 resize-deconv, 7x7/3, +LDR, relu) "
+            f"-> hdr_logDecompression; random-init weights, B={batch}/GPU")
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------------------------------------------
 def oracle_step_fn(args, sample):
     """CPU restatement of the selected workload on `sample` panoramas (returns a zero-argument callable)."""
     import torch
     from oracle import model_oracle as M
+    H, W = args.height, args.width
+    if args.workload == "train":
+        wg, ws, wd, vgg = make_train_weights(H, W)
+        d = make_hdr_batch(sample, H, W, seed=1)
+        gt = make_sunpose_gt(sample, H, W, seed=2)
+        T = torch.from_numpy
+        state = {}
+
+        def walk(w, g, path=""):
+            if isinstance(w, dict):
+                for k in w:
+                    walk(w[k], g, f"{path}{k}.")
+            elif isinstance(w, (list, tuple)):
+                for i, v in enumerate(w):
+                    walk(v, g, f"{path}{i}.")
+            else:
+                gr = g.get(path[:-1])
+                if gr is not None:
+                    ms = state.setdefault(path, np.zeros_like(w))
+                    w_new, ms_new = M.rmsprop_step(w, ms, gr.numpy().reshape(w.shape).astype(np.float32))
+                    w[...] = w_new.astype(np.float32)
+                    ms[...] = ms_new
+
+        def step():
+            hdr_t, ldr = M.ldr_synth(T(d["hdr"]), T(d["t"]), T(d["crf"]), T(d["sigma_s"]), T(d["sigma_c"]), T(d["noise_s"]), T(d["noise_c"]))
+            r = M.train_step(ldr.numpy(), hdr_t.numpy(), gt, wg, ws, wd, vgg, acc_dtype=torch.float32)
+            walk(wg, r["grads_gen"])
+            walk(ws, {k[4:]: v for k, v in r["grads_gen"].items() if k.startswith("sun.sunlayer") or k.startswith("sun.fc")})
+            walk(wd, r["grads_dis"])
+        return step
     if args.workload == "trunk_train":
         blocks = [{k: torch.from_numpy(v).requires_grad_(True) for k, v in b.items()} for b in make_weights()]
-        x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
-        tgt = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=2))
+        x = torch.from_numpy(make_input(sample, H // 4, W // 4, seed=1))
+        tgt = torch.from_numpy(make_input(sample, H // 4, W // 4, seed=2))
         params = [v for blk in blocks for v in blk.values()]
         ms = [torch.zeros_like(v) for v in params]
 
@@ -177,12 +275,12 @@ def oracle_step_fn(args, sample):
         return step
     if args.workload == "trunk":
         blocks = [{k: torch.from_numpy(v) for k, v in b.items()} for b in make_weights()]
-        x = torch.from_numpy(make_input(sample, args.height // 4, args.width // 4, seed=1))
+        x = torch.from_numpy(make_input(sample, H // 4, W // 4, seed=1))
         return lambda: M.res_layer(x, blocks, K_SIZE)
-    ldr = make_ldr(sample, args.height, args.width, seed=1)
+    ldr = make_ldr(sample, H, W, seed=1)
     if args.workload == "sun_train":
-        _, ws = make_inference_weights(args.height, args.width)
-        gt = make_sunpose_gt(sample, args.height, args.width, seed=2)
+        _, ws = make_inference_weights(H, W)
+        gt = make_sunpose_gt(sample, H, W, seed=2)
         state = {}
 
         def step():
@@ -200,7 +298,7 @@ def oracle_step_fn(args, sample):
                     val -= (lr_t * m / (np.sqrt(v) + 1e-7)).astype(np.float32)
         return step
     if args.workload == "inference":
-        wg, ws = make_inference_weights(args.height, args.width)
+        wg, ws = make_inference_weights(H, W)
         return lambda: M.generator_inference(ldr, wg, ws, K_SIZE)
     w = make_generator_weights()
     return lambda: M.sky_branch(ldr, w, K_SIZE)
@@ -237,42 +335,162 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def time_oracle(args, budget_s):
+    """Times the oracle step on the full batch (the same config as our arm); the number of timed steps is bounded by a wall-clock
+    budget so the run ends within minutes.  Returns (panoramas/s, seconds per step, steps timed)."""
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    step = oracle_step_fn(args, args.batch)
+    step()                                              # one untimed step (allocator, thread pool)
+    reps, t0 = 0, time.perf_counter()
+    while reps < args.steps and (reps < 2 or time.perf_counter() - t0 < budget_s):
+        step()
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return args.batch / dt, dt, reps
+
+
 def run_reference(args):
-    """Reference arm: the path's CPU restatement (oracle port; TF cannot be installed) on all host cores."""
+    """Reference arm: the path's CPU restatement (oracle port; TensorFlow cannot be installed) on all host cores, full batch per step.
+    Imports numpy, torch and oracle/ only — never the product package or its CUDA library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle import model_oracle as M
-    torch.set_num_threads(os.cpu_count())
-    sample = min(args.batch, 8)                     # bounded sample of the B=32 batch per step
-    step = oracle_step_fn(args, sample)
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = sample / dt
+    value, dt, reps = time_oracle(args, budget_s=150.0)
     METRIC = METRICS[args.workload].replace("32x128", f"{args.height}x{args.width}")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.batch, args.height, args.width, args.workload),
-                       "note": "reference dataflow (materialised pad/gather/blend/matmul) restated on torch-CPU; not TensorFlow"},
+                       "note": "reference dataflow (materialised pad/gather/blend/matmul, autograd backward) restated on torch-CPU; not TensorFlow",
+                       "steps_timed": reps, "warmup_done": 1},
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{sample} of {args.batch} panoramas per step, {args.steps} steps"},
+                             "sample": f"{args.batch} of {args.batch} panoramas per step (full batch), {reps} timed steps within a 150 s budget"},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def measure_inference(pkg, args, rank, flush):
-    """Device-resident throughput of full generator inference (BASELINE configs[0]) measured in the same process: CUDA-graph replay,
-    L2 flushed between steps, CUDA events.  Reported next to the train-step line so one run carries both halves of the metric."""
+def cpu_baseline(args):
+    """The oracle (a port of the reference dataflow) timed on the host cores on the full batch, bounded to ~20 s of wall clock."""
+    value, dt, reps = time_oracle(args, budget_s=20.0)
+    return {"value": round(value, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{args.batch} of {args.batch} panoramas per step (full batch), {reps} steps, torch-CPU fp32 restatement of the reference dataflow"}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------------------------
+def conv_work(name, a):
+    """(label, FLOPs, algorithmic bytes) of one traced C-ABI conv call from its integer arguments (include/skydome_b200.h)."""
+    def out(n, s):
+        return -(-n // s)
+    if name == "sky_da_conv2d_fwd":
+        B, h, w, Ci, F, k = a[8:14]; s = 1; kind = "da fwd"
+    elif name == "sky_conv2d_fwd":
+        B, h, w, Ci, F, k, s = a[6:13]; kind = "conv fwd"
+    elif name == "sky_conv2d_fwd_blend":
+        B, h, w, Ci, k = a[7:12]; F, s, kind = 3, 1, "conv fwd + tail"
+    elif name in ("sky_conv2d_smallc_fwd",):
+        B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "small-C conv fwd"
+    elif name == "sky_da_conv2d_smallc_fwd":
+        B, h, w, Ci, F, k = a[7:13]; s = 1; kind = "small-C da fwd"
+    elif name == "sky_da_conv2d_bwd_data":
+        B, h, w, Ci, F, k = a[4:10]; s = 1; kind = "da dgrad"
+    elif name == "sky_da_conv2d_bwd_filter":
+        B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "da wgrad"
+    elif name == "sky_da_conv2d_smallc_bwd_filter":
+        B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "small-C da wgrad"
+    elif name == "sky_conv2d_bwd_data":
+        B, h, w, Ci, F, k, s = a[4:11]; kind = "conv dgrad"
+    elif name == "sky_conv2d_bwd_filter":
+        B, h, w, Ci, _, F, k, s = a[5:13]; kind = ("da wgrad" if a[2] else "conv wgrad")
+    else:
+        return None
+    M = B * out(h, s) * out(w, s)
+    flops = 2.0 * M * k * k * Ci * F
+    nbytes = 4.0 * (B * h * w * Ci + M * F + k * k * Ci * F)
+    return f"{kind} {Ci}->{F} k{k}" + (f" s{s}" if s != 1 else "") + f" M={M}", flops, nbytes
+
+
+def trace_step(pkg, run_eager, reps=3):
+    """Device time of every C-ABI call of one step, from CUDA events around each call on its own stream (`_lib.LIB.trace`), averaged over
+    `reps` eager steps.  Returns (rows sorted by total time, total traced ms): row = dict(label, calls, ms_total, ms_per_call, flops, bytes)."""
+    import torch
+    lib = pkg._lib.LIB
+    acc = {}
+    for _ in range(reps):
+        lib.trace = []
+        run_eager()
+        torch.cuda.synchronize()
+        tr, lib.trace = lib.trace, None
+        for name, a, s, e in tr:
+            ints = [v for v in a]
+            cw = conv_work(name, ints)
+            label = cw[0] if cw else name
+            r = acc.setdefault(label, dict(label=label, entry=name, calls=0, ms_total=0.0, flops=cw[1] if cw else None, bytes=cw[2] if cw else None))
+            r["calls"] += 1
+            r["ms_total"] += s.elapsed_time(e)
+    rows = sorted(acc.values(), key=lambda r: -r["ms_total"])
+    for r in rows:
+        r["calls"] = r["calls"] / reps
+        r["ms_total"] = r["ms_total"] / reps
+        r["ms_per_call"] = r["ms_total"] / r["calls"]
+    return rows, sum(r["ms_total"] for r in rows)
+
+
+def roofline_of(rows, total_ms, peaks):
+    """The roofline object of the largest-share kernel group of the step."""
+    hbm = peaks["hbm_gbs"] if peaks else 6500.0
+    bf16 = peaks["bf16_tflops"] if peaks else 1590.0
+    top = next((r for r in rows if r["flops"]), None)
+    if top is None:
+        return None
+    ai = top["flops"] / top["bytes"]
+    ridge = (bf16 / 2) * 1e12 / (hbm * 1e9)
+    t = top["ms_per_call"] * 1e-3
+    if ai >= ridge:
+        ach, peak, unit, bound = top["flops"] / t / 1e12, bf16 / 2, "TFLOP/s", "tensor"
+        note = "TF32 operands: peak = 1/2 x measured bf16 burst (%s); algorithmic FLOPs 2*M*K*N" % ("MEASURED_PEAKS.json" if peaks else "fallback")
+    else:
+        ach, peak, unit, bound = top["bytes"] / t / 1e9, hbm, "GB/s", "hbm"
+        note = "algorithmic bytes 4*(in + out + kernel); measured HBM copy bandwidth (%s)" % ("MEASURED_PEAKS.json" if peaks else "fallback")
+    return {"kernel": top["label"], "entry_point": top["entry"], "bound": bound, "achieved": round(ach, 2), "peak": round(peak, 1), "unit": unit,
+            "frac": round(ach / peak, 4), "traffic": None, "share_of_step": round(top["ms_total"] / total_ms, 4),
+            "ms_per_launch": round(top["ms_per_call"], 5), "launches_per_step": top["calls"], "flops_per_launch": top["flops"],
+            "bytes_per_launch": top["bytes"], "peak_note": note,
+            "how": "CUDA events around every C-ABI call on its launching stream over 3 eager steps of this run (L2 warm, like inside the step)"}
+
+
+def build_train(pkg, args, rank, mode):
+    """The full train step of one arithmetic mode: returns (step object, run(hdr_dev, gt_dev) -> loss tensor, host inputs, device inputs)."""
     import torch
     B, H, W = args.batch, args.height, args.width
-    gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=args.math)
+    wg, ws, wd, vgg = make_train_weights(H, W)
+    step = pkg.train.Step(batch_size=B, im_height=H, im_width=W, vgg_data_dict=vgg, math_mode=mode)
+    step.init_training(B)
+    step._gen.set_weights(wg)
+    step._sun.set_weights(ws)
+    step._dis.set_weights(wd)
+    d = make_hdr_batch(B, H, W, seed=1 + rank)
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+    host["gt"] = torch.from_numpy(make_sunpose_gt(B, H, W, seed=200 + rank)).pin_memory()
+    dev = {k: v.cuda() for k, v in host.items()}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    def run():
+        hdr_t, ldr = step._preprocessing(dev["hdr"], dev["crf"], dev["t"], dev["sigma_s"], dev["sigma_c"], dev["noise_s"], dev["noise_c"])   # train.py:475
+        step.train_step([hdr_t, ldr], dev["gt"], global_batch=B * world)                                                                       # :476
+        return step.last_losses["total"]
+    return step, run, host, dev
+
+
+def measure_inference(pkg, args, rank, flush, mode):
+    """Device-resident throughput of full generator inference (BASELINE configs[0]) measured in the same process: CUDA-graph replay,
+    L2 flushed between steps, CUDA events."""
+    import torch
+    B, H, W = args.batch, args.height, args.width
+    gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=mode)
     x = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).cuda()
     sun.sunposeEstimation(x)
     wg, ws = make_inference_weights(H, W)
@@ -299,8 +517,91 @@ def measure_inference(pkg, args, rank, flush):
         evs.append((s, e))
     torch.cuda.synchronize()
     t = sum(s.elapsed_time(e) for s, e in evs) / args.steps
-    return {"workload": workload_name(B, H, W, "inference"), "value": round(B / (t * 1e-3), 1), "unit": UNIT, "ms_per_step": round(t, 4),
-            "steps": args.steps, "cuda_graph": True}
+    return {"value": round(B / (t * 1e-3), 1), "unit": UNIT, "ms_per_step": round(t, 4), "dtype": DTYPE[mode], "cuda_graph": True}
+
+
+def graph_or_eager(fn, world, allow_graph=True):
+    """Captures `fn` (already warmed up) into a CUDA graph on a side stream; falls back to eager launches if capture is refused."""
+    import torch
+    if not allow_graph:
+        return None
+    try:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                fn()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        return graph
+    except Exception as exc:      # noqa: BLE001
+        print(f"[bench] CUDA-graph capture refused ({type(exc).__name__}: {str(exc)[:200]}); launching eagerly", file=sys.stderr)
+        torch.cuda.synchronize()
+        return None
+
+
+def timed(fn, steps, flush):
+    import torch
+    evs = []
+    for _ in range(steps):
+        flush.zero_()                        # L2 flush between iterations, outside the timed events
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in evs]
+
+
+def run_sweep(pkg, args):
+    """BASELINE configs[3]: distortion-aware conv layer sweep, batch 64, fwd + dgrad + wgrad, CUDA events, L2 flushed between reps."""
+    import torch
+    lib, check = pkg._lib.LIB, pkg._lib.check
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else None
+    tf32_peak, hbm = (peaks["bf16_tflops"] if peaks else 1590.0) / 2, (peaks["hbm_gbs"] if peaks else 6500.0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    B = args.batch if args.batch != 32 else 64
+    rows = []
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    for (H, W) in ((32, 128), (64, 256), (128, 512)):
+        for (Ci, F, k) in ((128, 128, 3), (64, 64, 3), (32, 32, 7), (3, 32, 7), (32, 3, 7)):
+            M = B * H * W
+            if M * max(Ci, F) >= 2 ** 31:
+                continue
+            x = torch.randn(B, H, W, Ci, device="cuda")
+            dy = torch.randn(B, H, W, F, device="cuda")
+            layer = pkg.conv2d(F, kernel_size=k, math_mode=args.math)
+            layer.build((B, H, W, Ci))
+            fns = {"fwd": lambda: layer(x)}
+            if Ci % 32 == 0 and F % 32 == 0:
+                dx, dk, db = torch.empty_like(x), torch.empty_like(layer.kernel), torch.empty_like(layer.bias)
+                fns["dgrad"] = lambda: check(lib.sky_da_conv2d_bwd_data(dy.data_ptr(), layer.offset_table.data_ptr(), layer.kernel.data_ptr(), dx.data_ptr(),
+                                                                        B, H, W, Ci, F, k, 0, st()))
+                fns["wgrad"] = lambda: check(lib.sky_conv2d_bwd_filter(x.data_ptr(), dy.data_ptr(), layer.offset_table.data_ptr(), dk.data_ptr(), db.data_ptr(),
+                                                                       B, H, W, Ci, Ci, F, k, 1, 0, st()))
+            flops, nbytes = 2.0 * M * k * k * Ci * F, 4.0 * M * (Ci + F)
+            tensor_bound = flops / nbytes >= tf32_peak * 1e12 / (hbm * 1e9)
+            for name, fn in fns.items():
+                fn()
+                ms = timed(fn, 6, flush)[1:]
+                t = float(np.mean(ms)) * 1e-3
+                rows.append({"hw": f"{H}x{W}", "layer": f"{Ci}->{F} k{k}", "pass": name, "ms": round(t * 1e3, 4), "tflops": round(flops / t / 1e12, 2),
+                             "gbs": round(nbytes / t / 1e9, 1), "bound": "tensor" if tensor_bound else "hbm",
+                             "frac": round((flops / t / 1e12 / tf32_peak) if tensor_bound else (nbytes / t / 1e9 / hbm), 4)})
+            del x, dy, layer
+            torch.cuda.empty_cache()
+    best = max((r for r in rows if r["bound"] == "tensor"), key=lambda r: r["frac"])
+    line = {"metric": METRICS["sweep"], "value": best["tflops"], "unit": "TFLOP/s", "n_gpus": 1, "steps": 5, "warmup": 1, "ms_per_step": best["ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.math], "data": "synthetic",
+            "config": {"workload": workload_name(B, 0, 0, "sweep"), "batch": B, "l2": "256 MB buffer written between timed iterations"},
+            "roofline": {"kernel": f"{best['layer']} {best['pass']} at {best['hw']}", "bound": "tensor", "achieved": best["tflops"], "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": best["frac"], "traffic": None},
+            "sweep": rows, "gpu_launches": len(rows) * 6}
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args):
@@ -315,17 +616,33 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = load_package()
+    if args.workload == "sweep":
+        if rank == 0:
+            run_sweep(pkg, args)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     B, H, W = args.batch, args.height, args.width
     h, w = H // 4, W // 4
     METRIC = METRICS[args.workload].replace("32x128", f"{args.height}x{args.width}")
-    trainer = None
-    extra_inputs = []
-    if args.workload == "trunk_train":
+    trainer = None          # object holding flat_w (replica sync check)
+    flat_w = None
+    h2d_pairs = []          # (device tensor, pinned host tensor) copied every e2e step
+    allow_graph = True
+    if args.workload == "train":
+        step_obj, forward0, host, dev = build_train(pkg, args, rank, args.math)
+        forward = lambda inp: forward0()
+        h2d_pairs = [(dev[k], host[k]) for k in ("hdr", "t", "crf", "sigma_s", "sigma_c", "gt")]     # the noise draws stay on the device (RNG state, not data)
+        x_host, x = host["hdr"], dev["hdr"]
+        flat_w = step_obj.fv_gen.flat_w
+        allow_graph = world == 1
+    elif args.workload == "trunk_train":
         trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
         trunk.build((B, h, w, C))
         trunk.set_weights(make_weights())
         trainer = pkg.trunk_train.TrunkTrainer(trunk, (B, h, w, C), lr=1e-4)
+        flat_w = trainer.flat_w
         target = torch.from_numpy(make_input(B, h, w, seed=100 + rank)).cuda()
         loss_buf = trainer._loss
 
@@ -333,30 +650,27 @@ def run_ours(args):
             trainer.train_step(inp, target)
             return loss_buf
         x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()
-        # per res-block: fwd 2 conv + 2 IN; bwd 2 x (IN reduce + IN apply) + 2 dgrad + 2 wgrad + 2 dbias + 2 pack (re-pack after the
-        # update); + loss + rmsprop
-        launches_per_step = None
+        allow_graph = False
     elif args.workload == "trunk":
         trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
         trunk.build((B, h, w, C))
         trunk.set_weights(make_weights())
         forward = trunk
         x_host = torch.from_numpy(make_input(B, h, w, seed=1 + rank)).pin_memory()   # each rank: its own shard of the batch
-        launches_per_step = None
     elif args.workload == "sun_train":
         sun = pkg.sunpose_net.model(im_height=H, im_width=W, math_mode=args.math)
         trainer = pkg.train_sun.SunTrainer(sun, B, H, W, lr=1e-4)
+        flat_w = trainer.flat_w
         sun.set_weights(make_inference_weights(H, W)[1])
         gt_host = torch.from_numpy(make_sunpose_gt(B, H, W, seed=200 + rank)).pin_memory()
         gt_dev = gt_host.cuda()
-        extra_inputs.append((gt_dev, gt_host))        # the step's second input: copied host -> device every e2e step
         x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
-        trunk = None
+        h2d_pairs = [(gt_dev, gt_host)]
 
         def forward(inp):
-            trainer.sun_train_step([None, inp], gt_dev)
+            trainer.sun_train_step([None, inp], gt_dev, global_batch=B * world)
             return trainer.loss
-        launches_per_step = None
+        allow_graph = False          # Adam's step count is a host scalar
     elif args.workload == "inference":
         gen, sun = pkg.inference.build_models(batch_size=B, im_height=H, im_width=W, math_mode=args.math)
         x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
@@ -364,67 +678,46 @@ def run_ours(args):
         wg, ws = make_inference_weights(H, W)
         gen.set_weights(wg)
         sun.set_weights(ws)
-        trunk = gen.res
         forward = lambda inp: pkg.inference.generator_in_step(gen, sun, inp)
-        launches_per_step = None                      # counted from the entry points one step calls (see below)
     else:
         gen = pkg.model(batch_size=B, im_height=H, im_width=W, da_kernel_size=K_SIZE, math_mode=args.math)
         gen.build(B)
         gen.set_weights(make_generator_weights())
-        trunk = gen.res
         forward = gen.sky_inference
         x_host = torch.from_numpy(make_ldr(B, H, W, seed=1 + rank)).pin_memory()
-        # encoder 3 conv + 3 IN; trunk 12 conv + 12 IN; decoder 2 resize + 3 conv + 2 IN
-        launches_per_step = None
-    x = x_host.cuda()
-    y_host = torch.empty_like(forward(x).cpu()).pin_memory()
-    h2d_bytes = x_host.numel() * x_host.element_size() + sum(h.numel() * h.element_size() for _, h in extra_inputs)
-    # kernel launches of one step, from the C-ABI entry points it calls (weights are packed / transposed by now)
+    if args.workload != "train":
+        x = x_host.cuda()
+        h2d_pairs = [(x, x_host)] + h2d_pairs
+    for _ in range(2):
+        y = forward(x)                               # eager warm-up (packs weights, sizes scratch)
+    torch.cuda.synchronize()
+    y_host = torch.empty_like(y.cpu()).pin_memory()
+    h2d_bytes = sum(hh.numel() * hh.element_size() for _, hh in h2d_pairs)
+    # kernel launches of one step: the library counts every kernel it launches
     pkg._lib.LIB.counts = {}
     n0 = pkg._lib.LIB.sky_launch_count()
     forward(x)
-    counted = pkg._lib.LIB.sky_launch_count() - n0          # exact: the library counts every kernel it launches
+    launches_per_step = pkg._lib.LIB.sky_launch_count() - n0
     abi_calls = {k: v for k, v in pkg._lib.LIB.counts.items() if k != "sky_launch_count"}
     pkg._lib.LIB.counts = None
-    if launches_per_step is None:
-        launches_per_step = counted
-    if world > 1 and trainer is not None:
-        trainer.flat_w.copy_(trainer.flat_w)     # replicas start from identical weights (same numpy seed on every rank)
+    torch.cuda.synchronize()
+    # kernel shares of the step and the roofline of its largest kernel, from a device timeline of eager steps
+    rows, traced_ms = trace_step(pkg, lambda: forward(x))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
 
-    # ---- the step: captured once into a CUDA graph (24 kernel launches + 12 memsets) ----
-    use_graph = trainer is None                  # the train step (NCCL all-reduce inside) is launched eagerly
-    side = torch.cuda.Stream()
-    graph = None
-    if use_graph:
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                y = forward(x)                   # eager warm-up (packs weights, sizes scratch)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                y = forward(x)
-    else:
-        for _ in range(2):
-            y = forward(x)
-    torch.cuda.synchronize()
+    # ---- the step: captured once into a CUDA graph where it holds no collective and no host-side scalar state ----
+    holder = {}
+
+    def capture_target():
+        holder["y"] = forward(x)
+    graph = graph_or_eager(capture_target, world, allow_graph)
+    if graph is not None:
+        y = holder["y"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        evs = []
-        for _ in range(steps):
-            flush.zero_()                        # L2 flush between iterations, outside the timed events
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn()
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize()
-        return [s.elapsed_time(e) for s, e in evs]
 
     def run_step():
         if graph is not None:
@@ -432,23 +725,19 @@ def run_ours(args):
         else:
             forward(x)
 
-    def step_device():
-        run_step()
-
     def step_e2e():
-        x.copy_(x_host, non_blocking=True)       # H2D of the step's input(s) from pinned memory
-        for dev_t, host_t in extra_inputs:
-            dev_t.copy_(host_t, non_blocking=True)
+        for dev_t, host_t in h2d_pairs:
+            dev_t.copy_(host_t, non_blocking=True)       # H2D of the step's inputs from pinned memory
         run_step()
-        y_host.copy_(y, non_blocking=True)       # D2H of the step's result (inference: HDR map; training: the loss)
+        y_host.copy_(holder.get("y", y) if graph is not None else y, non_blocking=True)       # D2H of the step's result (train: the loss)
 
     for _ in range(max(args.warmup, 3)):
-        step_device()
-    # keep warming for at least 0.4 s of wall time: clocks, the caching allocator's per-stream pools (the step uses side streams)
-    # and NCCL's channels reach their steady state only after a few dozen steps; untimed, the same count on every rank
+        run_step()
+    # keep warming for at least 0.4 s of wall time: clocks, the caching allocator's per-stream pools and NCCL's channels reach their
+    # steady state only after a few dozen steps; untimed, the same count on every rank
     torch.cuda.synchronize()
     t_w = time.perf_counter()
-    step_device()
+    run_step()
     torch.cuda.synchronize()
     extra = int(min(200, max(0, 0.4 / max(time.perf_counter() - t_w, 1e-4))))
     if world > 1:                                   # the train step contains a collective: every rank must run the same number of steps
@@ -456,52 +745,28 @@ def run_ours(args):
         dist.all_reduce(ex, op=dist.ReduceOp.MAX)
         extra = int(ex.item())
     for _ in range(extra):
-        step_device()
+        run_step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms = timed(step_device, args.steps)
+    ms = timed(run_step, args.steps, flush)
     barrier()
     for _ in range(3):
         step_e2e()
     barrier()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, flush)
     barrier()
     clocks = sampler.stop() if sampler else None
-
-    # ---- dominant kernel: the band-staged DA conv, timed per launch with CUDA events on its stream ----
-    conv_ms = []
-    if args.workload == "sun_train":
-        # sunlayer1.conv2 (32 -> 32, 7x7, full resolution): the largest single launch of the step, forward direction
-        pc, pk, pf, pm = 32, 7, 32, B * H * W
-        probe_layer = sun.sunlayer1.conv2
-        xt = torch.randn(B, H, W, pc, device="cuda")
-        stats = torch.zeros(B, pf, 2, dtype=torch.float64, device="cuda")
-    else:
-        pc, pk, pf, pm = C, K_SIZE, C, B * h * w
-        probe_layer = trunk.sequence[0].conv1
-        xt = torch.from_numpy(make_input(B, h, w, seed=7)).cuda()          # a trunk-shaped activation
-        stats = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
-    for rep in range(12 + 3):
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        probe_layer.call(xt, stats=stats)
-        e.record()
-        torch.cuda.synchronize()
-        if rep >= 3:
-            conv_ms.append(s.elapsed_time(e))
-    conv_t = float(np.mean(conv_ms))
 
     tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)           # max over ranks
     t_dev, t_e2e = (float(v) / args.steps for v in tot.tolist())
     in_sync = None
-    if world > 1 and trainer is not None:
-        # data-parallel sanity: after the timed steps every replica must hold the same weights (same init, averaged gradients)
-        chk = trainer.flat_w.double().sum().reshape(1)
+    if world > 1 and flat_w is not None:
+        # data-parallel sanity: after the timed steps every replica must hold the same weights (same init, summed gradients)
+        chk = flat_w.double().sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -510,73 +775,71 @@ def run_ours(args):
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else None
-        bf16_peak = peaks["bf16_tflops"] if peaks else 1590.0
-        flops = 2.0 * pm * (pk * pk * pc) * pf
-        achieved = flops / (conv_t * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("k7" if args.workload == "sun_train" else "trunk", {}).get("dram_bytes_per_launch")
+        is_train = args.workload in ("train", "sun_train", "trunk_train")
         line = {
             "metric": METRIC, "value": round(world * B / (t_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t_dev, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32(3xtf32)", "data": "synthetic",
-            "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B, "parallelism": (f"batch shards x{world}, " + ("gradient all-reduce (NCCL) of the flat buffer, Dense part overlapped with the conv backward"
-                                                                     if trainer is not None else "no collective")),
-                       "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None},
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.math], "data": "synthetic",
+            "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B,
+                       "parallelism": (f"batch shards x{world}, " + ("one gradient all-reduce (NCCL) of the flat buffers per step, the Dense bucket started "
+                                                                     "early and overlapped with the rest of the backward pass" if is_train else "no collective")),
+                       "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None,
+                       "math_mode": args.math},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": y_host.numel() * y_host.element_size(), "ms_per_step": round(t_e2e, 4)},
-            "gpu_launches": launches_per_step * args.steps, "abi_calls_per_step": abi_calls,
-            "roofline": {"kernel": "da_conv2d_fwd_band_kernel (%d->%d, k=%d, M=%d)" % (pc, pf, pk, pm), "bound": "tensor",
-                         "achieved": round(achieved, 2), "peak": round(bf16_peak / 2, 1), "unit": "TFLOP/s",
-                         "frac": round(achieved / (bf16_peak / 2), 4), "traffic": traffic,
-                         "peak_note": ("TF32 operands: peak = 1/2 x measured bf16 burst (%s)" % ("of measured" if peaks else "of fallback")),
-                         "frac_of_bf16_peak": round(achieved / bf16_peak, 4), "ms_per_launch": round(conv_t, 5),
-                         "flops_per_launch": flops},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "abi_calls_per_step": abi_calls,
+            "roofline": roofline_of(rows, traced_ms, peaks),
+            "kernel_shares": [{"kernel": r["label"], "launches": r["calls"], "ms": round(r["ms_total"], 4), "share": round(r["ms_total"] / traced_ms, 4),
+                               "tflops": (round(r["flops"] / (r["ms_per_call"] * 1e-3) / 1e12, 1) if r["flops"] else None)} for r in rows[:14]],
+            "traced_step_ms": round(traced_ms, 4),
             "clocks": clocks,
         }
         if in_sync is not None:
             line["replicas_in_sync"] = in_sync
-        if world == 1:
-            if args.workload == "sun_train" and not args.no_inference:
-                line["inference"] = measure_inference(pkg, args, rank, flush)
+        if world == 1 and not args.lean:
+            if args.workload == "train":
+                other = "tf32" if args.math == "3xtf32" else "3xtf32"
+                modes = {args.math: {"train_ms_per_step": round(t_dev, 4), "train_value": round(B / (t_dev * 1e-3), 1), "dtype": DTYPE[args.math]}}
+                line["inference"] = measure_inference(pkg, args, rank, flush, args.math)
+                modes[args.math]["inference_value"] = line["inference"]["value"]
+                # the other arithmetic mode, same process, same inputs
+                del graph
+                step2, fwd2, _, _ = build_train(pkg, args, rank, other)
+                for _ in range(2):
+                    fwd2()
+                g2 = graph_or_eager(fwd2, world, True)
+                run2 = (g2.replay if g2 is not None else fwd2)
+                for _ in range(5):
+                    run2()
+                ms2 = timed(run2, args.steps, flush)
+                t2 = float(np.mean(ms2))
+                modes[other] = {"train_ms_per_step": round(t2, 4), "train_value": round(B / (t2 * 1e-3), 1), "dtype": DTYPE[other],
+                                "inference_value": measure_inference(pkg, args, rank, flush, other)["value"]}
+                line["modes"] = modes
+                line["parity"] = {"3xtf32": "whole step vs the fp64 oracle: y_final_lin 3.4e-5 (log-luminance rel-L2; north_star bar 1e-3), losses <= 9e-5, "
+                                            "every gradient <= 5.3e-3 (tests/test_gpu_train_step.py)",
+                                  "tf32": "per layer vs the TF32-emulating oracle <= 2e-5; whole step vs the fp64 oracle: y_final_lin 3.1e-3, gradients <= 1e-1"}
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args):
-    """The oracle (a port of the reference dataflow) timed on the host cores, on a bounded sample."""
-    import torch
-    torch.set_num_threads(os.cpu_count())
-    B = args.batch
-    sample = min(B, 8)
-    step = oracle_step_fn(args, sample)
-    step()
-    reps, t0 = 0, time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 40):
-        step()
-        reps += 1
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": round(sample / dt, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{sample} of {B} panoramas per step, {reps} steps, torch-CPU fp32 restatement of the reference dataflow"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="panoramas per GPU per step")
     ap.add_argument("--height", type=int, default=32)
     ap.add_argument("--width", type=int, default=128)
-    ap.add_argument("--math", default="tf32", choices=["tf32", "3xtf32"])
-    ap.add_argument("--workload", default="sun_train", choices=["sun_train", "inference", "sky", "trunk", "trunk_train"],
-                    help="sun_train: the sun-position pre-train step, BASELINE configs[1] (default; the line also carries the full-inference "
-                         "throughput, configs[0]); inference: full generator inference; sky: its sky branch; trunk: the DA residual trunk alone")
-    ap.add_argument("--no-inference", action="store_true", help="sun_train: skip the secondary full-inference measurement")
+    ap.add_argument("--math", default="3xtf32", choices=["tf32", "3xtf32"],
+                    help="arithmetic of the tensor-core contractions: 3xtf32 (default; fp32-class results, meets the 1e-3 parity bar) or tf32")
+    ap.add_argument("--workload", default="train", choices=["train", "sun_train", "inference", "sky", "trunk", "trunk_train", "sweep"],
+                    help="train: the full train step, BASELINE configs[2] (default; the line also carries the full-inference throughput, "
+                         "configs[0], and both arithmetic modes); sun_train: the sun-position pre-train step, configs[1]; sweep: configs[3]")
+    ap.add_argument("--lean", action="store_true", help="skip the secondary measurements (inference, other mode, cpu_baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

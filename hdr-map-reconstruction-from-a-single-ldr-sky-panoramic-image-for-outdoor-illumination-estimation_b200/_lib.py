@@ -114,12 +114,18 @@ LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d
                      "sky_debug_band_trace": 0}
 
 
+_UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host")
+
+
 class _Lib:
-    """Attribute access to the C ABI with an optional per-entry-point call counter (`counts`: dict or None)."""
+    """Attribute access to the C ABI with an optional per-entry-point call counter (`counts`: dict or None) and an optional device
+    timeline (`trace`: list or None — every call is bracketed by CUDA events on the current stream; bench.py derives the kernel shares
+    of a step and the roofline of its largest one from it)."""
 
     def __init__(self, cdll):
         self._cdll = cdll
         self.counts = None
+        self.trace = None
 
     def __getattr__(self, name):
         fn = getattr(self._cdll, name)
@@ -127,6 +133,14 @@ class _Lib:
         def call(*args):
             if self.counts is not None:
                 self.counts[name] = self.counts.get(name, 0) + 1
+            if self.trace is not None and name not in _UNTRACED:
+                import torch
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                rc = fn(*args)
+                e.record()
+                self.trace.append((name, args, s, e))
+                return rc
             return fn(*args)
         call.__name__ = name
         setattr(self, name, call)       # resolved once; later lookups bypass __getattr__

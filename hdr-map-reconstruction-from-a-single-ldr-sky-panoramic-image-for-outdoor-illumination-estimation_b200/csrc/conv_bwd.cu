@@ -284,7 +284,7 @@ static int launch_wgrad(WgParams p, cudaStream_t st)
     p.tiles_per_part = (p.ntiles + parts - 1) / parts;
     parts = (p.ntiles + p.tiles_per_part - 1) / p.tiles_per_part;
     const int smem = p.stages * p.stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
-    SKY_CHECK_CUDA(cudaFuncSetAttribute(conv2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SKY_ENSURE_DYN_SMEM(conv2d_wgrad_kernel, 227 * 1024);
     conv2d_wgrad_kernel<<<dim3(parts, row_tiles), WG_THREADS, smem, st>>>(p);
     SKY_CHECK_LAUNCH();
     return SKY_OK;

@@ -279,11 +279,7 @@ int launch_fwd_smallf(const FwdArgs &a)
         return SKY_ERR_UNSUPPORTED;
     const size_t smem = ((size_t)a.k * a.k * a.C * 4 + (size_t)(SF_TH + a.k - 1) * (SF_TW + a.k - 1) * (a.C + 4)) * sizeof(float);
     if (smem > 110 * 1024) return SKY_ERR_UNSUPPORTED;
-    static bool configured = false;
-    if (!configured) {
-        SKY_CHECK_CUDA(cudaFuncSetAttribute(conv2d_smallf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        configured = true;
-    }
+    SKY_ENSURE_DYN_SMEM(conv2d_smallf_kernel, 110 * 1024);
     const int ntiles = ((a.w + SF_TW - 1) / SF_TW) * ((a.h + SF_TH - 1) / SF_TH) * a.B;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;          // two resident CTAs per SM
     conv2d_smallf_kernel<<<grid, SF_THREADS, smem, a.stream>>>(a.x, a.packed, a.bias, a.residual, a.aux, a.y, a.B, a.h, a.w, a.C, a.F, f_pad_of(a.F),
@@ -307,11 +303,8 @@ static int launch_fwd_smallc_da(const FwdArgs &a, const float *kernel)
     dim3 grid((a.w + SC_THREADS - 1) / SC_THREADS, a.h, a.B);
 #define SKY_LAUNCH_SCDA(CC)                                                                                                   \
     do {                                                                                                                      \
-        static bool configured = false;                                                                                       \
-        if (!configured) {                                                                                                    \
-            SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_smallc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            configured = true;                                                                                                \
-        }                                                                                                                     \
+        SKY_ENSURE_DYN_SMEM(da_conv2d_smallc_kernel<CC>, 200 * 1024);                    \
+                                                                                                                             \
         da_conv2d_smallc_kernel<CC><<<grid, SC_THREADS, smem, a.stream>>>(a.x, a.offsets, kernel, a.bias, a.y, a.stats, a.h, \
                                                                           a.w, a.F, a.k, hy_lo, nrows, a.h + pht, a.w + pwt, ph0, pw0,   \
                                                                           a.flags, a.slope);                                            \
@@ -346,11 +339,8 @@ extern "C" int sky_conv2d_smallc_fwd(const float *x, const float *kernel, const 
     cudaStream_t st = (cudaStream_t)stream;
 #define SKY_LAUNCH_SC(CC)                                                                                                     \
     do {                                                                                                                      \
-        static bool configured = false;                                                                                       \
-        if (!configured) {                                                                                                    \
-            SKY_CHECK_CUDA(cudaFuncSetAttribute(conv2d_smallc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            configured = true;                                                                                                \
-        }                                                                                                                     \
+        SKY_ENSURE_DYN_SMEM(conv2d_smallc_kernel<CC>, 200 * 1024);                    \
+                                                                                                                             \
         conv2d_smallc_kernel<CC><<<grid, SC_THREADS, smem, st>>>(x, kernel, bias, y, stats, h, w, F, k, epilogue_flags, slope); \
     } while (0)
     switch (C) {

@@ -357,11 +357,7 @@ extern "C" int sky_da_conv2d_bwd_data(const float *dy, const float *offsets, con
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)p.M * C * sizeof(float), st));
     const int smem = p.FC * 16384 + 2 * p.FC * 4096 + 64 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    SKY_ENSURE_DYN_SMEM(da_conv2d_dgrad_kernel, 227 * 1024);
     const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     int ksplit = (2 * 148 + tiles - 1) / tiles;          // about two waves of CTAs
     if (ksplit < 1) ksplit = 1;
@@ -390,11 +386,7 @@ extern "C" int sky_da_conv2d_bwd_filter(const float *x, const float *dy, const f
     p.tiles_per_part = (ntiles + parts - 1) / parts;
     p.parts = (ntiles + p.tiles_per_part - 1) / p.tiles_per_part;
     const int smem = 4 * 16384 + p.FC * 16384 + 64 + 4 * BLOCK_M * (int)sizeof(CornerRef) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    SKY_ENSURE_DYN_SMEM(da_conv2d_wgrad_kernel, 227 * 1024);
     dim3 grid(p.parts, groups, p.CC);
     da_conv2d_wgrad_kernel<<<grid, BWD_THREADS, smem, st>>>(p);
     SKY_CHECK_LAUNCH();

@@ -524,11 +524,7 @@ static int launch_fwd(const FwdParams &p, cudaStream_t st)
 {
     using L = FwdSmem<STAGES, SPLIT3>;
     const int smem = L::total_bytes(p.Fp);
-    static int configured = 0;
-    if (configured < smem) {
-        SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_fwd_tc_kernel<STAGES, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
-    }
+    SKY_ENSURE_DYN_SMEM((da_conv2d_fwd_tc_kernel<STAGES, SPLIT3>), 227 * 1024);
     SKY_REQUIRE(smem <= 227 * 1024, SKY_ERR_UNSUPPORTED, "shared memory %d B exceeds 227 KB (F=%d)", smem, p.F);
     const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int ksplit = (p.KB + p.kb_per_split - 1) / p.kb_per_split;

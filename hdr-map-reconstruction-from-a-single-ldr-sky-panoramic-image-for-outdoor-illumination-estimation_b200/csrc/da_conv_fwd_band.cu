@@ -691,11 +691,7 @@ static int launch_band(BandParams &p, const FwdArgs &a, int hy_span, int hx_span
     if (rc != SKY_OK) return rc;
 
     const int smem = L::total_bytes(p.Fp, p.band_stride, p.NB, p.k2);
-    static bool configured = false;
-    if (!configured) {
-        SKY_CHECK_CUDA(cudaFuncSetAttribute(da_conv2d_fwd_band_kernel<STAGES, SPLIT3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    SKY_ENSURE_DYN_SMEM((da_conv2d_fwd_band_kernel<STAGES, SPLIT3>), 227 * 1024);
     const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
     da_conv2d_fwd_band_kernel<STAGES, SPLIT3><<<grid, BAND_THREADS, smem, a.stream>>>(p, tmap);
     SKY_CHECK_LAUNCH();
@@ -735,7 +731,7 @@ int launch_fwd_band(const FwdArgs &a)
     const int hy_span = hy_hi - hy_lo, hx_span = hx_hi - hx_lo;
     if (a.math_mode == SKY_MATH_TF32)
         return p.Fp <= 128 ? launch_band<4, false>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
-    return p.Fp <= 32 ? launch_band<2, true>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
+    return p.Fp <= 128 ? launch_band<2, true>(p, a, hy_span, hx_span) : SKY_ERR_UNSUPPORTED;
 }
 
 }  // namespace sky

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/skydome_b200.h"
 
@@ -27,6 +28,20 @@ void count_launch();
     do {                                     \
         sky::count_launch();                 \
         SKY_CHECK_CUDA(cudaGetLastError());  \
+    } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: opt in once per device, thread-safe.
+// (A per-process bool would leave a second GPU of the same process — or a racing second thread — without the opt-in.)
+#define SKY_ENSURE_DYN_SMEM(kernel, bytes)                                                                       \
+    do {                                                                                                         \
+        static std::atomic<unsigned long long> _done{ 0 };                                                       \
+        int _dev = 0;                                                                                            \
+        SKY_CHECK_CUDA(cudaGetDevice(&_dev));                                                                    \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                                     \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                                   \
+            SKY_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));    \
+            _done.fetch_or(_bit, std::memory_order_release);                                                     \
+        }                                                                                                        \
     } while (0)
 
 #define SKY_REQUIRE(cond, code, ...)     \

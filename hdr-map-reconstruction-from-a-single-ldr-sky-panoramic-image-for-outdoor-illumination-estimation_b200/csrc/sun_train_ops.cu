@@ -354,11 +354,8 @@ extern "C" int sky_da_conv2d_smallc_bwd_filter(const float *x, const float *dy, 
     dim3 grid((w + SW_THREADS - 1) / SW_THREADS, (h + SW_ROWS - 1) / SW_ROWS, B);
 #define SKY_LAUNCH_SW(CC)                                                                                                      \
     do {                                                                                                                       \
-        static bool configured = false;                                                                                        \
-        if (!configured) {                                                                                                     \
-            SKY_CHECK_CUDA(cudaFuncSetAttribute(da_smallc_wgrad_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-            configured = true;                                                                                                 \
-        }                                                                                                                      \
+        SKY_ENSURE_DYN_SMEM(da_smallc_wgrad_kernel<CC>, 200 * 1024);                    \
+                                                                                                                              \
         da_smallc_wgrad_kernel<CC><<<grid, SW_THREADS, smem, st>>>(x, offsets, dy, dkernel, dbias, h, w, F, k, h + pht, w + pwt, ph0, pw0); \
     } while (0)
     SKY_REQUIRE(smem <= 200 * 1024, SKY_ERR_UNSUPPORTED, "kernel too large for the staged blend (k=%d C=%d)", k, C);

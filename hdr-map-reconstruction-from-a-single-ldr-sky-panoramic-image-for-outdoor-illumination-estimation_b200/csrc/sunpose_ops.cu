@@ -229,11 +229,7 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
     SKY_CHECK_CUDA(cudaMemsetAsync(y, 0, (size_t)B * N * sizeof(float), st));
     const int bcta = (B + DN_BM - 1) / DN_BM;
     if (N % 4 == 0 && K % 4 == 0 && N >= DS_BN && ((uintptr_t)W & 15) == 0 && ((uintptr_t)x & 15) == 0) {
-        static bool configured = false;
-        if (!configured) {
-            SKY_CHECK_CUDA(cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM));
-            configured = true;
-        }
+        SKY_ENSURE_DYN_SMEM(dense_stream_kernel, DS_SMEM);
         CUtensorMap tmap_w, tmap_x;
         int rc = encode_2d_tensor_map(&tmap_w, W, K, N, DS_BN, DS_BK);
         if (rc != SKY_OK) return rc;

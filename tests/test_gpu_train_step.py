@@ -6,8 +6,13 @@ Tolerances (relative L2 unless stated):
   BatchNormalization forward / backward, resize adjoint, tail, radiance head, LSGAN / L1 adjoints     1e-5   (fp32 elementwise / fp64 sums)
   whole step, `3xtf32` forward convs vs the fp64 oracle: losses 2e-3, every gradient of G u Sun and D  5e-2  (TF32 backward convs; conv
       biases in front of a norm have exactly-zero gradients and are compared absolutely)
-  whole step, `tf32` vs the TF32-EMULATING oracle (operands rounded to 10 mantissa bits, what TensorFlow computes on any Ampere-or-newer
-      GPU): losses 5e-3, gradients 5e-2; vs the fp64 oracle the same run is only held to 3e-1 (ReLU-mask / arg-max flips).
+  single layers, `tf32` vs the TF32-EMULATING oracle on identical inputs (operands rounded to 10 mantissa bits with cvt.rna, fp64
+      accumulate — what TensorFlow's GPU kernels compute on any Ampere-or-newer GPU up to summation order): 2e-5 forward, data gradient
+      and weight gradient.  This is the proof that the tensor-core kernels are right GIVEN TF32 operands (vs fp64 they sit at ~3e-4).
+  whole step, `tf32`: TF32 rounding is chaotic over stacked layers — a 1e-6 difference in one layer's input re-draws the rounding of
+      0.1 % of the next layer's operands, and after a few layers two TF32 evaluations are as far apart as either is from fp64 — so the
+      emulating oracle cannot pin the whole path tighter than the fp64 one: measured y_final_lin 2.2e-3 (emulating) / 3.1e-3 (fp64),
+      gradients up to 7e-2 / 1e-1 (bars 5e-3 / 1e-2 and 1e-1 / 3e-1).  The mode that meets north_star's 1e-3 is `3xtf32` (3.4e-5).
 """
 import json
 import os
@@ -115,6 +120,59 @@ def test_da_weight_gradient_pipelined(pkg, B, h, w, C, F, k):
                                                       B, h, w, C, C, F, k, 1, 0, st()))
     assert rel(dk.cpu().numpy(), want_dk) < 2e-3, rel(dk.cpu().numpy(), want_dk)
     assert rel(db.cpu().numpy(), want_db) < 1e-4
+
+
+@pytest.mark.parametrize("C,F,k,s", [(128, 128, 3, 1), (64, 128, 3, 2), (256, 256, 3, 1), (64, 128, 4, 2), (32, 64, 3, 1)])
+def test_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k, s):
+    """Same inputs, same TF32 operand rounding (round-to-nearest, ties away), fp64 accumulate in the oracle vs fp32 in TMEM: the
+    forward, data-gradient and weight-gradient kernels agree to summation-order noise."""
+    B, h, w = 2, 8, 16
+    rng = np.random.default_rng(C + F + k + s)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    w4 = (rng.standard_normal((k, k, C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(F)).astype(np.float32)
+    xt, wt, bt = T(x).double().requires_grad_(True), T(w4).double().requires_grad_(True), T(bias).double()
+    with tf32_emu.emulate():
+        y = M.conv2d_same(xt, wt, bt, stride=s, acc_dtype=torch.float64, tf32=True)
+        dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        y.backward(T(dy).double())
+    layer = pkg.ops.conv2d(F, strides=s, k_h=k, k_w=k, kernel_initializer=w4, bias_initializer=bias)
+    xd, dyd = T(x).cuda(), T(dy).cuda()
+    got = layer(xd)
+    assert rel(got.cpu().numpy(), y.detach().numpy()) < 2e-5, rel(got.cpu().numpy(), y.detach().numpy())
+    dx = layer.backward_data(xd, dyd)
+    assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 2e-5, rel(dx.cpu().numpy(), xt.grad.numpy())
+    dk, db = torch.empty_like(layer.w), torch.empty_like(layer.biases)
+    layer.backward_filter(xd, dyd, dk, db)
+    assert rel(dk.cpu().numpy(), wt.grad.numpy()) < 2e-5, rel(dk.cpu().numpy(), wt.grad.numpy())
+
+
+@pytest.mark.parametrize("C,F,k", [(128, 128, 3), (32, 32, 7), (64, 64, 3)])
+def test_da_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k):
+    """The distortion-aware layer (band-staged forward, scatter data gradient, pipelined weight gradient) against the materialised
+    oracle with TF32-rounded contraction operands.  The forward kernel blends separably (dy * (dx * .)), the oracle in the reference's
+    four-product order: the blended pixel differs in its last fp32 bit, which re-draws a TF32 rounding now and then (bar 1e-4)."""
+    B, h, w = 2, 16, 64
+    rng = np.random.default_rng(C + k)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    kern = (rng.standard_normal((k * k * C, F)) / np.sqrt(k * k * C)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(F)).astype(np.float32)
+    xt, kt, bt = T(x).double().requires_grad_(True), T(kern).double().requires_grad_(True), T(bias).double()
+    with tf32_emu.emulate():
+        y = O.conv2d_forward(xt, kt, bt, k, acc_dtype=torch.float64)
+        dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+        y.backward(T(dy).double())
+    layer = pkg.conv2d(F, kernel_size=k, kernel_initializer=kern, bias_initializer=bias)
+    xd, dyd = T(x).cuda(), T(dy).cuda()
+    got = layer(xd)
+    assert rel(got.cpu().numpy(), y.detach().numpy()) < 1e-4, rel(got.cpu().numpy(), y.detach().numpy())
+    dx, dk, db = pkg.distortion_aware_ops.conv2d_backward(layer, xd, dyd)
+    assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 1e-4, rel(dx.cpu().numpy(), xt.grad.numpy())
+    assert rel(dk.cpu().numpy(), kt.grad.numpy()) < 1e-4, rel(dk.cpu().numpy(), kt.grad.numpy())
+    dk2 = torch.empty_like(dk)
+    pkg._lib.check(pkg._lib.LIB.sky_conv2d_bwd_filter(xd.data_ptr(), dyd.data_ptr(), layer.offset_table.data_ptr(), dk2.data_ptr(), None,
+                                                      B, h, w, C, C, F, k, 1, 0, st()))
+    assert rel(dk2.cpu().numpy(), kt.grad.numpy()) < 1e-4, rel(dk2.cpu().numpy(), kt.grad.numpy())
 
 
 # --------------------------------------------------------------------------------------------------------------------------------
@@ -333,7 +391,7 @@ def _zero_grad_bias(name):
                                                                                    ("conv1_d", "conv2_d", "conv3_d", "conv3_f", "conv2_f", "conv3_u", "conv2_u"))
 
 
-@pytest.mark.parametrize("mode,emulate,tol_loss,tol_y,tol_grad", [("3xtf32", False, 2e-3, 1e-3, 5e-2), ("tf32", True, 5e-3, 2e-3, 5e-2),
+@pytest.mark.parametrize("mode,emulate,tol_loss,tol_y,tol_grad", [("3xtf32", False, 2e-3, 1e-3, 5e-2), ("tf32", True, 5e-3, 5e-3, 1e-1),
                                                                   ("tf32", False, 2e-2, 1e-2, 3e-1)])
 def test_train_step_vs_autograd(pkg, mode, emulate, tol_loss, tol_y, tol_grad):
     B, H, W = 2, 32, 128
