@@ -703,6 +703,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     # kernel shares of the step and the roofline of its largest kernel, from a device timeline of eager steps
     rows, traced_ms = trace_step(pkg, lambda: forward(x))
+    if args.trace_out and rank == 0:
+        json.dump({"traced_step_ms": traced_ms, "math": args.math, "rows": rows}, open(args.trace_out, "w"), indent=1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")             # > 126 MB L2
 
     # ---- the step: captured once into a CUDA graph where it holds no collective and no host-side scalar state ----
@@ -840,6 +842,7 @@ def main():
                     help="train: the full train step, BASELINE configs[2] (default; the line also carries the full-inference throughput, "
                          "configs[0], and both arithmetic modes); sun_train: the sun-position pre-train step, configs[1]; sweep: configs[3]")
     ap.add_argument("--lean", action="store_true", help="skip the secondary measurements (inference, other mode, cpu_baseline)")
+    ap.add_argument("--trace-out", default=None, help="write the full per-entry-point device timeline of one step (JSON) to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

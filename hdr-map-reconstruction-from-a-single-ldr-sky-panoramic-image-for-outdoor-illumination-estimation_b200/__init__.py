@@ -7,6 +7,7 @@ from .distortion_aware_ops import conv2d, deconv2d   # noqa: F401
 from . import generator                 # noqa: F401
 from .generator import resBlock, resLayer, InstanceNormalization   # noqa: F401
 from . import sharding                  # noqa: F401
+from . import _flat                      # noqa: F401
 from . import ops                        # noqa: F401
 from .generator import model             # noqa: F401
 from . import trunk_train              # noqa: F401

@@ -156,31 +156,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv2d_wgrad_kernel(const WgPar
                 }
             }
             named_bar_sync(1, WG_PROD_THREADS);
-            // ---- A: Pix[pixel][kernel row], MN-major ----
-#pragma unroll 2
-            for (int r = 0; r < WG_PX / WG_PROD_WARPS; ++r) {
-                const int px = px0 + WG_PROD_WARPS * r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k_ok) {
-                    if (p.plain) {
-                        const WgPix e = reinterpret_cast<const WgPix *>(tab)[px];
-                        const int iy = e.iy0 + ta, ix = e.ix0 + tb;
-                        if (e.ok && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
-                            v = __ldg(reinterpret_cast<const float4 *>(p.x + ((size_t)e.base + (size_t)iy * p.w + ix) * p.C + c));
-                    } else {
+            // ---- A: Pix[pixel][kernel row], MN-major.  All gathers of a batch are issued before the first store: the stage is bound by
+            //      L2 latency, so loads in flight per thread are what counts (8 for the plain sampler, 4 pixels x 4 corners otherwise) ----
+            uint8_t *a_dst = a_tile + (q >> 3) * (WG_PX * 128);
+            if (p.plain) {
+                float4 v[WG_PX / WG_PROD_WARPS];
+#pragma unroll
+                for (int r = 0; r < WG_PX / WG_PROD_WARPS; ++r) {
+                    const WgPix e = reinterpret_cast<const WgPix *>(tab)[px0 + WG_PROD_WARPS * r];
+                    const int iy = e.iy0 + ta, ix = e.ix0 + tb;
+                    v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (k_ok && e.ok && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w)
+                        v[r] = __ldg(reinterpret_cast<const float4 *>(p.x + ((size_t)e.base + (size_t)iy * p.w + ix) * p.C + c));
+                }
+#pragma unroll
+                for (int r = 0; r < WG_PX / WG_PROD_WARPS; ++r)
+                    *reinterpret_cast<uint4 *>(a_dst + wg_sw_offset((uint32_t)(px0 + WG_PROD_WARPS * r), (uint32_t)(q & 7))) = wg_tf32x4(v[r]);
+            } else {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 pv[4][4];
+                    float wv[4][4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int px = px0 + WG_PROD_WARPS * (4 * half + r);
                         const CornerRef cr = reinterpret_cast<const CornerRef *>(tab)[px * 4 + (t - t_first)];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            if (cr.off[u] < 0) continue;
-                            const float4 pv = __ldg(reinterpret_cast<const float4 *>(p.x + cr.off[u] + c));
-                            v.x = fmaf(cr.w[u], pv.x, v.x); v.y = fmaf(cr.w[u], pv.y, v.y);
-                            v.z = fmaf(cr.w[u], pv.z, v.z); v.w = fmaf(cr.w[u], pv.w, v.w);
+                            const bool ok = k_ok && cr.off[u] >= 0;
+                            wv[r][u] = ok ? cr.w[u] : 0.f;
+                            pv[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ok) pv[r][u] = __ldg(reinterpret_cast<const float4 *>(p.x + cr.off[u] + c));
                         }
                     }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            v.x = fmaf(wv[r][u], pv[r][u].x, v.x); v.y = fmaf(wv[r][u], pv[r][u].y, v.y);
+                            v.z = fmaf(wv[r][u], pv[r][u].z, v.z); v.w = fmaf(wv[r][u], pv[r][u].w, v.w);
+                        }
+                        *reinterpret_cast<uint4 *>(a_dst + wg_sw_offset((uint32_t)(px0 + WG_PROD_WARPS * (4 * half + r)), (uint32_t)(q & 7))) = wg_tf32x4(v);
+                    }
                 }
-                *reinterpret_cast<uint4 *>(a_tile + (q >> 3) * (WG_PX * 128) + wg_sw_offset((uint32_t)px, (uint32_t)(q & 7))) = wg_tf32x4(v);
             }
             // ---- B: dY[pixel][filter], MN-major ----
+#pragma unroll 4
             for (int e = tid; e < WG_PX * f4n; e += WG_PROD_THREADS) {
                 const int px = e / f4n, c4 = e % f4n, m = m0 + px, f = 4 * c4;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -252,6 +274,108 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv2d_wgrad_kernel(const WgPar
     }
     __syncthreads();
     if (warp == WG_PROD_WARPS) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight gradient of the 3-filter layers (conv1_f / conv1_u, generator.py:76,85: 7x7, 32 -> 3): dW[(t,c), f] = sum_m x[m @ t, c] dy[m, f]
+// 1.2 GFLOP at B = 32, all input reuse: on the tensor-core kernel its cost is the 822 MB im2col gather (0.93 ms).  Here a persistent CTA
+// walks 8 x 32 pixel tiles, stages the (8 + k - 1) x (32 + k - 1) input patch and the dy tile in shared memory, and each thread keeps the
+// sums of 4 channels x up to 4 taps x F filters in registers across ALL its tiles (one atomicAdd per sum at the end).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SFW_TH = 8, SFW_TW = 32, SFW_THREADS = 128, SFW_MAXT = 4;
+
+__global__ void __launch_bounds__(SFW_THREADS) conv2d_wgrad_smallf_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                                           float *__restrict__ dw, int B, int h, int w, int C, int F, int k)
+{
+    extern __shared__ __align__(16) float sfw[];
+    const int k2 = k * k, r = k / 2, PW = SFW_TW + k - 1, PH = SFW_TH + k - 1, PS = C + 4;
+    float *patch = sfw;                                          // [PH][PW][PS]
+    float4 *dyt = reinterpret_cast<float4 *>(sfw + (size_t)PH * PW * PS);   // [SFW_TH * SFW_TW] (f padded to 4)
+    const int tid = threadIdx.x, c4n = C / 4, tgn = SFW_THREADS / c4n;
+    const int cg = tid % c4n, tg = tid / c4n;                    // 4-channel group, tap group: taps tg, tg + tgn, ...
+    const int tiles_x = (w + SFW_TW - 1) / SFW_TW, tiles_y = (h + SFW_TH - 1) / SFW_TH, ntiles = tiles_x * tiles_y * B;
+    float acc[SFW_MAXT][4][4];
+#pragma unroll
+    for (int a = 0; a < SFW_MAXT; ++a)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[a][u][f] = 0.f;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / (tiles_x * tiles_y), trem = tile % (tiles_x * tiles_y);
+        const int i0 = (trem / tiles_x) * SFW_TH, j0 = (trem % tiles_x) * SFW_TW;
+        __syncthreads();
+        for (int e = tid; e < PH * PW * c4n; e += SFW_THREADS) {
+            const int c4 = e % c4n, px = (e / c4n) % PW, py = e / (c4n * PW);
+            const int yy = i0 + py - r, xx = j0 + px - r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(reinterpret_cast<const float4 *>(x + (((size_t)b * h + yy) * w + xx) * C) + c4);
+            *reinterpret_cast<float4 *>(patch + (size_t)(py * PW + px) * PS + 4 * c4) = v;
+        }
+        for (int e = tid; e < SFW_TH * SFW_TW; e += SFW_THREADS) {
+            const int i = i0 + e / SFW_TW, j = j0 + e % SFW_TW;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < h && j < w) {
+                const float *src = dy + (((size_t)b * h + i) * w + j) * F;
+                v.x = __ldg(src);
+                if (F > 1) v.y = __ldg(src + 1);
+                if (F > 2) v.z = __ldg(src + 2);
+                if (F > 3) v.w = __ldg(src + 3);
+            }
+            dyt[e] = v;
+        }
+        __syncthreads();
+        for (int p0 = 0; p0 < SFW_TH * SFW_TW; p0 += 8) {        // 8 pixels of one tile row: their dy stays in registers over the taps
+            float4 g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = dyt[p0 + q];
+            const int py = p0 / SFW_TW, px = p0 % SFW_TW;
+#pragma unroll
+            for (int a = 0; a < SFW_MAXT; ++a) {
+                const int t = tg + a * tgn;
+                if (t >= k2) break;
+                const float *src = patch + (size_t)((py + t / k) * PW + px + t % k) * PS + 4 * cg;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(src + (size_t)q * PS);
+                    const float xs[4] = { xv.x, xv.y, xv.z, xv.w };
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[a][u][0] = fmaf(xs[u], g[q].x, acc[a][u][0]);
+                        acc[a][u][1] = fmaf(xs[u], g[q].y, acc[a][u][1]);
+                        acc[a][u][2] = fmaf(xs[u], g[q].z, acc[a][u][2]);
+                        acc[a][u][3] = fmaf(xs[u], g[q].w, acc[a][u][3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < SFW_MAXT; ++a) {
+        const int t = tg + a * tgn;
+        if (t >= k2) break;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if (f < F) atomicAdd(dw + ((size_t)t * C + 4 * cg + u) * F + f, acc[a][u][f]);
+    }
+}
+
+// returns SKY_ERR_UNSUPPORTED (no error text) when the layer is outside what the kernel covers
+static int launch_wgrad_smallf(const float *x, const float *dy, float *dw, int B, int h, int w, int C, int F, int k, cudaStream_t st)
+{
+    if (F > 4 || C % 4 != 0 || C > 128 || SFW_THREADS % (C / 4) != 0 || (k & 1) == 0) return SKY_ERR_UNSUPPORTED;
+    const int tgn = SFW_THREADS / (C / 4);
+    if (k * k > SFW_MAXT * tgn) return SKY_ERR_UNSUPPORTED;
+    const size_t smem = ((size_t)(SFW_TH + k - 1) * (SFW_TW + k - 1) * (C + 4) + (size_t)SFW_TH * SFW_TW * 4) * sizeof(float);
+    if (smem > 160 * 1024) return SKY_ERR_UNSUPPORTED;
+    SKY_ENSURE_DYN_SMEM(conv2d_wgrad_smallf_kernel, 160 * 1024);
+    const int ntiles = ((w + SFW_TW - 1) / SFW_TW) * ((h + SFW_TH - 1) / SFW_TH) * B;
+    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    conv2d_wgrad_smallf_kernel<<<grid, SFW_THREADS, smem, st>>>(x, dy, dw, B, h, w, C, F, k);
+    SKY_CHECK_LAUNCH();
+    return SKY_OK;
 }
 
 // db[f] (+)= sum_m dy[m*ldF + f]
@@ -369,7 +493,10 @@ extern "C" int sky_conv2d_bwd_filter(const float *x, const float *dy, const floa
     }
     p.M = B * p.oh * p.ow;
     if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dkernel, 0, (size_t)p.k2 * C_store * F * sizeof(float), st));
-    for (int f0 = 0; f0 < F; f0 += 256) {          // more than 256 filters (d4: 512): column slices of the same dY
+    int rc_small = SKY_ERR_UNSUPPORTED;
+    if (!offsets && stride == 1 && C_store == C) rc_small = launch_wgrad_smallf(x, dy, dkernel, B, h, w, C, F, k, st);   // conv1_f / conv1_u
+    if (rc_small != SKY_OK && rc_small != SKY_ERR_UNSUPPORTED) return rc_small;
+    for (int f0 = 0; rc_small == SKY_ERR_UNSUPPORTED && f0 < F; f0 += 256) {          // more than 256 filters (d4: 512): column slices of the same dY
         p.f0 = f0; p.F = (F - f0) < 256 ? (F - f0) : 256;
         int rc = launch_wgrad(p, st);
         if (rc != SKY_OK) return rc;

@@ -1,6 +1,14 @@
 """Batch sharding of the path across the GPUs of one box: every conv / instance-norm term is per-sample,
-so rank r simply owns a contiguous slice of the panoramas and no data-path collective exists for inference.  The only
-torch.distributed traffic is the timing protocol of bench.py (barrier + max over ranks)."""
+so rank r simply owns a contiguous slice of the panoramas and no data-path collective exists for inference (north_star:
+"independent per-GPU shards with no collective").  The only torch.distributed traffic of an inference run is the timing
+protocol of bench.py (barrier + max over ranks).
+
+Two terms of the reference couple the samples of a batch, and under sharding both are evaluated PER SHARD (a documented
+deviation): tf.reduce_max(sunpose_pred) over the whole batch (generator.py:160) — so a sharded inference equals
+the reference run on each shard's batch, not on the concatenated batch — and, in training, the BatchNormalization batch
+statistics of sunRadNet / the discriminator.  Training normalises every loss adjoint by the GLOBAL batch (train.Step.train_step /
+train_sun.SunTrainer.sun_train_step take `global_batch`), so the all-reduced SUM of the per-rank gradients is the gradient of
+the global-batch mean for any shard sizes; a rank whose shard is empty contributes zeros and still joins the collectives."""
 from __future__ import annotations
 
 import torch

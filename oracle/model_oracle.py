@@ -43,7 +43,11 @@ def res_block(x, w, k=3, dilation=1, acc_dtype=torch.float32):
     a1 = leaky_relu(instance_norm(c1, w["norm1_gamma"].to(dt), w["norm1_beta"].to(dt)), 0.1)
     c2 = O.conv2d_forward(a1 if dt == torch.float32 else a1, w["conv2_kernel"], w["conv2_bias"], k, dilation, acc_dtype=dt)
     n2 = instance_norm(c2, w["norm2_gamma"].to(dt), w["norm2_beta"].to(dt))
-    return x.to(dt) + n2
+    ident = x.to(dt)
+    if "identity_kernel" in w:                 # generator.py:23-24: 1x1 projection shortcut when the channel count changes
+        ik = O._as_t(w["identity_kernel"])
+        ident = conv2d_same(x, ik.reshape(1, 1, x.shape[-1], -1), w["identity_bias"], acc_dtype=dt)
+    return ident + n2
 
 
 def res_layer(x, blocks, k=3, dilation=1, acc_dtype=torch.float32):

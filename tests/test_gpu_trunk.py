@@ -63,6 +63,36 @@ def test_res_block_and_trunk_vs_oracle(pkg, mode, tol_block, tol_trunk):
     assert rel_l2(got, want32) <= tol_trunk
 
 
-def test_projection_shortcut_is_out_of_scope(pkg):
-    with pytest.raises(NotImplementedError):
-        pkg.resBlock(64, 128)
+def test_projection_shortcut(pkg):
+    """resBlock with filter_in != filter_out (generator.py:21-24): the identity branch is a 1x1 ops.conv2d.  Forward and the gradient
+    w.r.t. the block input / the projection kernel against autograd through the oracle (TF32 operands: 2e-3 / 2e-2)."""
+    import numpy as np
+    from oracle import model_oracle as M
+    rng = np.random.default_rng(9)
+    B, h, w, Ci, Co, k = 2, 8, 32, 64, 128, 3
+    x = rng.standard_normal((B, h, w, Ci)).astype(np.float32)
+    wts = {}
+    c = Ci
+    for i in (1, 2):
+        wts[f"conv{i}_kernel"] = (rng.standard_normal((k * k * c, Co)) / np.sqrt(k * k * c)).astype(np.float32)
+        wts[f"conv{i}_bias"] = (0.1 * rng.standard_normal(Co)).astype(np.float32)
+        wts[f"norm{i}_gamma"] = (1 + 0.1 * rng.standard_normal(Co)).astype(np.float32)
+        wts[f"norm{i}_beta"] = (0.1 * rng.standard_normal(Co)).astype(np.float32)
+        c = Co
+    wts["identity_kernel"] = (rng.standard_normal((Ci, Co)) / np.sqrt(Ci)).astype(np.float32)
+    wts["identity_bias"] = (0.1 * rng.standard_normal(Co)).astype(np.float32)
+    leaves = {kk: torch.from_numpy(v).double().requires_grad_(True) for kk, v in wts.items()}
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    want = M.res_block(xt, leaves, k, acc_dtype=torch.float64)
+    up = rng.standard_normal(tuple(want.shape)).astype(np.float32)
+    want.backward(torch.from_numpy(up).double())
+    blk = pkg.resBlock(Ci, Co)
+    blk.build((B, h, w, Ci))
+    blk.set_weights(wts)
+    fv = pkg._flat.FlatVars(blk.owner_list(), "cuda")
+    got = blk(torch.from_numpy(x).cuda(), save=True)
+    assert rel_l2(got.cpu().numpy(), want.detach().numpy()) <= 2e-3
+    dx = blk.backward(torch.from_numpy(up).cuda(), fv)
+    assert rel_l2(dx.cpu().numpy(), xt.grad.numpy()) <= 2e-2
+    assert rel_l2(fv.grad(blk.identity, "w").cpu().numpy().reshape(Ci, Co), leaves["identity_kernel"].grad.numpy()) <= 2e-3
+    assert rel_l2(fv.grad(blk.conv1, "kernel").cpu().numpy(), leaves["conv1_kernel"].grad.numpy()) <= 2e-2

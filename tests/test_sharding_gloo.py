@@ -101,3 +101,37 @@ def test_shard_bounds_edge_cases(pkg):
     assert [sb(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert [sb(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]      # empty shards
     assert sb(0, 0, 1) == (0, 0)
+
+
+def _worker_ragged(rank, world, port, ret):
+    """Ragged shards (3 samples over 2 ranks) and an empty shard (1 sample over 2 ranks): with the adjoints normalised by the GLOBAL
+    batch, the two-bucket all-reduce protocol of train_sun / train returns the global-batch mean gradient on every rank."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = importlib.import_module(PKG_NAME)
+    ts, sh = pkg.train_sun, pkg.sharding
+    out = {}
+    for gb in (3, 1):
+        per_sample = torch.arange(gb * 6, dtype=torch.float32).reshape(gb, 6) + 1.0      # sample i's gradient of its own loss term
+        lo, hi = sh.shard_bounds(gb, rank, world)
+        flat_g = per_sample[lo:hi].sum(0) / gb if hi > lo else torch.zeros(6)             # adjoints scaled by 1 / global batch; empty shard: zeros
+        work = ts.start_tail_allreduce(flat_g, 4)                                         # "Dense" bucket first ...
+        ts.finish_allreduce(flat_g, 4, work)                                              # ... then the rest, then join
+        out[gb] = (flat_g.tolist(), per_sample.mean(0).tolist())
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_ragged_and_empty_shards_give_the_global_mean():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_ragged, args=(world, port, ret), nprocs=world, join=True)
+        ret = dict(ret)
+    for rank in (0, 1):
+        for gb in (3, 1):
+            got, want = ret[rank][gb]
+            assert np.allclose(got, want, rtol=1e-6), (rank, gb, got, want)
