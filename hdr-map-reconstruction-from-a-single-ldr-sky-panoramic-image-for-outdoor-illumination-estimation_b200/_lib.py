@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libskydome_b200.so")
 OK = 0
 ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
 EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_SUN_BLEND, EPI_MASK, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 16, 32, 256
+EPI_FORCE_BAND = 512
 MATH_TF32, MATH_3XTF32 = 0, 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -26,6 +27,13 @@ SIGNATURES = {
     "sky_da_packed_weight_bytes": (_sz, [_i, _i, _i, _i]),
     "sky_da_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_fwd": (_i, [_vp] * 8 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "sky_da_strip_weight_bytes": (_sz, [_vp, _i, _i, _i, _i, _i, _i]),
+    "sky_da_strip_pack_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sky_da_conv2d_fwd_strip": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "sky_da_strip_plan_info": (_i, [_vp, _i, _i, _i, _vp]),
+    "sky_da_strip_plan_export": (_i, [_vp, _i, _i, _i] + [_vp] * 5),
+    "sky_conv_strip_plan_info": (_i, [_i] * 9 + [_vp]),
+    "sky_conv_strip_plan_export": (_i, [_i] * 9 + [_vp] * 3),
     "sky_conv2d_fwd": (_i, [_vp] * 6 + [_i] * 8 + [_f, _i, _vp]),
     "sky_conv2d_smallc_fwd": (_i, [_vp] * 5 + [_i] * 7 + [_f, _vp]),
     "sky_da_conv2d_smallc_fwd": (_i, [_vp] * 7 + [_i] * 7 + [_f, _vp]),
@@ -110,11 +118,13 @@ def load():
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
 LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
-                     "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_last_error": 0, "sky_version": 0,
+                     "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_da_strip_weight_bytes": 0, "sky_da_strip_plan_info": 0, "sky_da_strip_plan_export": 0,
+                     "sky_conv_strip_plan_info": 0, "sky_conv_strip_plan_export": 0, "sky_last_error": 0, "sky_version": 0,
                      "sky_debug_band_trace": 0}
 
 
-_UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host")
+_UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host", "sky_da_strip_weight_bytes",
+             "sky_da_strip_plan_info", "sky_da_strip_plan_export", "sky_conv_strip_plan_info", "sky_conv_strip_plan_export")
 
 
 class _Lib:

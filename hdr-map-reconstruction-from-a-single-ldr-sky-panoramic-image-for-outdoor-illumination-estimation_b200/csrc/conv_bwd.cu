@@ -12,7 +12,7 @@
 //                    tile) into a 2-3 stage mbarrier ring, one thread issues tcgen05.mma (M = 128 kernel rows, N = filters, K = 8
 //                    pixels) into a TMEM accumulator that stays resident over the CTA's pixel partition, 4 warps drain it with vector
 //                    reductions.  Sampler: plain (stride 1 / 2, TensorFlow SAME) or the distortion-aware geometry (da_sample).
-#include "da_conv.cuh"
+#include "strip_conv.cuh"
 
 namespace sky {
 
@@ -443,7 +443,7 @@ extern "C" int sky_conv2d_bwd_data(const float *dy, const void *packed_t, float 
     SKY_REQUIRE(dy && packed_t && dx, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension");
     SKY_REQUIRE(k >= 1 && k <= 15 && (stride == 1 || stride == 2), SKY_ERR_UNSUPPORTED, "kernel size %d / stride %d not supported", k, stride);
-    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_MASK | SKY_EPI_RESIDUAL)), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK or SKY_EPI_RESIDUAL only");
+    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_MASK | SKY_EPI_RESIDUAL | SKY_EPI_FORCE_DIRECT)), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK or SKY_EPI_RESIDUAL only");
     SKY_REQUIRE((epilogue_flags & (SKY_EPI_MASK | SKY_EPI_RESIDUAL)) != (SKY_EPI_MASK | SKY_EPI_RESIDUAL), SKY_ERR_INVALID,
                 "SKY_EPI_MASK and SKY_EPI_RESIDUAL share the aux tensor");
     SKY_REQUIRE(!(epilogue_flags & (SKY_EPI_MASK | SKY_EPI_RESIDUAL)) || aux, SKY_ERR_INVALID, "SKY_EPI_MASK / SKY_EPI_RESIDUAL without the aux tensor");
@@ -459,9 +459,14 @@ extern "C" int sky_conv2d_bwd_data(const float *dy, const void *packed_t, float 
     SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
     SKY_REQUIRE((long)B * h * w * (long)(C > F ? C : F) < (1L << 31), SKY_ERR_UNSUPPORTED, "tensor exceeds 2^31 elements");
     a.transposed = 1; a.out_h = h; a.out_w = w; a.tp_ph0 = k - 1 - ph0; a.tp_pw0 = k - 1 - pw0;
-    if (C <= 256) return launch_fwd_direct(a);
-    SKY_REQUIRE(C % 256 == 0, SKY_ERR_UNSUPPORTED, "data gradient: more than 256 input channels must come in multiples of 256 (got %d)", C);
-    a.F = 256; a.ldF = C; a.nslices = C / 256;
+    if (C > 256) {
+        SKY_REQUIRE(C % 256 == 0, SKY_ERR_UNSUPPORTED, "data gradient: more than 256 input channels must come in multiples of 256 (got %d)", C);
+        a.F = 256; a.ldF = C; a.nslices = C / 256;
+    }
+    if (!(epilogue_flags & SKY_EPI_FORCE_DIRECT)) {
+        int rc = launch_fwd_strip_plain(a);        // row strips over dy (stride 2: one row class per output column parity)
+        if (rc != SKY_ERR_UNSUPPORTED) return rc;
+    }
     return launch_fwd_direct(a);
 }
 

@@ -8,7 +8,7 @@
 //                           the bias (+ LeakyReLU / residual) and store NHWC.
 //   sky_da_conv2d_fwd_simt  fp32 CUDA-core restatement of the same contract (cross-check, odd shapes)
 //   sky_resize_bilinear_fwd TF2 half-pixel bilinear resize (deconv2d.call :322)
-#include "da_conv.cuh"
+#include "strip_conv.cuh"
 
 namespace sky {
 
@@ -676,14 +676,20 @@ static int conv2d_plain(FwdArgs a, int stride)
     }
     if (F <= 256) {
         if ((a.C % BLOCK_K) == 0 && !(a.flags & SKY_EPI_FORCE_DIRECT)) {
-            int rc = launch_fwd_band(a);        // identity sampler in the band-staged kernel (any stride the band fits)
+            int rc = (a.flags & SKY_EPI_FORCE_BAND) ? SKY_ERR_UNSUPPORTED : launch_fwd_strip_plain(a);   // row strips: k strips instead of k*k im2col tiles
+            if (rc != SKY_ERR_UNSUPPORTED) return rc;
+            rc = launch_fwd_band(a);            // identity sampler in the band-staged kernel (any stride the band fits)
             if (rc != SKY_ERR_UNSUPPORTED) return rc;
         }
         return launch_fwd_direct(a);
     }
-    if (F % 256 == 0) {          // equal slices: one launch, slices in blockIdx.z
+    if (F % 256 == 0) {          // equal slices: one launch, slices in blockIdx.z / blockIdx.y
         FwdArgs b = a;
         b.F = 256; b.ldF = F; b.nslices = F / 256;
+        if ((a.C % BLOCK_K) == 0 && !(a.flags & (SKY_EPI_FORCE_DIRECT | SKY_EPI_FORCE_BAND))) {
+            int rc = launch_fwd_strip_plain(b);
+            if (rc != SKY_ERR_UNSUPPORTED) return rc;
+        }
         return launch_fwd_direct(b);
     }
     const uint8_t *packed = (const uint8_t *)a.packed;

@@ -120,7 +120,10 @@ def test_conv_forward_vs_oracle(pkg, ops, B, h, w, C, F, k):
         got = layer(xd).cpu().numpy()
         assert np.isfinite(got).all()
         assert rel_l2(got, want) <= tol, (mode, rel_l2(got, want))
-        # the direct-gather kernel (no smem band) must agree with the band-staged one
+        # the default is the row-strip kernel where it applies (C % 32 == 0); the band-staged producer kernel of round 1 and the
+        # direct-gather kernel (no smem band) must agree with it
+        band = layer(xd, kernel_path="band").cpu().numpy()
+        assert rel_l2(band, want) <= tol, (mode, "band", rel_l2(band, want))
         direct = layer(xd, force_direct=True).cpu().numpy()
         assert rel_l2(direct, want) <= tol, (mode, "direct", rel_l2(direct, want))
         # fused instance-norm moments: sum and sum of squares of y per (sample, filter)

@@ -1,0 +1,185 @@
+"""Row-strip plans (csrc/strip_plan.cu) checked on the CPU: the host tables the library builds are exported through the C ABI and the
+strip formulation  y[i, j] = sum over strips, windows of  V[j + shift] . Weff  is evaluated in numpy (fp64) from them, then compared
+with the oracle's materialised pad -> gather -> blend -> matmul dataflow (distortion_aware_ops.py:50-123) and with a direct SAME
+convolution / its data gradient for the plain plans.  No device is needed: plans are built from the host copy of the offset table."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import da_oracle as O
+
+ROW = np.dtype([("out_row", "i4"), ("oc0", "i4"), ("sb", "i4"), ("se", "i4")])
+STRIP = np.dtype([("kind", "i4"), ("r0", "i4"), ("r1", "i4"), ("wy0", "f4"), ("wy1", "f4"), ("u0", "i4"), ("cm", "i4"), ("c0", "i4"),
+                  ("wb", "i4"), ("we", "i4")])
+WIN = np.dtype([("start_row", "i4"), ("wtile0", "i4")])
+TERM = np.dtype([("tap", "i4"), ("coef", "f4")])
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def da_plan(pkg, off, h, w, k):
+    lib, chk = pkg._lib.LIB, pkg._lib.check
+    info = np.zeros(8, np.int32)
+    chk(lib.sky_da_strip_plan_info(_vp(off), h, w, k, _vp(info)))
+    nr, ns, nw, nt = (int(v) for v in info[:4])
+    rows, strips, wins = np.zeros(nr, ROW), np.zeros(ns, STRIP), np.zeros(nw, WIN)
+    tb, terms = np.zeros(nw + 1, np.int32), np.zeros(max(nt, 1), TERM)
+    chk(lib.sky_da_strip_plan_export(_vp(off), h, w, k, _vp(rows), _vp(strips), _vp(wins), _vp(tb), _vp(terms)))
+    return info, rows, strips, wins, tb, terms
+
+
+def map_col(q, in_w, pw0, W):
+    """da_map_col of strip_conv.cu."""
+    if q < 0:
+        q += in_w
+    elif q > in_w - 1:
+        q -= in_w
+    if q < 0:
+        q += in_w
+    if q > in_w - 1:
+        q -= in_w
+    c = q - pw0
+    return c if 0 <= c < W else -1
+
+
+def emulate_da(x, kern, bias, off, k, plan):
+    info, rows, strips, wins, tb, terms = plan
+    B, h, w, C = x.shape
+    F = kern.shape[1]
+    NB = int(info[6])
+    (ph0, _), (pw0, pwt) = O.pad_amounts(h, k), (O.pad_amounts(w, k)[0], sum(O.pad_amounts(w, k)))
+    in_w = w + pwt
+    x64, k64 = x.astype(np.float64), kern.astype(np.float64).reshape(k * k, C, F)
+    y = np.zeros((B, h, w, F))
+    samp = O.sample(h, w, k, off)
+    for rp in rows:
+        i = int(rp["out_row"])
+        for sd in strips[rp["sb"]:rp["se"]]:
+            for wi in range(sd["wb"], sd["we"]):
+                weff = sum(float(t["coef"]) * k64[t["tap"]] for t in terms[tb[wi]:tb[wi + 1]])       # [C, F]
+                if sd["kind"] == 1:
+                    t = int(sd["r0"])           # exact tap: the oracle's own corners / weights per pixel
+                    assert terms[tb[wi]]["tap"] == t and tb[wi + 1] - tb[wi] == 1
+                    for j in range(w):
+                        pix = np.zeros((B, C))
+                        for (yn, xn, wn) in (("y0", "x0", "w0"), ("y0", "x1", "w1"), ("y1", "x0", "w2"), ("y1", "x1", "w3")):
+                            r, c = samp[yn][i, j, t] - ph0, samp[xn][i, j, t] - pw0
+                            if 0 <= r < h and 0 <= c < w:
+                                pix += float(samp[wn][i, j, t]) * x64[:, r, c, :]
+                        y[:, i, j, :] += pix @ weff
+                    continue
+                assert wins[wi]["start_row"] % NB == 0
+                shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // NB
+                for j in range(w):
+                    c = map_col(int(sd["cm"]) * (j + shift) + int(sd["c0"]) + pw0, in_w, pw0, w)
+                    if c < 0:
+                        continue
+                    v = np.zeros((B, C))
+                    if sd["r0"] >= 0:
+                        v += float(sd["wy0"]) * x64[:, sd["r0"], c, :]
+                    if sd["r1"] >= 0:
+                        v += float(sd["wy1"]) * x64[:, sd["r1"], c, :]
+                    y[:, i, j, :] += v @ weff
+    return y + bias.astype(np.float64)
+
+
+@pytest.mark.parametrize("h,w,k", [(8, 32, 3), (16, 64, 3), (32, 128, 7), (4, 16, 3), (16, 64, 5)])
+def test_da_strip_plan_reproduces_the_layer(pkg, h, w, k):
+    rng = np.random.default_rng(h * 1000 + w + k)
+    B, C, F = 2, 4, 5
+    off = O.offsets(h, w, k)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    kern = rng.standard_normal((k * k * C, F)).astype(np.float32)
+    bias = rng.standard_normal(F).astype(np.float32)
+    plan = da_plan(pkg, off, h, w, k)
+    info = plan[0]
+    assert info[0] == h and info[5] * info[6] == 128 and info[7] <= 192 and info[7] % 8 == 0
+    want = O.conv2d_forward(x, kern, bias, k, acc_dtype=torch.float64).numpy()
+    got = emulate_da(x, kern, bias, off, k, plan)
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    # the only deviation: a row's horizontal factors are the exact fraction of b + x_off, the reference's are fp32 per pixel (j + b + x_off
+    # rounded): a few ulp of the coordinate
+    assert rel <= 2e-5, (rel, info)
+    # every window starts inside the strip the kernel allocates
+    _, rows, strips, wins, tb, terms = plan
+    assert int(wins["start_row"].max()) + 128 <= int(info[7])
+
+
+def test_da_strip_plan_statistics(pkg):
+    """The trunk geometry (8x32, k=3): k strips per row except at the zenith, (2k-1) windows per strip at most."""
+    off = O.offsets(8, 32, 3)
+    info, rows, strips, wins, tb, terms = da_plan(pkg, off, 8, 32, 3)
+    per_row = [int(r["se"] - r["sb"]) for r in rows]
+    wins_per_row = [int(sum(s["we"] - s["wb"] for s in strips[r["sb"]:r["se"]])) for r in rows]
+    print("strips per row", per_row, "windows per row", wins_per_row, "exact strips", int(info[4]), "SR", int(info[7]))
+    assert max(wins_per_row[2:]) <= 3 * 5
+    assert int(info[4]) <= 9        # exact taps, if any, only on the zenith row
+
+
+def conv_plan(pkg, h, w, k, stride, transposed, oh, ow, ph0, pw0):
+    lib, chk = pkg._lib.LIB, pkg._lib.check
+    info = np.zeros(8, np.int32)
+    chk(lib.sky_conv_strip_plan_info(h, w, k, stride, transposed, oh, ow, ph0, pw0, _vp(info)))
+    rows, strips, wins = np.zeros(int(info[0]), ROW), np.zeros(int(info[1]), STRIP), np.zeros(int(info[2]), WIN)
+    chk(lib.sky_conv_strip_plan_export(h, w, k, stride, transposed, oh, ow, ph0, pw0, _vp(rows), _vp(strips), _vp(wins)))
+    return info, rows, strips, wins
+
+
+def emulate_plain(x, taps, plan, OH, OW, ocs):
+    """x [B,h,w,C]; taps [k*k, C, F] (the weight tile of tap t); returns [B,OH,OW,F]."""
+    info, rows, strips, wins = plan
+    B, h, w, C = x.shape
+    NB = int(info[6])
+    y = np.zeros((B, OH, OW, taps.shape[2]))
+    ncols = OW // ocs
+    for rp in rows:
+        for sd in strips[rp["sb"]:rp["se"]]:
+            assert sd["kind"] == 0 and sd["r1"] < 0 and sd["wy0"] == 1.0
+            for wi in range(sd["wb"], sd["we"]):
+                shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // NB
+                for jj in range(ncols):
+                    c = int(sd["cm"]) * (jj + shift) + int(sd["c0"])
+                    if 0 <= c < w:
+                        y[:, rp["out_row"], rp["oc0"] + ocs * jj, :] += x[:, sd["r0"], c, :] @ taps[wins[wi]["wtile0"]]
+    return y
+
+
+@pytest.mark.parametrize("h,w,k,stride", [(8, 32, 3, 1), (16, 16, 3, 2), (8, 32, 4, 2), (4, 16, 4, 1), (32, 128, 7, 1), (5, 12, 3, 2)])
+def test_plain_strip_plan_forward(pkg, h, w, k, stride):
+    rng = np.random.default_rng(k * 100 + stride)
+    B, C, F = 2, 3, 4
+    x = rng.standard_normal((B, h, w, C))
+    wt = rng.standard_normal((k, k, C, F))
+    oh, ow = -(-h // stride), -(-w // stride)
+    plan = conv_plan(pkg, h, w, k, stride, 0, oh, ow, 0, 0)
+    got = emulate_plain(x, wt.reshape(k * k, C, F), plan, oh, ow, 1)
+    th, tw = max((oh - 1) * stride + k - h, 0), max((ow - 1) * stride + k - w, 0)          # TensorFlow SAME: the smaller half in front
+    xp = torch.nn.functional.pad(torch.from_numpy(x).permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2))
+    want = torch.nn.functional.conv2d(xp, torch.from_numpy(wt).permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1).numpy()
+    assert np.allclose(got, want, atol=1e-10)
+
+
+@pytest.mark.parametrize("h,w,k,stride", [(8, 32, 4, 2), (16, 16, 3, 2), (8, 16, 4, 1), (6, 12, 4, 2)])
+def test_plain_strip_plan_data_gradient(pkg, h, w, k, stride):
+    """dx of a SAME conv run as a forward pass over dy with the flipped, transposed kernel (the convention of sky_conv2d_bwd_data)."""
+    rng = np.random.default_rng(k * 10 + stride)
+    B, C, F = 2, 3, 4
+    oh, ow = -(-h // stride), -(-w // stride)
+    th, tw = max((oh - 1) * stride + k - h, 0), max((ow - 1) * stride + k - w, 0)
+    ph0, pw0 = th // 2, tw // 2
+    xt = torch.from_numpy(rng.standard_normal((B, h, w, C))).requires_grad_(True)
+    wt = rng.standard_normal((k, k, C, F))
+    xp = torch.nn.functional.pad(xt.permute(0, 3, 1, 2), (pw0, tw - pw0, ph0, th - ph0))
+    y = torch.nn.functional.conv2d(xp, torch.from_numpy(wt).permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+    dy = rng.standard_normal(tuple(y.shape))
+    y.backward(torch.from_numpy(dy))
+    want = xt.grad.numpy()
+    # tap (a, b) of the transposed pass multiplies dy by kernel[k-1-a, k-1-b]^T (sky_conv2d_transpose_weights)
+    taps = np.stack([wt[k - 1 - a, k - 1 - b].T for a in range(k) for b in range(k)])      # [k*k, F, C]
+    plan = conv_plan(pkg, oh, ow, k, stride, 1, h, w, k - 1 - ph0, k - 1 - pw0)
+    got = emulate_plain(dy, taps, plan, h, w, 2 if stride == 2 else 1)
+    assert np.allclose(got, want, atol=1e-10)
