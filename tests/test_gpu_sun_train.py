@@ -95,11 +95,16 @@ def test_smallc_weight_gradient(pkg):
     assert rel(db.cpu().numpy(), want_db) < 1e-5
 
 
-@pytest.mark.parametrize("mode,tol_fc,tol_conv", [("tf32", 8e-2, 1.5e-1), ("3xtf32", 1e-3, 5e-3)])
-def test_sun_train_step_vs_autograd(pkg, mode, tol_fc, tol_conv):
-    """With `3xtf32` forward convs the activations agree with the oracle to 1e-5, no ReLU mask / arg-max flips occur, and what remains
-    is the TF32 rounding of the backward convs; with TF32 forward convs a handful of flipped units adds several percent (measured:
+@pytest.mark.parametrize("mode,fwd_kernel,tol_fc,tol_conv", [("tf32", "strip", 8e-2, 1.5e-1), ("3xtf32", "band", 1e-3, 5e-3),
+                                                             ("3xtf32", "strip", 1e-3, 5e-2)])
+def test_sun_train_step_vs_autograd(pkg, monkeypatch, mode, fwd_kernel, tol_fc, tol_conv):
+    """With `3xtf32` forward convs on the band-staged kernel the activations agree with the oracle to ~1e-6, no ReLU mask / arg-max flips
+    occur, and what remains is the TF32 rounding of the backward convs (every backward kernel proven to <= 5e-3 end to end).  The
+    row-strip forward kernel agrees to ~7e-6 per layer in `3xtf32` (more accumulation steps in TMEM): 2 of 65536 ReLU units of sunlayer3
+    flip against the oracle, which moves the gradients below them by ~1.4e-2 (tools/dbg_strip_layer3.py) — a property of the
+    discontinuity, the same backward kernels run.  With TF32 forward convs a handful of flipped units adds several percent (measured:
     fc2 1e-3, fc1 5e-2, convs 7-12e-2)."""
+    monkeypatch.setattr(pkg.distortion_aware_ops, "DA_FORWARD_KERNEL", fwd_kernel)
     rng = np.random.default_rng(2)
     B, H, W = 2, 32, 128
     ldr = (np.round(255 * rng.uniform(0, 1, (B, H, W, 3))) / 255).astype(np.float32)
@@ -126,7 +131,7 @@ def test_sun_train_step_vs_autograd(pkg, mode, tol_fc, tol_conv):
             report[f"{name}.norm{i}.beta"] = rel(tr._g(norm, "beta").cpu().numpy(), want[name][f"norm{i}_beta"].numpy())
     import json, os
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump({k: round(v, 5) for k, v in report.items()}, open(f"gpurun_out/sun_train_grad_report_{mode}.json", "w"), indent=1)
+    json.dump({k: round(v, 5) for k, v in report.items()}, open(f"gpurun_out/sun_train_grad_report_{mode}_{fwd_kernel}.json", "w"), indent=1)
     for k, v in report.items():
         if k.endswith(".bias") and "conv" in k:
             continue      # a conv bias in front of an instance norm has an exactly-zero gradient: only noise on both sides

@@ -149,7 +149,7 @@ def test_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k, s):
 
 @pytest.mark.parametrize("C,F,k", [(128, 128, 3), (32, 32, 7), (64, 64, 3)])
 def test_da_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k):
-    """The distortion-aware layer (band-staged forward, scatter data gradient, pipelined weight gradient) against the materialised
+    """The distortion-aware layer (band-staged and row-strip forward, scatter data gradient, pipelined weight gradient) against the materialised
     oracle with TF32-rounded contraction operands.  The forward kernel blends separably (dy * (dx * .)), the oracle in the reference's
     four-product order: the blended pixel differs in its last fp32 bit, which re-draws a TF32 rounding now and then (bar 1e-4)."""
     B, h, w = 2, 16, 64
@@ -164,8 +164,17 @@ def test_da_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k):
         y.backward(T(dy).double())
     layer = pkg.conv2d(F, kernel_size=k, kernel_initializer=kern, bias_initializer=bias)
     xd, dyd = T(x).cuda(), T(dy).cuda()
-    got = layer(xd)
+    got = layer(xd, kernel_path="band")
     assert rel(got.cpu().numpy(), y.detach().numpy()) < 1e-4, rel(got.cpu().numpy(), y.detach().numpy())
+    # The row-strip kernel (the default forward) rounds different operands to TF32 — the vertically blended row and the tap's weights
+    # times the horizontal factor, instead of the fully blended pixel and the bare weights — so against THIS oracle it agrees to TF32
+    # rounding only; its own operand rounding is emulated from the exported plan and must be met to fp32 accumulation error.
+    import test_strip_plan as SP
+    got_s = layer(xd).cpu().numpy()
+    assert rel(got_s, y.detach().numpy()) < 6e-4, rel(got_s, y.detach().numpy())
+    off = O.offsets(h, w, k)
+    emu = SP.emulate_da(x, kern, bias, off, k, SP.da_plan(pkg, off, h, w, k), rnd=lambda a: tf32_emu.round_tf32(T(a)).numpy())
+    assert rel(got_s, emu) < 2e-5, rel(got_s, emu)
     dx, dk, db = pkg.distortion_aware_ops.conv2d_backward(layer, xd, dyd)
     assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 1e-4, rel(dx.cpu().numpy(), xt.grad.numpy())
     assert rel(dk.cpu().numpy(), kt.grad.numpy()) < 1e-4, rel(dk.cpu().numpy(), kt.grad.numpy())
@@ -391,7 +400,12 @@ def _zero_grad_bias(name):
                                                                                    ("conv1_d", "conv2_d", "conv3_d", "conv3_f", "conv2_f", "conv3_u", "conv2_u"))
 
 
-@pytest.mark.parametrize("mode,emulate,tol_loss,tol_y,tol_grad", [("3xtf32", False, 2e-3, 1e-3, 5e-2), ("tf32", True, 5e-3, 5e-3, 1e-1),
+# The gradient bars are set by discontinuities, not by kernel error: one ReLU mask or max-pool arg-max that differs from the oracle's moves
+# the gradients of an 8x32 instance-norm plane by percents (tools/dbg_strip_layer3.py: 2 flipped units of 65536 -> 6e-3 on the layer).
+# The per-kernel tests above pin every backward kernel to <= 1e-4 against the TF32-emulating oracle.  The distortion-aware forward
+# (row-strip kernel) rounds other operands to TF32 than the emulating oracle does (the vertically blended row and factor-scaled
+# weights instead of the blended pixel), so the `tf32 vs TF32 oracle` row is no longer flip-free: 1.5e-1 (measured 1.0e-1).
+@pytest.mark.parametrize("mode,emulate,tol_loss,tol_y,tol_grad", [("3xtf32", False, 2e-3, 1e-3, 5e-2), ("tf32", True, 5e-3, 5e-3, 1.5e-1),
                                                                   ("tf32", False, 2e-2, 1e-2, 3e-1)])
 def test_train_step_vs_autograd(pkg, mode, emulate, tol_loss, tol_y, tol_grad):
     B, H, W = 2, 32, 128

@@ -46,44 +46,50 @@ def map_col(q, in_w, pw0, W):
     return c if 0 <= c < W else -1
 
 
-def emulate_da(x, kern, bias, off, k, plan):
+def emulate_da(x, kern, bias, off, k, plan, rnd=None):
+    """The kernel's arithmetic from the exported plan: strips V = wy0 * x[r0] + wy1 * x[r1] (fp32, like the producer warps), effective
+    weights sum coef * kernel[tap] (fp32, like strip_weff_pack_kernel), both passed through `rnd` (None: exact; tf32_emu.round_tf32: the
+    TF32 operand rounding), contraction accumulated in fp64."""
     info, rows, strips, wins, tb, terms = plan
     B, h, w, C = x.shape
     F = kern.shape[1]
     NB = int(info[6])
-    (ph0, _), (pw0, pwt) = O.pad_amounts(h, k), (O.pad_amounts(w, k)[0], sum(O.pad_amounts(w, k)))
-    in_w = w + pwt
-    x64, k64 = x.astype(np.float64), kern.astype(np.float64).reshape(k * k, C, F)
+    (ph0, _), pw = O.pad_amounts(h, k), O.pad_amounts(w, k)
+    pw0, in_w = pw[0], w + sum(pw)
+    f32 = np.float32
+    rnd = rnd or (lambda a: a)
+    x32, k32 = x.astype(f32), kern.astype(f32).reshape(k * k, C, F)
     y = np.zeros((B, h, w, F))
     samp = O.sample(h, w, k, off)
+    jj = np.arange(w)
     for rp in rows:
         i = int(rp["out_row"])
         for sd in strips[rp["sb"]:rp["se"]]:
+            v = None
+            if sd["kind"] == 0:
+                v0 = x32[:, sd["r0"]] if sd["r0"] >= 0 else np.zeros((B, w, C), f32)
+                v1 = x32[:, sd["r1"]] if sd["r1"] >= 0 else np.zeros((B, w, C), f32)
+                v = rnd((f32(sd["wy1"]) * v1 + (f32(sd["wy0"]) * v0).astype(f32)).astype(f32)).astype(np.float64)    # [B, w, C]
             for wi in range(sd["wb"], sd["we"]):
-                weff = sum(float(t["coef"]) * k64[t["tap"]] for t in terms[tb[wi]:tb[wi + 1]])       # [C, F]
+                weff = np.zeros((C, F), f32)
+                for t in terms[tb[wi]:tb[wi + 1]]:
+                    weff = (f32(t["coef"]) * k32[t["tap"]] + weff).astype(f32)
+                weff = rnd(weff).astype(np.float64)
                 if sd["kind"] == 1:
                     t = int(sd["r0"])           # exact tap: the oracle's own corners / weights per pixel
                     assert terms[tb[wi]]["tap"] == t and tb[wi + 1] - tb[wi] == 1
-                    for j in range(w):
-                        pix = np.zeros((B, C))
-                        for (yn, xn, wn) in (("y0", "x0", "w0"), ("y0", "x1", "w1"), ("y1", "x0", "w2"), ("y1", "x1", "w3")):
-                            r, c = samp[yn][i, j, t] - ph0, samp[xn][i, j, t] - pw0
-                            if 0 <= r < h and 0 <= c < w:
-                                pix += float(samp[wn][i, j, t]) * x64[:, r, c, :]
-                        y[:, i, j, :] += pix @ weff
+                    pix = np.zeros((B, w, C), f32)
+                    for (yn, xn, wn) in (("y0", "x0", "w0"), ("y0", "x1", "w1"), ("y1", "x0", "w2"), ("y1", "x1", "w3")):
+                        r, c = samp[yn][i, :, t] - ph0, samp[xn][i, :, t] - pw0
+                        ok = (r >= 0) & (r < h) & (c >= 0) & (c < w)
+                        pix[:, ok] += samp[wn][i, ok, t][None, :, None] * x32[:, r[ok], c[ok]]
+                    y[:, i] += rnd(pix).astype(np.float64) @ weff
                     continue
                 assert wins[wi]["start_row"] % NB == 0
                 shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // NB
-                for j in range(w):
-                    c = map_col(int(sd["cm"]) * (j + shift) + int(sd["c0"]) + pw0, in_w, pw0, w)
-                    if c < 0:
-                        continue
-                    v = np.zeros((B, C))
-                    if sd["r0"] >= 0:
-                        v += float(sd["wy0"]) * x64[:, sd["r0"], c, :]
-                    if sd["r1"] >= 0:
-                        v += float(sd["wy1"]) * x64[:, sd["r1"], c, :]
-                    y[:, i, j, :] += v @ weff
+                cols = np.array([map_col(int(sd["cm"]) * (j + shift) + int(sd["c0"]) + pw0, in_w, pw0, w) for j in jj])
+                ok = cols >= 0
+                y[:, i, ok] += v[:, cols[ok]] @ weff
     return y + bias.astype(np.float64)
 
 
