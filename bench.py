@@ -387,6 +387,8 @@ def conv_work(name, a):
         return -(-n // s)
     if name == "sky_da_conv2d_fwd":
         B, h, w, Ci, F, k = a[8:14]; s = 1; kind = "da fwd"
+    elif name == "sky_da_conv2d_fwd_strip":
+        B, h, w, Ci, F, k = a[7:13]; s = 1; kind = "da fwd"
     elif name == "sky_conv2d_fwd":
         B, h, w, Ci, F, k, s = a[6:13]; kind = "conv fwd"
     elif name == "sky_conv2d_fwd_blend":
@@ -397,6 +399,8 @@ def conv_work(name, a):
         B, h, w, Ci, F, k = a[7:13]; s = 1; kind = "small-C da fwd"
     elif name == "sky_da_conv2d_bwd_data":
         B, h, w, Ci, F, k = a[4:10]; s = 1; kind = "da dgrad"
+    elif name == "sky_da_conv2d_bwd_data_strip":
+        B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "da dgrad"
     elif name == "sky_da_conv2d_bwd_filter":
         B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "da wgrad"
     elif name == "sky_da_conv2d_smallc_bwd_filter":

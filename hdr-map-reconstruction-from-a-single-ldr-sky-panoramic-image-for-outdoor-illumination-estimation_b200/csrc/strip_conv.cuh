@@ -62,7 +62,8 @@ struct StripPlan {                 // host view of a cached plan; the arrays liv
 
 // plans are built once per layer geometry and cached for the life of the process (host tables + device copies)
 // (device = false: host tables only — plan statistics / export without a GPU)
-int get_plan_da(const float *offsets_host, int h, int w, int k, const StripPlan **out, bool device = true);
+// transposed: the data-gradient plan (strips over dy rows, merged transposed effective weights)
+int get_plan_da(const float *offsets_host, int h, int w, int k, const StripPlan **out, bool device = true, bool transposed = false);
 int get_plan_plain(int h, int w, int k, int stride, int transposed, int out_h, int out_w, int tp_ph0, int tp_pw0, const StripPlan **out,
                    bool device = true);
 

@@ -162,59 +162,93 @@ int ensure_device(HostPlan &hp)
     return SKY_OK;
 }
 
-int build_da(const float *off, int h, int w, int k, HostPlan &hp)
+// One kernel row of one output row: the vertical geometry (shared by its k taps) and the horizontal terms by column shift.
+struct KernelRow {
+    bool have_ref = false;
+    HostSample ref{};
+    std::map<int, std::vector<WeffTerm>> by_shift;      // unpadded, unwrapped column shift -> (tap, horizontal factor)
+    std::vector<int> exact_taps;                         // taps that do not reduce to one shift for the whole row
+};
+
+// `relaxed`: a tap whose strict check fails is still folded when, at every column, the two-corner stencil of the reference arithmetic
+// and the row's stencil agree as (column -> weight) maps to 2e-5 — the fraction of b + x_off sits within an ulp of an integer, so the
+// reference's floor depends on j while the weights of the PHYSICAL columns do not (used by the data-gradient plan, whose TF32 operands
+// are three orders of magnitude coarser).
+int analyse_kernel_row(const float *off, int h, int w, int k, int i, int a, bool relaxed, KernelRow &kr)
 {
     const int k2 = k * k;
     int ph0, pht, pw0, pwt;
     pad_axis(h, k, &ph0, &pht);
     pad_axis(w, k, &pw0, &pwt);
     const int in_h = h + pht, in_w = w + pwt;
+    const float tol = 8.f * (float)in_w * 1.1920929e-7f;      // a few ulp of the coordinate j + b + x_off
+    for (int b = 0; b < k; ++b) {
+        const int t = a * k + b;
+        const float yo = off[((size_t)i * k2 + t) * 2 + 0], xo = off[((size_t)i * k2 + t) * 2 + 1];
+        if (!(yo == yo) || !(xo == xo)) return SKY_ERR_UNSUPPORTED;        // NaN table: the caller's other path reports it
+        const HostSample s0 = host_sample(i, 0, a, b, yo, xo, in_h, in_w);
+        bool regular = true;
+        if (!kr.have_ref) { kr.ref = s0; kr.have_ref = true; }
+        else if (s0.y0 != kr.ref.y0 || s0.y1 != kr.ref.y1 || s0.dy1 != kr.ref.dy1 || s0.dy0 != kr.ref.dy0) regular = false;
+        const double xs = (double)b + (double)xo;                            // x - j in the padded frame
+        if (!(fabs(xs) < 1e6)) regular = false;
+        int sq = 0;
+        float dx1r = 1.f, dx0r = 0.f;
+        if (regular) {
+            const double fl = floor(xs);
+            sq = (int)fl;
+            dx0r = (float)(xs - fl);
+            dx1r = (float)(1.0 - (xs - fl));
+            bool strict = true, loose = true;
+            for (int j = 0; j < w && (strict || (relaxed && loose)); ++j) {
+                const HostSample s = host_sample(i, j, a, b, yo, xo, in_h, in_w);
+                const int e0 = host_map_col(j + sq, in_w, pw0, w), e1 = host_map_col(j + sq + 1, in_w, pw0, w);
+                const int g0 = (s.x0 - pw0 >= 0 && s.x0 - pw0 < w) ? s.x0 - pw0 : -1;
+                const int g1 = (s.x1 - pw0 >= 0 && s.x1 - pw0 < w) ? s.x1 - pw0 : -1;
+                if (fabsf(s.dx1 - dx1r) > tol || fabsf(s.dx0 - dx0r) > tol) strict = false;
+                if (g0 != e0 && !(dx1r == 0.f && s.dx1 == 0.f)) strict = false;
+                if (g1 != e1 && !(dx0r == 0.f && s.dx0 == 0.f)) strict = false;
+                if (s.y0 != kr.ref.y0 || s.y1 != kr.ref.y1) { strict = false; loose = false; }
+                // stencils as column -> weight maps (column -1 = zero halo: its weight is irrelevant)
+                const int cols[4] = { g0, g1, e0, e1 };
+                const float wts[4] = { s.dx1, s.dx0, -dx1r, -dx0r };
+                for (int u = 0; u < 4 && loose; ++u) {
+                    if (cols[u] < 0) continue;
+                    float sum = 0.f;
+                    for (int v = 0; v < 4; ++v)
+                        if (cols[v] == cols[u]) sum += wts[v];
+                    if (fabsf(sum) > 2e-5f) loose = false;
+                }
+            }
+            regular = strict || (relaxed && loose);
+        }
+        if (!regular) { kr.exact_taps.push_back(t); continue; }
+        const int su = sq - pw0;                                              // shift in unpadded, unwrapped columns
+        if (dx1r != 0.f) kr.by_shift[su].push_back(WeffTerm{ t, dx1r });
+        if (dx0r != 0.f) kr.by_shift[su + 1].push_back(WeffTerm{ t, dx0r });
+    }
+    return SKY_OK;
+}
+
+int build_da(const float *off, int h, int w, int k, HostPlan &hp)
+{
+    const int k2 = k * k;
+    int ph0, pht;
+    pad_axis(h, k, &ph0, &pht);
     const int TW = pow2_floor(std::min(w, BLOCK_M)), NB = BLOCK_M / TW;
     const int cap = (SR_MAX - BLOCK_M) / NB;
-    const float tol = 8.f * (float)in_w * 1.1920929e-7f;      // a few ulp of the coordinate j + b + x_off
     int span_max = 0;
     for (int i = 0; i < h; ++i) {
         RowPlan rp;
         rp.out_row = i; rp.oc0 = 0; rp.strip_begin = (int)hp.strips.size();
         std::vector<int> exact_taps;
         for (int a = 0; a < k; ++a) {
-            bool have_ref = false;
-            HostSample ref{};
-            std::map<int, std::vector<WeffTerm>> by_shift;
-            for (int b = 0; b < k; ++b) {
-                const int t = a * k + b;
-                const float yo = off[((size_t)i * k2 + t) * 2 + 0], xo = off[((size_t)i * k2 + t) * 2 + 1];
-                if (!(yo == yo) || !(xo == xo)) return SKY_ERR_UNSUPPORTED;        // NaN table: the caller's other path reports it
-                const HostSample s0 = host_sample(i, 0, a, b, yo, xo, in_h, in_w);
-                bool regular = true;
-                if (!have_ref) { ref = s0; have_ref = true; }
-                else if (s0.y0 != ref.y0 || s0.y1 != ref.y1 || s0.dy1 != ref.dy1 || s0.dy0 != ref.dy0) regular = false;
-                const double xs = (double)b + (double)xo;                            // x - j in the padded frame
-                if (!(fabs(xs) < 1e6)) regular = false;
-                int sq = 0;
-                float dx1r = 1.f, dx0r = 0.f;
-                if (regular) {
-                    const double fl = floor(xs);
-                    sq = (int)fl;
-                    dx0r = (float)(xs - fl);
-                    dx1r = (float)(1.0 - (xs - fl));
-                    for (int j = 0; j < w && regular; ++j) {
-                        const HostSample s = host_sample(i, j, a, b, yo, xo, in_h, in_w);
-                        const int e0 = host_map_col(j + sq, in_w, pw0, w), e1 = host_map_col(j + sq + 1, in_w, pw0, w);
-                        const int g0 = (s.x0 - pw0 >= 0 && s.x0 - pw0 < w) ? s.x0 - pw0 : -1;
-                        const int g1 = (s.x1 - pw0 >= 0 && s.x1 - pw0 < w) ? s.x1 - pw0 : -1;
-                        if (fabsf(s.dx1 - dx1r) > tol || fabsf(s.dx0 - dx0r) > tol) regular = false;
-                        if (g0 != e0 && !(dx1r == 0.f && s.dx1 == 0.f)) regular = false;
-                        if (g1 != e1 && !(dx0r == 0.f && s.dx0 == 0.f)) regular = false;
-                        if (s.y0 != ref.y0 || s.y1 != ref.y1) regular = false;
-                    }
-                }
-                if (!regular) { exact_taps.push_back(t); continue; }
-                const int su = sq - pw0;                                              // shift in unpadded, unwrapped columns
-                if (dx1r != 0.f) by_shift[su].push_back(WeffTerm{ t, dx1r });
-                if (dx0r != 0.f) by_shift[su + 1].push_back(WeffTerm{ t, dx0r });
-            }
-            if (!have_ref || by_shift.empty()) continue;
+            KernelRow kr;
+            const int rc = analyse_kernel_row(off, h, w, k, i, a, false, kr);
+            if (rc != SKY_OK) return rc;
+            exact_taps.insert(exact_taps.end(), kr.exact_taps.begin(), kr.exact_taps.end());
+            if (!kr.have_ref || kr.by_shift.empty()) continue;
+            const HostSample &ref = kr.ref;
             StripDesc proto{};
             proto.kind = 0;
             proto.r0 = (ref.y0 - ph0 >= 0 && ref.y0 - ph0 < h) ? ref.y0 - ph0 : -1;
@@ -224,7 +258,7 @@ int build_da(const float *off, int h, int w, int k, HostPlan &hp)
             const bool row0_dead = proto.r0 < 0 || proto.wy0 == 0.f, row1_dead = proto.r1 < 0 || proto.wy1 == 0.f;
             if (row0_dead && row1_dead) continue;                                     // the blended row is identically zero
             std::vector<ShiftWin> sw;
-            for (auto &kv : by_shift) sw.push_back(ShiftWin{ kv.first, 0, kv.second });
+            for (auto &kv : kr.by_shift) sw.push_back(ShiftWin{ kv.first, 0, kv.second });
             emit_strips(hp, sw, proto, NB, cap, &span_max, true);
         }
         for (int t : exact_taps) {
@@ -238,6 +272,50 @@ int build_da(const float *off, int h, int w, int k, HostPlan &hp)
             hp.wins.push_back(WinDesc{ 0, (int)hp.wins.size() });
             sd.win_end = (int)hp.wins.size();
             hp.strips.push_back(sd);
+        }
+        rp.strip_end = (int)hp.strips.size();
+        hp.rows.push_back(rp);
+    }
+    return finish_plan(hp, TW, NB, span_max, w, 1, 1);
+}
+
+// Data gradient of the distortion-aware layer as a row-strip convolution over dy (the transpose of the forward plan, in gather form):
+// input row r of dx collects, from every forward (output row i, kernel row a) whose blended strip reads r with vertical weight wy, the
+// terms  dy[i, c - s, :] . (wy * Weff_{i,a,s})^T.  Strips = plain dy rows, windows = (i, -s) with all coinciding terms merged into one
+// effective weight, columns through the transposed column map (the unique dy column j with forward_map(j + s) = c).  No atomics.
+int build_da_transposed(const float *off, int h, int w, int k, HostPlan &hp)
+{
+    int ph0, pht;
+    pad_axis(h, k, &ph0, &pht);
+    const int TW = pow2_floor(std::min(w, BLOCK_M)), NB = BLOCK_M / TW;
+    const int cap = (SR_MAX - BLOCK_M) / NB;
+    // per input row r: dy row i -> (transposed shift -> terms)
+    std::vector<std::map<int, std::map<int, std::vector<WeffTerm>>>> acc(h);
+    for (int i = 0; i < h; ++i)
+        for (int a = 0; a < k; ++a) {
+            KernelRow kr;
+            const int rc = analyse_kernel_row(off, h, w, k, i, a, true, kr);
+            if (rc != SKY_OK) return rc;
+            if (!kr.exact_taps.empty()) return SKY_ERR_UNSUPPORTED;                   // the scatter kernel keeps such layers
+            if (!kr.have_ref) continue;
+            const int rr[2] = { kr.ref.y0 - ph0, kr.ref.y1 - ph0 };
+            const float wy[2] = { kr.ref.dy1, kr.ref.dy0 };
+            for (int c = 0; c < 2; ++c) {
+                if (rr[c] < 0 || rr[c] >= h || wy[c] == 0.f) continue;
+                for (auto &kv : kr.by_shift)
+                    for (const WeffTerm &t : kv.second) acc[rr[c]][i][-kv.first].push_back(WeffTerm{ t.tap, t.coef * wy[c] });
+            }
+        }
+    int span_max = 0;
+    for (int r = 0; r < h; ++r) {
+        RowPlan rp;
+        rp.out_row = r; rp.oc0 = 0; rp.strip_begin = (int)hp.strips.size();
+        for (auto &by_i : acc[r]) {
+            StripDesc proto{};
+            proto.kind = 0; proto.r0 = by_i.first; proto.r1 = -1; proto.wy0 = 1.f; proto.wy1 = 0.f; proto.cm = 1; proto.c0 = 0;
+            std::vector<ShiftWin> sw;
+            for (auto &kv : by_i.second) sw.push_back(ShiftWin{ kv.first, 0, kv.second });
+            emit_strips(hp, sw, proto, NB, cap, &span_max, true);
         }
         rp.strip_end = (int)hp.strips.size();
         hp.rows.push_back(rp);
@@ -310,7 +388,7 @@ int build_plain(int h, int w, int k, int stride, int transposed, int OH, int OW,
 }
 
 std::mutex g_mu;
-std::map<std::tuple<int, int, int, unsigned long long>, HostPlan *> g_da;
+std::map<std::tuple<int, int, int, int, unsigned long long>, HostPlan *> g_da;
 std::map<std::tuple<int, int, int, int, int, int, int, int, int>, HostPlan *> g_plain;
 
 unsigned long long fnv1a(const void *p, size_t n)
@@ -333,15 +411,15 @@ static int export_plan(const HostPlan &hp, void *rows, void *strips, void *wins,
     return SKY_OK;
 }
 
-int get_plan_da(const float *offsets_host, int h, int w, int k, const StripPlan **out, bool device)
+int get_plan_da(const float *offsets_host, int h, int w, int k, const StripPlan **out, bool device, bool transposed)
 {
     if (h <= 0 || w <= 0 || k < 3 || !(k & 1)) return SKY_ERR_UNSUPPORTED;
-    const auto key = std::make_tuple(h, w, k, fnv1a(offsets_host, (size_t)h * k * k * 2 * sizeof(float)));
+    const auto key = std::make_tuple(h, w, k, transposed ? 1 : 0, fnv1a(offsets_host, (size_t)h * k * k * 2 * sizeof(float)));
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_da.find(key);
     if (it == g_da.end()) {
         HostPlan *hp = new HostPlan();
-        const int rc = build_da(offsets_host, h, w, k, *hp);
+        const int rc = transposed ? build_da_transposed(offsets_host, h, w, k, *hp) : build_da(offsets_host, h, w, k, *hp);
         if (rc != SKY_OK) { delete hp; return rc; }
         it = g_da.emplace(key, hp).first;
     }
@@ -385,22 +463,22 @@ using namespace sky;
 
 // Plan export for tests and the design notes (host only, no device needed).  info: out8 = rows, strips, windows, terms, exact-tap strips,
 // tile width, panoramas per tile, strip rows.  export: copies the host tables (RowPlan 16 B, StripDesc 40 B, WinDesc 8 B, WeffTerm 8 B).
-extern "C" int sky_da_strip_plan_info(const float *offsets_host, int h, int w, int k, int *out8)
+extern "C" int sky_da_strip_plan_info(const float *offsets_host, int h, int w, int k, int transposed, int *out8)
 {
     SKY_REQUIRE(offsets_host && out8, SKY_ERR_INVALID, "NULL pointer");
     const StripPlan *pl = nullptr;
-    int rc = get_plan_da(offsets_host, h, w, k, &pl, false);
+    int rc = get_plan_da(offsets_host, h, w, k, &pl, false, transposed != 0);
     SKY_REQUIRE(rc == SKY_OK, rc, "no strip plan for h=%d w=%d k=%d", h, w, k);
     plan_info(*pl, out8);
     return SKY_OK;
 }
 
-extern "C" int sky_da_strip_plan_export(const float *offsets_host, int h, int w, int k, void *rows, void *strips, void *wins, int *term_begin,
-                                        void *terms)
+extern "C" int sky_da_strip_plan_export(const float *offsets_host, int h, int w, int k, int transposed, void *rows, void *strips, void *wins,
+                                        int *term_begin, void *terms)
 {
     SKY_REQUIRE(offsets_host, SKY_ERR_INVALID, "NULL pointer");
     const StripPlan *pl = nullptr;
-    int rc = get_plan_da(offsets_host, h, w, k, &pl, false);
+    int rc = get_plan_da(offsets_host, h, w, k, &pl, false, transposed != 0);
     SKY_REQUIRE(rc == SKY_OK, rc, "no strip plan for h=%d w=%d k=%d", h, w, k);
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : g_da)

@@ -37,6 +37,18 @@ def test_backward_vs_oracle(pkg, B, h, w, C, F, k):
     layer.build(x.shape)
     dx, dk, db = pkg.distortion_aware_ops.conv2d_backward(layer, torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda())
     assert rel_l2(dx.cpu().numpy(), want_dx) <= TOL, ("dx", rel_l2(dx.cpu().numpy(), want_dx))
+    # the default data gradient is the row-strip kernel over the transposed plan (gather form, no atomics); the scatter kernel of round 1
+    # must agree, and `accumulate` adds to what dx holds
+    D = pkg.distortion_aware_ops
+    assert D.DA_BACKWARD_KERNEL == "strip" and layer._strip_t is not None
+    import unittest.mock as mock
+    with mock.patch.object(D, "DA_BACKWARD_KERNEL", "scatter"):
+        dx_s = D.conv2d_backward(layer, torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda(), need_dw=False)[0]
+    assert rel_l2(dx_s.cpu().numpy(), want_dx) <= TOL, ("dx scatter", rel_l2(dx_s.cpu().numpy(), want_dx))
+    base = torch.from_numpy(rng.standard_normal(x.shape).astype(np.float32)).cuda()
+    acc = base.clone()
+    D.conv2d_backward(layer, torch.from_numpy(x).cuda(), torch.from_numpy(dy).cuda(), need_dw=False, dx_out=acc, accumulate_dx=True)
+    assert rel_l2((acc - base).cpu().numpy(), want_dx) <= TOL
     assert rel_l2(dk.cpu().numpy(), want_dk) <= TOL, ("dkernel", rel_l2(dk.cpu().numpy(), want_dk))
     assert rel_l2(db.cpu().numpy(), want_db) <= 1e-5, ("dbias", rel_l2(db.cpu().numpy(), want_db))
 

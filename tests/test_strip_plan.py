@@ -21,14 +21,14 @@ def _vp(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def da_plan(pkg, off, h, w, k):
+def da_plan(pkg, off, h, w, k, transposed=0):
     lib, chk = pkg._lib.LIB, pkg._lib.check
     info = np.zeros(8, np.int32)
-    chk(lib.sky_da_strip_plan_info(_vp(off), h, w, k, _vp(info)))
+    chk(lib.sky_da_strip_plan_info(_vp(off), h, w, k, transposed, _vp(info)))
     nr, ns, nw, nt = (int(v) for v in info[:4])
     rows, strips, wins = np.zeros(nr, ROW), np.zeros(ns, STRIP), np.zeros(nw, WIN)
     tb, terms = np.zeros(nw + 1, np.int32), np.zeros(max(nt, 1), TERM)
-    chk(lib.sky_da_strip_plan_export(_vp(off), h, w, k, _vp(rows), _vp(strips), _vp(wins), _vp(tb), _vp(terms)))
+    chk(lib.sky_da_strip_plan_export(_vp(off), h, w, k, transposed, _vp(rows), _vp(strips), _vp(wins), _vp(tb), _vp(terms)))
     return info, rows, strips, wins, tb, terms
 
 
@@ -189,3 +189,62 @@ def test_plain_strip_plan_data_gradient(pkg, h, w, k, stride):
     plan = conv_plan(pkg, oh, ow, k, stride, 1, h, w, k - 1 - ph0, k - 1 - pw0)
     got = emulate_plain(dy, taps, plan, h, w, 2 if stride == 2 else 1)
     assert np.allclose(got, want, atol=1e-10)
+
+
+def map_col_t(q, in_w, W):
+    """da_map_col_t of strip_conv.cu: the unique dy column j = q + m * in_w, |m| <= 2, inside the map."""
+    for m in range(-2, 3):
+        j = q + m * in_w
+        if 0 <= j < W:
+            return j
+    return -1
+
+
+def emulate_da_dgrad(dy, kern, C, off, k, plan, rnd=None):
+    """dx from the transposed plan: strips are dy rows, windows carry the merged transposed effective weights."""
+    info, rows, strips, wins, tb, terms = plan
+    B, h, w, F = dy.shape
+    NB = int(info[6])
+    in_w = w + sum(O.pad_amounts(w, k))
+    f32 = np.float32
+    rnd = rnd or (lambda a: a)
+    k32 = kern.astype(f32).reshape(k * k, C, F)
+    dy_r = rnd(dy.astype(f32)).astype(np.float64)
+    dx = np.zeros((B, h, w, C))
+    for rp in rows:
+        r = int(rp["out_row"])
+        for sd in strips[rp["sb"]:rp["se"]]:
+            assert sd["kind"] == 0 and sd["r1"] < 0 and sd["wy0"] == 1.0 and sd["cm"] == 1 and sd["c0"] == 0
+            for wi in range(sd["wb"], sd["we"]):
+                weff = np.zeros((C, F), f32)
+                for t in terms[tb[wi]:tb[wi + 1]]:
+                    weff = (f32(t["coef"]) * k32[t["tap"]] + weff).astype(f32)
+                weff_t = rnd(weff).astype(np.float64).T                                   # [F, C]
+                shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // NB
+                cols = np.array([map_col_t(c + shift, in_w, w) for c in range(w)])
+                ok = cols >= 0
+                dx[:, r, ok] += dy_r[:, sd["r0"], cols[ok]] @ weff_t
+    return dx
+
+
+@pytest.mark.parametrize("h,w,k", [(8, 32, 3), (16, 64, 3), (32, 128, 7), (4, 16, 3)])
+def test_da_strip_plan_data_gradient(pkg, h, w, k):
+    """The transposed plan against autograd through the oracle's materialised forward (what TF autodiff derives)."""
+    rng = np.random.default_rng(h + w + k)
+    B, C, F = 2, 4, 5
+    off = O.offsets(h, w, k)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    kern = rng.standard_normal((k * k * C, F)).astype(np.float32)
+    bias = np.zeros(F, np.float32)
+    dy = rng.standard_normal((B, h, w, F)).astype(np.float32)
+    want = O.conv2d_backward(x, kern, bias, dy, k, acc_dtype=torch.float64)[0].numpy()
+    plan = da_plan(pkg, off, h, w, k, transposed=1)
+    info = plan[0]
+    assert info[4] == 0 and info[7] <= 192
+    got = emulate_da_dgrad(dy, kern, C, off, k, plan)
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel <= 3e-5, (rel, info)
+    _, rows, strips, wins, tb, terms = plan
+    assert int(wins["start_row"].max()) + 128 <= int(info[7])
+    print("transposed plan", (h, w, k), "windows per row", [int(sum(s["we"] - s["wb"] for s in strips[r["sb"]:r["se"]])) for r in rows][:12],
+          "strips per row", [int(r["se"] - r["sb"]) for r in rows][:12], "SR", int(info[7]))
