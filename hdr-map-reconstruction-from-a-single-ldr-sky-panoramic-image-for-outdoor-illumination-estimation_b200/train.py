@@ -39,8 +39,9 @@ class Step:
     """Owns the models of train.py:183-199 (_gen, _sun, _dis, vgg, vgg2), the two optimizers (:201-202) and runs the step functions."""
 
     def __init__(self, batch_size=32, im_height=IMSHAPE[0], im_width=IMSHAPE[1], *, vgg_data_dict=None, distortion_aware_sunpose=True,
-                 distortion_aware=True, math_mode=None, device="cuda", lr=LEARNING_RATE, rho=0.9, eps=1e-7):
+                 distortion_aware=True, math_mode=None, device="cuda", lr=LEARNING_RATE, rho=0.9, eps=1e-7, concurrent=True):
         kw = dict(math_mode=math_mode, device=device)
+        self.concurrent = bool(concurrent)   # train_step forks its independent parts onto two side streams
         self.H, self.W = im_height, im_width
         self._gen = _generator.model(batch_size=batch_size, im_height=im_height, im_width=im_width, distortion_aware=distortion_aware, **kw)
         self._sun = _sunpose_net.model(im_height=im_height, im_width=im_width, distortion_aware=distortion_aware_sunpose, **kw)
@@ -159,54 +160,93 @@ class Step:
         npix = B * H * W
         acc = zero_(self._acc)
         dev = ldr.device
+        # Independent parts of the step run on side streams (fork / join with stream waits, which a CUDA-graph capture records as graph
+        # edges): most launches of the step fill a fraction of the 148 SMs (the trunk convs at 32x128, B = 32: 64 tiles), so whatever does
+        # not depend on them overlaps.  s1: the sun branch (forward) / the DoG term / the sun-position backward; s2: the adversarial term,
+        # then the whole discriminator step.  `concurrent = False` keeps everything on the caller's stream.
+        main = torch.cuda.current_stream()
+        if self.concurrent and self._side is None:
+            self._side = (torch.cuda.Stream(), torch.cuda.Stream())
+        s1, s2 = self._side if self.concurrent else (main, main)
+
+        def fork(side):
+            if side is not main:
+                side.wait_stream(main)
+
+        def join(side):
+            if side is not main:
+                main.wait_stream(side)
+
         # ================================ generator_in_step(training=True), forward (:239-331) ================================
         both = torch.empty((2 * B, H, W, 3), dtype=torch.float32, device=dev)                    # [y_final_gamma; hdr_t_gamma]: VGG16's batch
         y_gamma = both[:B]
+        fork(s1)
+        with torch.cuda.stream(s1):
+            sm, acts = sun.sunposeEstimation(ldr, training=True)                                 # :253
+            sun.fc1.kernel_transposed()
+            sun.fc2.kernel_transposed()
+            y_c = sun.class_score(sm, gt)                                                        # :263-265 (outside the tape)
+            cams = [grad_cam.layer(y_c, a) for a in acts]                                        # :267-269
+            sun_rad_gamma, _, _ = gen.sun_rad_estimation(ldr, cams[0], cams[1], cams[2], sm, training=True, log_compress=True)   # :286-287
+            check(LIB.sky_kl_divergence(gt.data_ptr(), sm.data_ptr(), gt.numel(), acc[0:1].data_ptr(), _stream()))              # :303
+            g_sm = torch.empty_like(sm)
+            check(LIB.sky_kl_divergence_bwd(gt.data_ptr(), sm.data_ptr(), g_sm.data_ptr(), sm.numel(), 1.0 / Bg, 0, _stream()))
         check(LIB.sky_hdr_log_codec(hdr_t.data_ptr(), both[B:].data_ptr(), hdr_t.numel(), 0, st))                 # :246
         res_out = gen.encode(ldr, training=True, save=True)                                      # :249
         c_sky, sky_in = gen.decode_train(res_out, gen._dec, gen.conv1_f)                         # :250 up to conv1_f's raw output
-        sm, acts = sun.sunposeEstimation(ldr, training=True)                                     # :253
-        sun.fc1.kernel_transposed()
-        sun.fc2.kernel_transposed()
-        y_c = sun.class_score(sm, gt)                                                            # :263-265 (outside the tape)
-        cams = [grad_cam.layer(y_c, a) for a in acts]                                            # :267-269
-        sun_rad_gamma, _, _ = gen.sun_rad_estimation(ldr, cams[0], cams[1], cams[2], sm, training=True, log_compress=True)   # :286-287
         c_sun, sun_in = gen.decode_train(res_out, gen._dec_u, gen.conv1_u)                       # :288 up to conv1_u's raw output
         y_lin = torch.empty_like(c_sky)
         sky_lin, sun_lin = torch.empty_like(c_sky), torch.empty_like(c_sky)
         alpha = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
+        join(s1)
         check(LIB.sky_train_tail_fwd(c_sky.data_ptr(), c_sun.data_ptr(), ldr.data_ptr(), sun_rad_gamma.data_ptr(), hdr_t.data_ptr(), THRESHOLD,
                                      0.1, y_gamma.data_ptr(), y_lin.data_ptr(), sky_lin.data_ptr(), sun_lin.data_ptr(), alpha.data_ptr(),
                                      acc[8:9].data_ptr(), npix, st))                             # :251, 256-259, 289-298, 324
         # ---- loss terms with their adjoints ----
-        check(LIB.sky_kl_divergence(gt.data_ptr(), sm.data_ptr(), gt.numel(), acc[0:1].data_ptr(), st))                        # :303
-        g_sm = torch.empty_like(sm)
-        check(LIB.sky_kl_divergence_bwd(gt.data_ptr(), sm.data_ptr(), g_sm.data_ptr(), sm.numel(), 1.0 / Bg, 0, st))
+        fork(s1)
+        fork(s2)
+        with torch.cuda.stream(s1):
+            # DoG (:315-321)
+            base_y = torch.empty((B, 2 * H, 2 * W, 3), dtype=torch.float32, device=dev)
+            base_t = torch.empty_like(base_y)
+            check(LIB.sky_dog_base(y_lin.data_ptr(), base_y.data_ptr(), B, H, W, 3, _stream()))
+            check(LIB.sky_dog_base(hdr_t.data_ptr(), base_t.data_ptr(), B, H, W, 3, _stream()))
+            check(LIB.sky_dog_l1(base_y.data_ptr(), base_t.data_ptr(), B, 2 * H, 2 * W, 3, acc[4:8].data_ptr(), _stream()))
+            dbase = torch.empty_like(base_y)
+            check(LIB.sky_dog_l1_bwd(base_y.data_ptr(), base_t.data_ptr(), dbase.data_ptr(), B, 2 * H, 2 * W, 3,
+                                     1000.0 / (base_y.numel() // B * Bg), _stream()))
+            g_dog = torch.empty_like(y_lin)
+            check(LIB.sky_dog_base_bwd(dbase.data_ptr(), g_dog.data_ptr(), B, H, W, 3, 0, _stream()))
+        with torch.cuda.stream(s2):
+            # adversarial (:300, 327): the discriminator in inference mode on [ldr, y_final_lin], LSGAN gen_loss, data gradient back to y_final_lin
+            cat16 = torch.empty((2 * B, H, W, 8), dtype=torch.float32, device=dev)
+            dis.concat(ldr, hdr_t, out=cat16[:B])
+            dis.concat(ldr, y_lin, out=cat16[B:])
+            d_gen = dis.infer_forward(cat16[B:])
+            hh, ww = d_gen.shape[1], d_gen.shape[2]
+            n_d = B * (hh - 3) * (ww - 3)
+            g_same = torch.empty_like(d_gen)
+            check(LIB.sky_lsgan_bwd(d_gen.data_ptr(), g_same.data_ptr(), acc[9:10].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 1.0,
+                                    1.0 / (n_d // B * Bg), _stream()))
+            g_dis8 = dis.infer_backward_data(g_same)
+            adv_done = torch.cuda.Event()
+            adv_done.record(torch.cuda.current_stream())
+            # ============================ discriminator_in_step(training=True) + disc_tape.gradient (:351-380, 405) ============================
+            # needs nothing of the generator's backward pass: it stays on this stream until the optimizers
+            d_both = dis.train_forward(cat16, groups=2)                                          # :360-361, batch statistics per call
+            g_both = torch.empty_like(d_both)
+            check(LIB.sky_lsgan_bwd(d_both[:B].data_ptr(), g_both[:B].data_ptr(), acc[10:11].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 1.0,
+                                    0.5 / (n_d // B * Bg), _stream()))                           # real_loss (:236)
+            check(LIB.sky_lsgan_bwd(d_both[B:].data_ptr(), g_both[B:].data_ptr(), acc[11:12].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 0.0,
+                                    0.5 / (n_d // B * Bg), _stream()))                           # generated_loss (:237)
+            zero_(fvd.flat_g)
+            dis.train_backward(g_both, fvd)
         # perceptual (:306-312): VGG16 features of [prediction; target] in one batch, data gradient for the prediction half
         self.vgg.forward_saved(both)
         g_vgg4 = self.vgg.perceptual_backward(B, 0.01 * B / Bg, acc[1:4])
-        # DoG (:315-321)
-        base_y = torch.empty((B, 2 * H, 2 * W, 3), dtype=torch.float32, device=dev)
-        base_t = torch.empty_like(base_y)
-        check(LIB.sky_dog_base(y_lin.data_ptr(), base_y.data_ptr(), B, H, W, 3, st))
-        check(LIB.sky_dog_base(hdr_t.data_ptr(), base_t.data_ptr(), B, H, W, 3, st))
-        check(LIB.sky_dog_l1(base_y.data_ptr(), base_t.data_ptr(), B, 2 * H, 2 * W, 3, acc[4:8].data_ptr(), st))
-        dbase = torch.empty_like(base_y)
-        check(LIB.sky_dog_l1_bwd(base_y.data_ptr(), base_t.data_ptr(), dbase.data_ptr(), B, 2 * H, 2 * W, 3,
-                                 1000.0 / (base_y.numel() // B * Bg), st))
-        g_dog = torch.empty_like(y_lin)
-        check(LIB.sky_dog_base_bwd(dbase.data_ptr(), g_dog.data_ptr(), B, H, W, 3, 0, st))
-        # adversarial (:300, 327): the discriminator in inference mode on [ldr, y_final_lin], LSGAN gen_loss, data gradient back to y_final_lin
-        cat16 = torch.empty((2 * B, H, W, 8), dtype=torch.float32, device=dev)
-        dis.concat(ldr, hdr_t, out=cat16[:B])
-        dis.concat(ldr, y_lin, out=cat16[B:])
-        d_gen = dis.infer_forward(cat16[B:])
-        hh, ww = d_gen.shape[1], d_gen.shape[2]
-        n_d = B * (hh - 3) * (ww - 3)
-        g_same = torch.empty_like(d_gen)
-        check(LIB.sky_lsgan_bwd(d_gen.data_ptr(), g_same.data_ptr(), acc[9:10].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 1.0,
-                                1.0 / (n_d // B * Bg), st))
-        g_dis8 = dis.infer_backward_data(g_same)
+        join(s1)
+        if s2 is not main:
+            main.wait_event(adv_done)
         # ---- the tail's adjoint: all four terms meet here (:331: total = kl + 1000 DoG + gen + 10 L1 + 0.01 perceptual) ----
         dc_sky, dc_sun, d_srg = torch.empty_like(c_sky), torch.empty_like(c_sky), torch.empty_like(c_sky)
         check(LIB.sky_train_tail_bwd(c_sky.data_ptr(), c_sun.data_ptr(), ldr.data_ptr(), sun_rad_gamma.data_ptr(), alpha.data_ptr(), y_lin.data_ptr(),
@@ -214,23 +254,18 @@ class Step:
                                      0.1, dc_sky.data_ptr(), dc_sun.data_ptr(), d_srg.data_ptr(), npix, st))
         # ================================ gen_tape.gradient (:402) ================================
         zero_(fv.flat_g[:self._fc_offset])             # d gamma / d beta / atomically reduced kernels accumulate; the Dense gradients are overwritten
-        # sun radiance -> sun-position softmax (the max-normalisation of generator.py:160 included), joined with the KL adjoint
-        gen.sun.train_backward(d_srg, self._sun_grads(), g_sm, accumulate_dsm=True)
         work = []
-        sunpose_backward(sun, g_sm, fv.grad, on_dense_done=lambda: work.append(self._start_tail_allreduce()))
+        fork(s1)
+        with torch.cuda.stream(s1):
+            # sun radiance -> sun-position softmax (the max-normalisation of generator.py:160 included), joined with the KL adjoint
+            gen.sun.train_backward(d_srg, self._sun_grads(), g_sm, accumulate_dsm=True)
+            sunpose_backward(sun, g_sm, fv.grad, on_dense_done=lambda: work.append(self._start_tail_allreduce()))
         dres = torch.empty_like(res_out)
         gen.decode_backward(dc_sun, gen._dec_u, gen.conv1_u, sun_in, fv, dres, False)            # sun decoder (generator.py:127-156)
         gen.decode_backward(dc_sky, gen._dec, gen.conv1_f, sky_in, fv, dres, True)               # sky decoder (:110-125)
         gen.encode_backward(dres, fv)                                                            # trunk + encoder (:92-108)
-        # ================================ discriminator_in_step(training=True) + disc_tape.gradient (:351-380, 405) ================================
-        d_both = dis.train_forward(cat16, groups=2)                                              # :360-361, batch statistics per call
-        g_both = torch.empty_like(d_both)
-        check(LIB.sky_lsgan_bwd(d_both[:B].data_ptr(), g_both[:B].data_ptr(), acc[10:11].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 1.0,
-                                0.5 / (n_d // B * Bg), st))                                      # real_loss (:236)
-        check(LIB.sky_lsgan_bwd(d_both[B:].data_ptr(), g_both[B:].data_ptr(), acc[11:12].data_ptr(), B, hh, ww, 1, hh - 2, 1, ww - 2, 0.0,
-                                0.5 / (n_d // B * Bg), st))                                      # generated_loss (:237)
-        zero_(fvd.flat_g)
-        dis.train_backward(g_both, fvd)
+        join(s1)
+        join(s2)
         # ================================ optimizers (:403, 406) ================================
         self._finish_allreduce(work[0])
         self.apply_gradients()

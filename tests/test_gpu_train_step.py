@@ -175,8 +175,18 @@ def test_da_conv_kernels_vs_tf32_emulating_oracle(pkg, C, F, k):
     off = O.offsets(h, w, k)
     emu = SP.emulate_da(x, kern, bias, off, k, SP.da_plan(pkg, off, h, w, k), rnd=lambda a: tf32_emu.round_tf32(T(a)).numpy())
     assert rel(got_s, emu) < 2e-5, rel(got_s, emu)
-    dx, dk, db = pkg.distortion_aware_ops.conv2d_backward(layer, xd, dyd)
-    assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 1e-4, rel(dx.cpu().numpy(), xt.grad.numpy())
+    # data gradient: the scatter kernel contracts round(dy) with round(W) like this oracle; the row-strip kernel (default) contracts
+    # round(dy) with round(merged transposed effective weights) — TF32-level agreement with this oracle, fp32-accumulation-level
+    # agreement with the emulation of its own plan
+    import unittest.mock as mock
+    D = pkg.distortion_aware_ops
+    with mock.patch.object(D, "DA_BACKWARD_KERNEL", "scatter"):
+        dx_sc = D.conv2d_backward(layer, xd, dyd, need_dw=False)[0]
+    assert rel(dx_sc.cpu().numpy(), xt.grad.numpy()) < 1e-4, rel(dx_sc.cpu().numpy(), xt.grad.numpy())
+    dx, dk, db = D.conv2d_backward(layer, xd, dyd)
+    assert rel(dx.cpu().numpy(), xt.grad.numpy()) < 6e-4, rel(dx.cpu().numpy(), xt.grad.numpy())
+    emu_dx = SP.emulate_da_dgrad(dy, kern, C, off, k, SP.da_plan(pkg, off, h, w, k, transposed=1), rnd=lambda a: tf32_emu.round_tf32(T(a)).numpy())
+    assert rel(dx.cpu().numpy(), emu_dx) < 2e-5, rel(dx.cpu().numpy(), emu_dx)
     assert rel(dk.cpu().numpy(), kt.grad.numpy()) < 1e-4, rel(dk.cpu().numpy(), kt.grad.numpy())
     dk2 = torch.empty_like(dk)
     pkg._lib.check(pkg._lib.LIB.sky_conv2d_bwd_filter(xd.data_ptr(), dyd.data_ptr(), layer.offset_table.data_ptr(), dk2.data_ptr(), None,
