@@ -254,23 +254,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv2d_wgrad_kernel(const WgPar
         }
     } else {
         // ============================== MMA ISSUER ==============================
-        if (lane == 0 && tile_hi > tile_lo) {
+        // the whole warp walks the loop and the barrier waits; one elected lane issues (descriptor words stay in uniform registers)
+        if (tile_hi > tile_lo) {
             const uint32_t idesc = wg_idesc(128, (uint32_t)p.Fp);
-            uint32_t sg = 0;
+            uint32_t s = 0, phase = 0, sg = 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++sg) {
-                const int s = sg % p.stages;
-                mbar_wait(full0 + 8 * s, (sg / p.stages) & 1);
+                mbar_wait(full0 + 8 * s, phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * p.stage_bytes), b0 = a0 + WG_A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int g8 = 0; g8 < WG_PX / 8; ++g8)
-                    umma_tf32(tmem_base, wg_desc(a0 + g8 * 1024, WG_PX * 128, 512), wg_desc(b0 + g8 * 1024, WG_PX * 128, 512), idesc,
-                              (sg | (uint32_t)g8) != 0);
-                umma_commit(empty0 + 8 * s);
+                    for (int g8 = 0; g8 < WG_PX / 8; ++g8)
+                        umma_tf32(tmem_base, wg_desc(a0 + g8 * 1024, WG_PX * 128, 512), wg_desc(b0 + g8 * 1024, WG_PX * 128, 512), idesc,
+                                  (sg | (uint32_t)g8) != 0);
+                    umma_commit(empty0 + 8 * s);
+                }
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; phase ^= 1; }
             }
-            umma_commit(acc_full);
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         }
-        __syncwarp();
     }
     __syncthreads();
     if (warp == WG_PROD_WARPS) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
@@ -402,7 +406,8 @@ static int launch_wgrad(WgParams p, cudaStream_t st)
     SKY_REQUIRE(p.stages >= 2, SKY_ERR_UNSUPPORTED, "weight gradient: %d filters do not fit two pipeline stages", p.F);
     p.ntiles = (p.M + WG_PX - 1) / WG_PX;
     const int row_tiles = (p.K + 127) / 128;
-    int parts = (2 * 148 + row_tiles - 1) / row_tiles;
+    // one CTA per SM fits (the stages take the shared memory): one wave of pixel partitions, fewer partial sums to reduce
+    int parts = (148 + row_tiles - 1) / row_tiles;
     if (parts > p.ntiles) parts = p.ntiles;
     if (parts < 1) parts = 1;
     p.tiles_per_part = (p.ntiles + parts - 1) / parts;

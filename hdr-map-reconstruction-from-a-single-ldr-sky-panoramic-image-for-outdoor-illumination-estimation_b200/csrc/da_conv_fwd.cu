@@ -361,33 +361,37 @@ __global__ void __launch_bounds__(NUM_THREADS) da_conv2d_fwd_tc_kernel(const Fwd
         }
         tc_fence_before();
     } else if (warp == 4) {
-        // =========================== MMA ISSUER (one elected lane) ===========================
-        if (lane == 0) {
+        // =========================== MMA ISSUER (the warp walks the loop, one elected lane issues) ===========================
+        {
             const uint32_t idesc = umma_idesc_tf32(BLOCK_M, (uint32_t)p.Fp);
+            uint32_t s = 0, phase = 0;
             for (int kb = kb_lo; kb < kb_hi; ++kb) {
-                const int s = (kb - kb_lo) % STAGES;
-                mbar_wait(full0 + 8 * s, ((kb - kb_lo) / STAGES) & 1);
+                mbar_wait(full0 + 8 * s, phase);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
                 const uint32_t b_hi = a_hi + L::PLANES * L::A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-                    const uint32_t koff = ks * UMMA_K * 4;
-                    const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
-                    const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
-                    umma_tf32(tmem_base, da, db, idesc, ((kb - kb_lo) | ks) != 0);
-                    if (SPLIT3) {
-                        const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff);
-                        const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + b_bytes + koff);
-                        umma_tf32(tmem_base, da_lo, db, idesc, 1);
-                        umma_tf32(tmem_base, da, db_lo, idesc, 1);
+                    for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                        const uint32_t koff = ks * UMMA_K * 4;
+                        const uint64_t da = umma_desc_kmajor_sw128(a_hi + koff);
+                        const uint64_t db = umma_desc_kmajor_sw128(b_hi + koff);
+                        umma_tf32(tmem_base, da, db, idesc, ((kb - kb_lo) | ks) != 0);
+                        if (SPLIT3) {
+                            const uint64_t da_lo = umma_desc_kmajor_sw128(a_hi + L::A_BYTES + koff);
+                            const uint64_t db_lo = umma_desc_kmajor_sw128(b_hi + b_bytes + koff);
+                            umma_tf32(tmem_base, da_lo, db, idesc, 1);
+                            umma_tf32(tmem_base, da, db_lo, idesc, 1);
+                        }
                     }
+                    umma_commit(empty0 + 8 * s);            // smem stage free once these MMAs have read it
                 }
-                umma_commit(empty0 + 8 * s);            // smem stage free once these MMAs have read it
+                __syncwarp();
+                if (++s == STAGES) { s = 0; phase ^= 1; }
             }
-            umma_commit(tmem_full);                      // accumulator complete
+            if (elect_one()) umma_commit(tmem_full);         // accumulator complete
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // =========================== WEIGHT LOADER (one elected lane, bulk async copies) ===========================
         if (lane == 0) {

@@ -147,6 +147,16 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
+// One lane of a converged warp: the warp-uniform way to single out the thread that issues tcgen05.mma / tcgen05.commit.  With the
+// surrounding loop executed by the whole warp, descriptor words stay in uniform registers; under `if (lane == 0)` the compiler moves
+// them there lane by lane (R2UR + a BRA.U.ANY loop) before every MMA.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols)
 {

@@ -102,15 +102,6 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_interleaved(uint32_t saddr,
     return d;                          // layout type 0: no swizzle
 }
 
-// one lane of a converged warp (the warp-uniform way to single out the issuing thread: the surrounding loop stays uniform, so descriptor
-// words live in uniform registers instead of being moved there lane by lane before every tcgen05.mma)
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 // The reference's treatment of a column index (distortion_aware_ops.py:76-77 on the float coordinate, :90-91 on the integer corners),
 // restated on the integer part: `q` is a column in the PADDED frame before any wrap.  Returns the unpadded column, or -1 for a zero.
 __device__ __forceinline__ int da_map_col(int q, int in_w, int pw0, int W)
