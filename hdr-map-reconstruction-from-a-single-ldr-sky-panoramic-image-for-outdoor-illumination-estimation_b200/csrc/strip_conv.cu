@@ -571,55 +571,78 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
 // ---------------------------------------------------------------------------------------------------------------------
 // transposed != 0 (data gradient): tile rows are the layer's INPUT channels (N = C, padded to Np), the contraction runs over its filters
 // (KC = F / 32 chunks): tile (window, fc)[c][kk] = sum coef * kernel[tap*C + c, fc*32 + kk].
-__global__ void strip_weff_pack_kernel(const float *__restrict__ kernel, float *__restrict__ packed, const int *__restrict__ term_begin,
-                                       const WeffTerm *__restrict__ terms, int nwins, int C, int CC, int F, int Fp, int planes, int transposed)
+__global__ void strip_weff_pack_t_kernel(const float *__restrict__ kernel, float *__restrict__ packed, const int *__restrict__ term_begin,
+                                         const WeffTerm *__restrict__ terms, int nwins, int C, int F, int Np, int planes)
 {
-    if (transposed) {
-        const int KC = F / BLOCK_K, Np = Fp;                 // Fp carries the padded row count of a tile (here: padded C)
-        const long total = (long)nwins * KC * Np * BLOCK_K;
-        const size_t tile_floats = (size_t)Np * BLOCK_K;
-        for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-            const int kk = (int)(e % BLOCK_K);               // kk fastest: consecutive threads read consecutive filters of one kernel row
-            const int n = (int)((e / BLOCK_K) % Np);
-            const long wc = e / ((long)Np * BLOCK_K);
-            const int fc = (int)(wc % KC), w = (int)(wc / KC);
-            float v = 0.f;
-            if (n < C) {
-                const int tb = term_begin[w], te = term_begin[w + 1];
-                for (int q = tb; q < te; ++q) {
-                    const WeffTerm t = terms[q];
-                    v = fmaf(t.coef, kernel[((size_t)t.tap * C + n) * F + fc * BLOCK_K + kk], v);
-                }
-            }
-            const uint32_t hi = f32_to_tf32_rna(v);
-            const size_t o = (sw128_offset((uint32_t)n, (uint32_t)(kk >> 2)) >> 2) + (kk & 3);
-            float *tile = packed + (size_t)wc * planes * tile_floats;
-            tile[o] = __uint_as_float(hi);
-            if (planes == 2) tile[tile_floats + o] = __uint_as_float(f32_to_tf32_rna(v - __uint_as_float(hi)));
-        }
-        return;
-    }
-    const long total = (long)nwins * CC * Fp * BLOCK_K;
-    const size_t tile_floats = (size_t)Fp * BLOCK_K;
+    // one thread per (tile row n, 16-byte chunk): a 128-bit load per term (4 consecutive filters of kernel row tap*C + n), a 128-bit store;
+    // the 8 threads of a row write its 128 bytes
+    const int KC = F / BLOCK_K;
+    const long total = (long)nwins * KC * Np * 8;
+    const size_t tile_floats = (size_t)Np * BLOCK_K;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        // n fastest: consecutive threads read consecutive filters of one kernel row (coalesced)
-        const int n = (int)(e % Fp);
-        const int kk = (int)((e / Fp) % BLOCK_K);
-        const long wc = e / ((long)Fp * BLOCK_K);
-        const int cc = (int)(wc % CC), w = (int)(wc / CC);
-        float v = 0.f;
-        if (n < F) {
-            const int tb = term_begin[w], te = term_begin[w + 1];
+        const int chunk = (int)(e & 7);
+        const int n = (int)((e >> 3) % Np);
+        const long wc = e / ((long)Np * 8);
+        const int fc = (int)(wc % KC), w = (int)(wc / KC);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < C) {
+            const int tb = __ldg(term_begin + w), te = __ldg(term_begin + w + 1);
             for (int q = tb; q < te; ++q) {
                 const WeffTerm t = terms[q];
-                v = fmaf(t.coef, kernel[((size_t)t.tap * C + cc * BLOCK_K + kk) * F + n], v);
+                const float4 kv = __ldg(reinterpret_cast<const float4 *>(kernel + ((size_t)t.tap * C + n) * F + fc * BLOCK_K + 4 * chunk));
+                v.x = fmaf(t.coef, kv.x, v.x); v.y = fmaf(t.coef, kv.y, v.y); v.z = fmaf(t.coef, kv.z, v.z); v.w = fmaf(t.coef, kv.w, v.w);
             }
         }
-        const uint32_t hi = f32_to_tf32_rna(v);
-        const size_t o = (sw128_offset((uint32_t)n, (uint32_t)(kk >> 2)) >> 2) + (kk & 3);
-        float *tile = packed + (size_t)wc * planes * tile_floats;
-        tile[o] = __uint_as_float(hi);
-        if (planes == 2) tile[tile_floats + o] = __uint_as_float(f32_to_tf32_rna(v - __uint_as_float(hi)));
+        uint4 hi;
+        hi.x = f32_to_tf32_rna(v.x); hi.y = f32_to_tf32_rna(v.y); hi.z = f32_to_tf32_rna(v.z); hi.w = f32_to_tf32_rna(v.w);
+        uint8_t *tile = reinterpret_cast<uint8_t *>(packed + (size_t)wc * planes * tile_floats);
+        const uint32_t o = sw128_offset((uint32_t)n, (uint32_t)chunk);
+        *reinterpret_cast<uint4 *>(tile + o) = hi;
+        if (planes == 2) {
+            uint4 lo;
+            lo.x = f32_to_tf32_rna(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rna(v.y - __uint_as_float(hi.y));
+            lo.z = f32_to_tf32_rna(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rna(v.w - __uint_as_float(hi.w));
+            *reinterpret_cast<uint4 *>(tile + tile_floats * 4 + o) = lo;
+        }
+    }
+}
+
+// forward flavour: one block per (window, 32-channel chunk) tile.  The kernel variable is read along its filters (coalesced), the tile is
+// written along its k values (128-byte rows): the transpose goes through shared memory.
+__global__ void __launch_bounds__(256) strip_weff_pack_kernel(const float *__restrict__ kernel, float *__restrict__ packed,
+                                                             const int *__restrict__ term_begin, const WeffTerm *__restrict__ terms, int C,
+                                                             int CC, int F, int Fp, int planes)
+{
+    extern __shared__ float wsm[];                           // [32][Fp + 1]
+    const int wc = blockIdx.x, cc = wc % CC, w = wc / CC, ld = Fp + 1;
+    const int tb = __ldg(term_begin + w), te = __ldg(term_begin + w + 1);
+    for (int e = threadIdx.x; e < BLOCK_K * Fp; e += blockDim.x) {
+        const int kk = e / Fp, n = e - kk * Fp;
+        float v = 0.f;
+        if (n < F)
+            for (int q = tb; q < te; ++q) {
+                const WeffTerm t = terms[q];
+                v = fmaf(t.coef, __ldg(kernel + ((size_t)t.tap * C + cc * BLOCK_K + kk) * F + n), v);
+            }
+        wsm[kk * ld + n] = v;
+    }
+    __syncthreads();
+    const size_t tile_floats = (size_t)Fp * BLOCK_K;
+    uint8_t *tile = reinterpret_cast<uint8_t *>(packed + (size_t)wc * planes * tile_floats);
+    for (int e = threadIdx.x; e < Fp * 8; e += blockDim.x) {
+        const int chunk = e & 7, n = e >> 3;
+        const float v0 = wsm[(4 * chunk) * ld + n], v1 = wsm[(4 * chunk + 1) * ld + n], v2 = wsm[(4 * chunk + 2) * ld + n],
+                    v3 = wsm[(4 * chunk + 3) * ld + n];
+        uint4 hi;
+        hi.x = f32_to_tf32_rna(v0); hi.y = f32_to_tf32_rna(v1); hi.z = f32_to_tf32_rna(v2); hi.w = f32_to_tf32_rna(v3);
+        const uint32_t o = sw128_offset((uint32_t)n, (uint32_t)chunk);
+        *reinterpret_cast<uint4 *>(tile + o) = hi;
+        if (planes == 2) {
+            uint4 lo;
+            lo.x = f32_to_tf32_rna(v0 - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rna(v1 - __uint_as_float(hi.y));
+            lo.z = f32_to_tf32_rna(v2 - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rna(v3 - __uint_as_float(hi.w));
+            *reinterpret_cast<uint4 *>(tile + tile_floats * 4 + o) = lo;
+        }
     }
 }
 
@@ -761,11 +784,8 @@ extern "C" int sky_da_strip_pack_weights(const float *kernel, const float *offse
     if (rc != SKY_OK) return rc;
     SKY_REQUIRE(pl->terms != nullptr, SKY_ERR_CUDA, "strip plan tables are not on the device");
     const int Fp = f_pad_of(F), CC = C / BLOCK_K, planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
-    const long total = (long)pl->nwins * CC * Fp * BLOCK_K;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    strip_weff_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, pl->term_begin, pl->terms, pl->nwins, C, CC, F, Fp,
-                                                                    planes, 0);
+    strip_weff_pack_kernel<<<pl->nwins * CC, 256, BLOCK_K * (Fp + 1) * sizeof(float), (cudaStream_t)stream>>>(kernel, (float *)packed, pl->term_begin,
+                                                                                                             pl->terms, C, CC, F, Fp, planes);
     SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
@@ -821,11 +841,10 @@ extern "C" int sky_da_strip_pack_weights_t(const float *kernel, const float *off
     int rc = get_plan_da(offsets_host, h, w, k, &pl, true, true);
     if (rc != SKY_OK) return rc;
     const int Np = f_pad_of(C), KC = F / BLOCK_K, planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
-    const long total = (long)pl->nwins * KC * Np * BLOCK_K;
+    const long total = (long)pl->nwins * KC * Np * 8;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    strip_weff_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, pl->term_begin, pl->terms, pl->nwins, C, KC, F, Np,
-                                                                    planes, 1);
+    strip_weff_pack_t_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)packed, pl->term_begin, pl->terms, pl->nwins, C, F, Np, planes);
     SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
