@@ -822,9 +822,11 @@ def run_ours(args):
                 modes[other] = {"train_ms_per_step": round(t2, 4), "train_value": round(B / (t2 * 1e-3), 1), "dtype": DTYPE[other],
                                 "inference_value": measure_inference(pkg, args, rank, flush, other)["value"]}
                 line["modes"] = modes
-                line["parity"] = {"3xtf32": "whole step vs the fp64 oracle: y_final_lin 3.4e-5 (log-luminance rel-L2; north_star bar 1e-3), losses <= 9e-5, "
-                                            "every gradient <= 5.3e-3 (tests/test_gpu_train_step.py)",
-                                  "tf32": "per layer vs the TF32-emulating oracle <= 2e-5; whole step vs the fp64 oracle: y_final_lin 3.1e-3, gradients <= 1e-1"}
+                line["parity"] = {"3xtf32": "whole step vs the fp64 oracle (B = 2): y_final_lin 4.5e-5 (log-luminance rel-L2; north_star bar 1e-3), losses <= 9e-5, "
+                                            "gradients: median 1e-3, max 1.0e-2 (a flipped ReLU / arg-max unit moves an 8x32 instance-norm plane by percents; "
+                                            "every backward kernel alone <= 1e-4 vs the TF32-emulating oracle) (tests/test_gpu_train_step.py)",
+                                  "tf32": "per kernel vs its TF32 operand emulation <= 2e-5; whole step vs the fp64 oracle: y_final_lin 2.9e-3, losses <= 5e-4, "
+                                          "gradients median 2.4e-2, max 1.3e-1"}
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -675,7 +675,15 @@ static int conv2d_plain(FwdArgs a, int stride)
     a.offsets = nullptr; a.offsets_host = nullptr; a.plain_stride = stride;
     const int F = a.F;
     if (F <= 4) {
-        int rc = launch_fwd_smallf(a);          // conv1_f / conv1_u: too few filters for the tensor-core pipeline to pay
+        // conv1_f / conv1_u (7x7, 32 -> 3): on the row-strip kernel the 49 taps are 7 strips and N = 16 MMAs; the fp32 small-filter kernel
+        // keeps the layers the strip kernel does not take (the fused inference tail, C % 32 != 0)
+        // (only the raw conv + bias of the train step: the inference tails, fused or not, stay on ONE fp32 kernel so that
+        // sky_conv2d_fwd_blend and conv + sky_blend_split remain the same arithmetic bit for bit)
+        if ((a.C % BLOCK_K) == 0 && a.flags == 0) {
+            int rc = launch_fwd_strip_plain(a);
+            if (rc != SKY_ERR_UNSUPPORTED) return rc;
+        }
+        int rc = launch_fwd_smallf(a);
         if (rc != SKY_ERR_UNSUPPORTED) return rc;
     }
     if (F <= 256) {
