@@ -407,7 +407,7 @@ static int launch_wgrad(WgParams p, cudaStream_t st)
     p.ntiles = (p.M + WG_PX - 1) / WG_PX;
     const int row_tiles = (p.K + 127) / 128;
     // one CTA per SM fits (the stages take the shared memory): one wave of pixel partitions, fewer partial sums to reduce
-    int parts = (148 + row_tiles - 1) / row_tiles;
+    int parts = 148 / row_tiles;                    // floor: 17 x 9 = 153 CTAs would spill five CTAs into a second wave
     if (parts > p.ntiles) parts = p.ntiles;
     if (parts < 1) parts = 1;
     p.tiles_per_part = (p.ntiles + parts - 1) / parts;
