@@ -380,12 +380,13 @@ extern "C" int sky_da_conv2d_bwd_filter(const float *x, const float *dy, const f
     SKY_CHECK_CUDA(cudaMemsetAsync(dkernel, 0, (size_t)p.k2 * C * F * sizeof(float), st));
     const int ntiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     const int groups = (p.k2 + 3) / 4;
-    int parts = (2 * 148) / (groups * p.CC);        // about two waves of CTAs
+    const int smem = 4 * 16384 + p.FC * 16384 + 64 + 4 * BLOCK_M * (int)sizeof(CornerRef) + 1024;
+    const int per_sm = (227 * 1024) / (smem + 1024) > 1 ? (227 * 1024) / (smem + 1024) : 1;      // CTAs the shared memory lets an SM hold
+    int parts = per_sm * 148 / (groups * p.CC);     // whole waves only (a second, part-filled wave costs as much as a full one)
     if (parts < 1) parts = 1;
     if (parts > ntiles) parts = ntiles;
     p.tiles_per_part = (ntiles + parts - 1) / parts;
     p.parts = (ntiles + p.tiles_per_part - 1) / p.tiles_per_part;
-    const int smem = 4 * 16384 + p.FC * 16384 + 64 + 4 * BLOCK_M * (int)sizeof(CornerRef) + 1024;
     SKY_ENSURE_DYN_SMEM(da_conv2d_wgrad_kernel, 227 * 1024);
     dim3 grid(p.parts, groups, p.CC);
     da_conv2d_wgrad_kernel<<<grid, BWD_THREADS, smem, st>>>(p);

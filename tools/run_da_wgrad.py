@@ -24,3 +24,17 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ms.append(s.elapsed_time(e))
 print("wgrad", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:]) / 1e9))
+# the pipelined kernel of csrc/conv_bwd.cu through sky_conv2d_bwd_filter (offsets != NULL)
+lib, check = pkg._lib.LIB, pkg._lib.check
+dk, db = torch.empty_like(layer.kernel), torch.empty_like(layer.bias)
+st = lambda: torch.cuda.current_stream().cuda_stream
+ms = []
+for _ in range(reps):
+    flush.zero_()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    check(lib.sky_conv2d_bwd_filter(x.data_ptr(), dy.data_ptr(), layer.offset_table.data_ptr(), dk.data_ptr(), db.data_ptr(), B, h, w, C, C, F, k, 1, 0, st()))
+    e.record()
+    torch.cuda.synchronize()
+    ms.append(s.elapsed_time(e))
+print("wgrad (pipelined kernel, sky_conv2d_bwd_filter)", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:]) / 1e9))
