@@ -641,7 +641,7 @@ def run_ours(args):
         h2d_pairs = [(dev[k], host[k]) for k in ("hdr", "t", "crf", "sigma_s", "sigma_c", "gt")]     # the noise draws stay on the device (RNG state, not data)
         x_host, x = host["hdr"], dev["hdr"]
         flat_w = step_obj.fv_gen.flat_w
-        allow_graph = world == 1
+        allow_graph = world == 1 or args.graph_collectives     # N > 1: the step holds three NCCL all-reduces
     elif args.workload == "trunk_train":
         trunk = pkg.resLayer((C,) * N_BLOCKS, C, k_h=K_SIZE, k_w=K_SIZE, math_mode=args.math)
         trunk.build((B, h, w, C))
@@ -789,7 +789,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.math], "data": "synthetic",
             "config": {"workload": workload_name(B, H, W, args.workload), "global_batch": world * B,
                        "parallelism": (f"batch shards x{world}, " + ("one gradient all-reduce (NCCL) of the flat buffers per step, the Dense bucket started "
-                                                                     "early and overlapped with the rest of the backward pass" if is_train else "no collective")),
+                                                                     "early and overlapped with the rest of the backward pass; the collectives are part of the "
+                                                                     "step's CUDA graph when cuda_graph is true" if is_train else "no collective")),
                        "l2": "256 MB buffer written between timed iterations (outside the events)", "cuda_graph": graph is not None,
                        "math_mode": args.math},
             "e2e": {"value": round(world * B / (t_e2e * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
@@ -831,6 +832,17 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a captured graph holds NCCL kernels: release it and drain the device before the communicator goes away; the process then leaves
+        # without running the communicator's destructor (with graph-captured collectives it can wait forever on some NCCL versions)
+        graph = None
+        holder.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if args.graph_collectives:
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -848,6 +860,8 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "sun_train", "inference", "sky", "trunk", "trunk_train", "sweep"],
                     help="train: the full train step, BASELINE configs[2] (default; the line also carries the full-inference throughput, "
                          "configs[0], and both arithmetic modes); sun_train: the sun-position pre-train step, configs[1]; sweep: configs[3]")
+    ap.add_argument("--eager-collectives", dest="graph_collectives", action="store_false",
+                    help="N > 1: launch the train step eagerly instead of capturing it, NCCL all-reduces included, into one CUDA graph (the default)")
     ap.add_argument("--lean", action="store_true", help="skip the secondary measurements (inference, other mode, cpu_baseline)")
     ap.add_argument("--trace-out", default=None, help="write the full per-entry-point device timeline of one step (JSON) to this file")
     args = ap.parse_args()
