@@ -507,3 +507,38 @@ def test_plain_wiring_train_step(pkg):
     unit = step._gen.res.sequence[0]
     xin, c1, a1, c2, s1, s2 = unit._saved
     assert tuple(step.fv_gen.grad(unit.conv1, "w").shape) == (3, 3, 128, 128)
+
+
+def test_train_step_batch_8_losses(pkg):
+    """The full train step at a batch whose strip-kernel tiles span four panoramas (NB = 4 at the 8x32 trunk) and more than one batch
+    group: every loss term and the linear HDR output against the oracle's fp64 step (gradients are checked at B = 2 above)."""
+    B, H, W = 8, 32, 128
+    ldr, hdr_t, gt = _inputs(B, H, W, seed=9)
+    wg, ws, wd = M.random_full_generator_weights(3, H, W), M.random_sunpose_weights(5, H, W), M.random_discriminator_weights(4)
+    dd = pkg.vgg16.random_data_dict(1)
+    want = M.train_step(ldr, hdr_t, gt, wg, ws, wd, dd)
+    step = pkg.train.Step(batch_size=B, im_height=H, im_width=W, vgg_data_dict=dd, math_mode="3xtf32")
+    step.init_training(B)
+    step._gen.set_weights(wg)
+    step._sun.set_weights(ws)
+    step._dis.set_weights(wd)
+    outs = step.train_step([T(hdr_t).cuda(), T(ldr).cuda()], T(gt).cuda())
+    torch.cuda.synchronize()
+    got = {k: float(v) for k, v in step.last_losses.items()}
+    for k in ("kl", "perceptual", "dog", "l1", "gen", "total", "disc"):
+        assert abs(got[k] / float(want[k]) - 1) <= 2e-3, (k, got[k], float(want[k]))
+    logl = lambda y: np.log1p(10 * np.asarray(y, np.float64)) / np.log(11.0)
+    assert rel(logl(outs[0].cpu().numpy()), logl(want["y_final_lin"].numpy())) <= 1e-3
+    # single-stream and multi-stream steps are the same arithmetic up to the order of the atomics (fp64 moments, fp32 weight-gradient partial
+    # sums): the forward agrees to 1e-6; through ~40 TF32 backward layers the re-drawn roundings grow to a few 1e-4 on the deepest
+    # gradients — the same size as two runs of ONE configuration (tools/dbg_strip_grads.py: 5e-5 ... 5e-4)
+    step2 = pkg.train.Step(batch_size=B, im_height=H, im_width=W, vgg_data_dict=dd, math_mode="3xtf32", concurrent=False)
+    step2.init_training(B)
+    step2._gen.set_weights(wg)
+    step2._sun.set_weights(ws)
+    step2._dis.set_weights(wd)
+    outs2 = step2.train_step([T(hdr_t).cuda(), T(ldr).cuda()], T(gt).cuda())
+    torch.cuda.synchronize()
+    assert rel(outs2[0].cpu().numpy(), outs[0].cpu().numpy()) <= 1e-6
+    assert rel(step2.fv_gen.flat_g.cpu().numpy(), step.fv_gen.flat_g.cpu().numpy()) <= 2e-3
+    assert rel(step2.fv_dis.flat_g.cpu().numpy(), step.fv_dis.flat_g.cpu().numpy()) <= 2e-3
