@@ -401,7 +401,7 @@ def conv_work(name, a):
         B, h, w, Ci, F, k = a[4:10]; s = 1; kind = "da dgrad"
     elif name == "sky_da_conv2d_bwd_data_strip":
         B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "da dgrad"
-    elif name == "sky_da_conv2d_bwd_filter":
+    elif name in ("sky_da_conv2d_bwd_filter", "sky_da_conv2d_bwd_filter_strip"):
         B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "da wgrad"
     elif name == "sky_da_conv2d_smallc_bwd_filter":
         B, h, w, Ci, F, k = a[5:11]; s = 1; kind = "small-C da wgrad"

@@ -12,6 +12,7 @@ OK = 0
 ERR_INVALID, ERR_UNDEFINED_COORDS, ERR_CUDA, ERR_UNSUPPORTED, ERR_EVEN_KERNEL, ERR_NAN_OFFSET = -1, -2, -3, -4, -5, -6
 EPI_NONE, EPI_LEAKY_RELU, EPI_RESIDUAL, EPI_RELU, EPI_LOG_DECOMPRESS, EPI_SUN_BLEND, EPI_MASK, EPI_FORCE_DIRECT = 0, 1, 2, 4, 8, 16, 32, 256
 EPI_FORCE_BAND = 512
+EPI_NO_PAIR = 1024
 MATH_TF32, MATH_3XTF32 = 0, 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -43,6 +44,8 @@ SIGNATURES = {
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "sky_da_conv2d_bwd_filter_strip": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "sky_debug_wgrad_trace": (_i, [_vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
     "sky_instnorm_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp]),
     "sky_mse_loss": (_i, [_vp] * 4 + [ctypes.c_long, _vp]),
@@ -121,10 +124,10 @@ def load():
 
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
-LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2,
+LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2, "sky_da_conv2d_bwd_filter_strip": 2,
                      "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_da_strip_weight_bytes": 0, "sky_da_strip_weight_bytes_t": 0, "sky_da_strip_plan_info": 0, "sky_da_strip_plan_export": 0,
                      "sky_conv_strip_plan_info": 0, "sky_conv_strip_plan_export": 0, "sky_last_error": 0, "sky_version": 0,
-                     "sky_debug_band_trace": 0, "sky_debug_strip_trace": 0}
+                     "sky_debug_band_trace": 0, "sky_debug_strip_trace": 0, "sky_debug_wgrad_trace": 0}
 
 
 _UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host", "sky_da_strip_weight_bytes", "sky_da_strip_weight_bytes_t",

@@ -12,6 +12,9 @@
 //                    tile) into a 2-3 stage mbarrier ring, one thread issues tcgen05.mma (M = 128 kernel rows, N = filters, K = 8
 //                    pixels) into a TMEM accumulator that stays resident over the CTA's pixel partition, 4 warps drain it with vector
 //                    reductions.  Sampler: plain (stride 1 / 2, TensorFlow SAME) or the distortion-aware geometry (da_sample).
+#include <stdlib.h>
+#include <string.h>
+
 #include "strip_conv.cuh"
 
 namespace sky {
@@ -503,8 +506,14 @@ extern "C" int sky_conv2d_bwd_filter(const float *x, const float *dy, const floa
     }
     p.M = B * p.oh * p.ow;
     if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dkernel, 0, (size_t)p.k2 * C_store * F * sizeof(float), st));
+    // plain layers with C % 32 == 0: the strip formulation (strip_wgrad.cu) — the input rows are staged once per pixel tile for all the
+    // taps of a kernel row instead of being re-gathered per tap; SKY_WGRAD_KERNEL=gather keeps the kernels below (the cross-check)
     int rc_small = SKY_ERR_UNSUPPORTED;
-    if (!offsets && stride == 1 && C_store == C) rc_small = launch_wgrad_smallf(x, dy, dkernel, B, h, w, C, F, k, st);   // conv1_f / conv1_u
+    if (!offsets && C_store == C && C % 32 == 0 && !(F <= 4 && stride == 1) && !(getenv("SKY_WGRAD_KERNEL") && !strcmp(getenv("SKY_WGRAD_KERNEL"), "gather"))) {
+        rc_small = launch_wgrad_strip(x, dy, nullptr, dkernel, B, h, w, C, F, k, stride, st);
+        if (rc_small != SKY_OK && rc_small != SKY_ERR_UNSUPPORTED) return rc_small;
+    }
+    if (rc_small == SKY_ERR_UNSUPPORTED && !offsets && stride == 1 && C_store == C) rc_small = launch_wgrad_smallf(x, dy, dkernel, B, h, w, C, F, k, st);   // conv1_f / conv1_u
     if (rc_small != SKY_OK && rc_small != SKY_ERR_UNSUPPORTED) return rc_small;
     for (int f0 = 0; rc_small == SKY_ERR_UNSUPPORTED && f0 < F; f0 += 256) {          // more than 256 filters (d4: 512): column slices of the same dY
         p.f0 = f0; p.F = (F - f0) < 256 ? (F - f0) : 256;

@@ -274,6 +274,8 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap)
 }
 // Host: encode a 4-D fp32 NHWC tensor map with box (box_c, box_w, box_h, 1), no swizzle.
 int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, int w, int C, int box_c, int box_w, int box_h);
+// Host: dy [B, OH, OW, F] (F % 4 == 0) for the strip weight gradient, box = (32 f, 8 panoramas, box_cols columns, 1 row), 32-byte-atom 128-byte swizzle
+int encode_dy_wgrad_tensor_map(CUtensorMap *out, const float *base, int B, int OH, int OW, int F, int box_cols);
 // Host: encode a row-major fp32 matrix [rows][cols] with box (box_cols, box_rows), no swizzle (cols % 4 == 0, 16-byte aligned base).
 int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows);
 }  // namespace sky

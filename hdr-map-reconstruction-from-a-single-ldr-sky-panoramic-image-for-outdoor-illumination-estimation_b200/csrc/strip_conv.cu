@@ -14,6 +14,7 @@
 // Tile = one output row class x TW columns x NB panoramas (TW * NB = 128); tile row m = column * NB + panorama, so that a column shift of
 // s is a row shift of s * NB for every panorama of the tile at once.
 #include <math.h>
+#include <stdlib.h>
 
 #include "strip_conv.cuh"
 
@@ -30,6 +31,7 @@ constexpr int SC_EPI_WARP0 = 0;
 constexpr int SC_WARP_MMA = 4, SC_WARP_WLOAD = 8;
 constexpr int SC_THREADS = 20 * 32;
 constexpr int SC_EPI_COLS = 16, SC_EPI_STRIDE = 20;   // staging row stride (floats): odd multiple of 16 B -> conflict-free
+constexpr int SC_PAIR_MAX_N = 32;                      // widest layer (padded filters) that pairs tiles
 constexpr int SC_MAX_STRIPS = 16, SC_MAX_WINS = 192; // strips / windows of one row class (staged in shared memory)
 constexpr int SC_UNROLL2 = 5, SC_UNROLL1 = 8;          // producer items in flight per thread: strips blending two input rows / reading one
 static_assert(SC_EPI_WARP0 % 4 == 0, "epilogue warps must align with TMEM lane quadrants");
@@ -65,6 +67,7 @@ struct StripParams {
     size_t image_stride;                // bytes between the packed images of a layer with more than 256 filters
     int wmul, wcc_stride;               // weight tile of (window, chunk cc) = wtile0 * wmul + cc * wcc_stride
     int ncols, ocs, TW, NB, log_nb, tiles_x, tiles_b, ntiles;
+    int pair, pairs_per_row, nwork;     // pair = 2: a CTA step covers two tiles of one row class (M = 256 through two accumulators) per weight tile
     int SR, PS, strip_bytes, NSB, NWB, G, group_threads;
     int da, in_h, in_w, ph0, pw0;       // da = 1: distortion-aware column map (the reference's wrap in the padded frame) and exact taps;
                                         // da = 2: its transpose (data gradient); 0: plain convolution (zero outside the map)
@@ -83,9 +86,9 @@ struct StripSmem {
     static __host__ __device__ int num_bars(int NSB, int NWB) { return 2 * NSB + 2 * NWB + 4; }
     static constexpr int PLAN_BYTES = 2 * (SC_MAX_STRIPS * 8 + SC_MAX_WINS * 4) + SC_MAX_STRIPS * 40;   // the current row class: one copy per
                                                                                      // single-lane role + the producers' strip table
-    static __host__ __device__ int total_bytes(int PS, int Fs, int NSB, int NWB)
+    static __host__ __device__ int total_bytes(int PS, int Fs, int NSB, int NWB, int pair = 1)
     {
-        return round_up(NSB * strip_bytes(PS), 1024) + NWB * b_stage(Fs) + EPI_BYTES + PLAN_BYTES + num_bars(NSB, NWB) * 8 + 16 + 1024;
+        return round_up(NSB * pair * strip_bytes(PS), 1024) + NWB * b_stage(Fs) + EPI_BYTES + PLAN_BYTES + num_bars(NSB, NWB) * 8 + 16 + 1024;
     }
 };
 
@@ -100,18 +103,6 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_interleaved(uint32_t saddr,
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
     return d;                          // layout type 0: no swizzle
-}
-
-// The reference's treatment of a column index (distortion_aware_ops.py:76-77 on the float coordinate, :90-91 on the integer corners),
-// restated on the integer part: `q` is a column in the PADDED frame before any wrap.  Returns the unpadded column, or -1 for a zero.
-__device__ __forceinline__ int da_map_col(int q, int in_w, int pw0, int W)
-{
-    if (q < 0) q += in_w;                 // :76 (x < 0 -> x + in_w; the result is <= in_w - 1, so :77 does not fire after it)
-    else if (q > in_w - 1) q -= in_w;     // :77
-    if (q < 0) q += in_w;                 // :90
-    if (q > in_w - 1) q -= in_w;          // :91
-    const int c = q - pw0;
-    return (c >= 0 && c < W) ? c : -1;
 }
 
 // The transposed map of the data gradient: `q` = input column c minus the forward shift s; returns the unique dy column j in [0, W)
@@ -204,14 +195,15 @@ __device__ __forceinline__ void fill_strip(const StripParams &p, const StripDesc
     }
 }
 
-template <bool SPLIT3>
+template <bool SPLIT3, int PAIR>
 __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripParams p)
 {
     using L = StripSmem<SPLIT3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *strip_ring = smem;
-    uint8_t *b_ring = smem + round_up(p.NSB * p.strip_bytes, 1024);
+    const int stage_bytes = PAIR * p.strip_bytes;            // one ring stage = the strips of the step's `pair` tiles
+    uint8_t *b_ring = smem + round_up(p.NSB * stage_bytes, 1024);
     const int b_stage = L::b_stage(p.Fs);
     const int b_plane = p.Fs * BLOCK_K * 4;
     float *epi = reinterpret_cast<float *>(b_ring + p.NWB * b_stage);
@@ -261,9 +253,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
         uint32_t sb = 0, sphase = 1, turn = 0;
         int nstamp = 0, cur_rp = -1;
         StripDesc *s_sd = reinterpret_cast<StripDesc *>(plan_scratch + 2 * (2 * SC_MAX_STRIPS + SC_MAX_WINS));
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const int rp = tile / tiles_per_row, rem = tile % tiles_per_row;
-            const int j0 = (rem / p.tiles_b) * p.TW, b0 = (rem % p.tiles_b) * p.NB;
+        for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+            const int rp = work / p.pairs_per_row, t0 = (work % p.pairs_per_row) * PAIR;
             const RowPlan row = p.rows[rp];
             if (rp != cur_rp) {
                 // the row class's strip table goes to shared memory once (one coalesced load instead of a dependent global load per strip)
@@ -283,8 +274,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                     if (!mine) continue;
                     const StripDesc sd = s_sd[si - row.strip_begin];
                     mbar_wait_sleep(sempty0 + 8 * my_sb, my_phase);     // producers run ahead: back off, the issuing lane of the MMA warp shares the schedulers
-                    uint8_t *buf = strip_ring + my_sb * p.strip_bytes;
                     const int ch0 = cc * BLOCK_K;
+                    #pragma unroll
+                    for (int tp = 0; tp < PAIR; ++tp) {
+                    const int tq = t0 + tp;
+                    if (tq >= tiles_per_row) break;                         // odd tile count: the pair's second accumulator is never stored
+                    const int j0 = (tq / p.tiles_b) * p.TW, b0 = (tq % p.tiles_b) * p.NB;
+                    uint8_t *buf = strip_ring + my_sb * stage_bytes + tp * p.strip_bytes;
                     if (sd.kind == 0) {
                         if (sd.r1 >= 0 && sd.wy1 != 0.f) fill_strip<SC_UNROLL2, true, SPLIT3>(p, sd, buf, gtid, GT, j0, b0, ch0);
                         else fill_strip<SC_UNROLL1, false, SPLIT3>(p, sd, buf, gtid, GT, j0, b0, ch0);
@@ -309,10 +305,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                             strip_store(buf, p.PS, rho, c, o, SPLIT3);
                         }
                     }
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(sfull0 + 8 * my_sb);
-                    if (gtid == 0 && tile == (int)blockIdx.x && nstamp < 12) strip_stamp(p.flags, 40 + group * 3 + (nstamp++ % 3) );
+                    if (gtid == 0 && work == (int)blockIdx.x && nstamp < 12) strip_stamp(p.flags, 40 + group * 3 + (nstamp++ % 3) );
                 }
             }
         }
@@ -323,16 +320,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
         const int f_base = image * p.F + sub * p.Fs;                     // first filter of this slice in the layer
         const int Fv = min(p.Fs, p.F - sub * p.Fs);                      // valid filters of this slice (the last one may be ragged)
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int rp = tile / tiles_per_row, rem = tile % tiles_per_row;
-            const int j0 = (rem / p.tiles_b) * p.TW, b0 = (rem % p.tiles_b) * p.NB;
+        for (int work = blockIdx.x; work < p.nwork; work += gridDim.x, ++it) {
+            const int rp = work / p.pairs_per_row, t0 = (work % p.pairs_per_row) * PAIR;
             const RowPlan row = p.rows[rp];
             const uint32_t acc = it & 1;
             const bool no_terms = row.strip_begin == row.strip_end;      // a row class nothing contributes to: the accumulator is not written
             mbar_wait_sleep(tmem_full0 + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             if (etid == 0 && it == 0) strip_stamp(p.flags, 4);   // first accumulator complete
-            const uint32_t taddr = tmem_base + acc * (uint32_t)p.Fs + ((uint32_t)(wq * 32) << 16);
+            for (int tp = 0; tp < PAIR; ++tp) {
+            const int tq = t0 + tp;
+            if (tq >= tiles_per_row) break;
+            const int j0 = (tq / p.tiles_b) * p.TW, b0 = (tq % p.tiles_b) * p.NB;
+            const uint32_t taddr = tmem_base + (acc * (uint32_t)PAIR + (uint32_t)tp) * (uint32_t)p.Fs + ((uint32_t)(wq * 32) << 16);
             for (int c0 = 0; c0 < p.Fs; c0 += SC_EPI_COLS) {
                 {   // phase 1: the row owner (TMEM lane) parks 16 raw accumulator columns in the staging tile
                     uint32_t r[16];
@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                 }
                 named_bar_sync(2, 128);   // the staging tile is rewritten by the next column pass
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (etid == 0 && it == 0) strip_stamp(p.flags, 5);   // first epilogue done
@@ -445,12 +446,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
         // swizzled K-major (SBO = 1024 B); both version 1.  The issuing lane only adds row / k offsets to the low words.
         constexpr uint32_t A_HI = (128u >> 4) | (1u << 14), B_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t a_lbo = (((uint32_t)p.PS >> 4) & 0x3FFFu) << 16, a_kstep = (uint32_t)p.PS >> 3, a_lo_plane = (uint32_t)p.PS >> 1;
-        const uint32_t b_lo_plane = (uint32_t)b_plane >> 4;
+        const uint32_t b_lo_plane = (uint32_t)b_plane >> 4, strip_units = (uint32_t)p.strip_bytes >> 4;
         const uint32_t strip0 = smem_u32(strip_ring), bring0 = smem_u32(b_ring);
         uint32_t sb = 0, sphase = 0, ws = 0, wphase = 0, it = 0;
         int cur_rp = -1, nstrips = 0, w_first = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-            const int rp = tile / tiles_per_row;
+        for (int work = blockIdx.x; work < p.nwork; work += gridDim.x, ++it) {
+            const int rp = work / p.pairs_per_row;
             if (rp != cur_rp) {
                 __syncwarp();
                 const RowPlan row = p.rows[rp];
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                 const uint32_t acc = it & 1;
                 mbar_wait(tmem_empty0 + 8 * acc, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Fs;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(PAIR * p.Fs);
                 uint32_t first = 0;
                 for (int cc = 0; cc < p.CC; ++cc)
                     for (int si = 0; si < nstrips; ++si) {
@@ -478,23 +479,26 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                         mbar_wait(sfull0 + 8 * sb, sphase);
                         tc_fence_after();
                         // low descriptor word of the strip: start address (16-byte units) | plane stride; a window adds its start row
-                        const uint32_t a_lo0 = (((strip0 + sb * (uint32_t)p.strip_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+                        const uint32_t a_lo0 = (((strip0 + sb * (uint32_t)stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
                         for (int wi = wr.x; wi < wr.y; ++wi) {
                             const uint32_t a_lo = a_lo0 + (uint32_t)s_start[wi - w_first];
                             mbar_wait(bfull0 + 8 * ws, wphase);
                             tc_fence_after();
                             const uint32_t b_lo = (((bring0 + ws * (uint32_t)b_stage) & 0x3FFFFu) >> 4) | (1u << 16);
                             if (elect_one()) {
+                                for (int tp = 0; tp < PAIR; ++tp) {           // the same weight tile against the strip of every tile of the step
+                                    const uint32_t a_t = a_lo + (uint32_t)tp * strip_units, d_t = d_tmem + (uint32_t)(tp * p.Fs);
 #pragma unroll
-                                for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-                                    const uint64_t da = ((uint64_t)A_HI << 32) | (a_lo + ks * a_kstep);
-                                    const uint64_t db = ((uint64_t)B_HI << 32) | (b_lo + ks * 2u);
-                                    umma_tf32(d_tmem, da, db, idesc, first | (uint32_t)ks);
-                                    if (SPLIT3) {
-                                        const uint64_t da_lo = ((uint64_t)A_HI << 32) | (a_lo + ks * a_kstep + a_lo_plane);
-                                        const uint64_t db_lo = ((uint64_t)B_HI << 32) | (b_lo + ks * 2u + b_lo_plane);
-                                        umma_tf32(d_tmem, da_lo, db, idesc, 1);
-                                        umma_tf32(d_tmem, da, db_lo, idesc, 1);
+                                    for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                                        const uint64_t da = ((uint64_t)A_HI << 32) | (a_t + ks * a_kstep);
+                                        const uint64_t db = ((uint64_t)B_HI << 32) | (b_lo + ks * 2u);
+                                        umma_tf32(d_t, da, db, idesc, first | (uint32_t)ks);
+                                        if (SPLIT3) {
+                                            const uint64_t da_lo = ((uint64_t)A_HI << 32) | (a_t + ks * a_kstep + a_lo_plane);
+                                            const uint64_t db_lo = ((uint64_t)B_HI << 32) | (b_lo + ks * 2u + b_lo_plane);
+                                            umma_tf32(d_t, da_lo, db, idesc, 1);
+                                            umma_tf32(d_t, da, db_lo, idesc, 1);
+                                        }
                                     }
                                 }
                                 umma_commit(bempty0 + 8 * ws);
@@ -521,15 +525,15 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
         const uint8_t *base = p.packed + (size_t)image * p.image_stride + (size_t)sub * p.Fs * (BLOCK_K * 4);
         uint32_t ws = 0, wphase = 1;                       // wphase: parity of the stage's previous consumer phase
         int cur_rp = -1, nstrips = 0, w_first = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            const int rp = tile / tiles_per_row;
+        for (int work = blockIdx.x; work < p.nwork; work += gridDim.x) {
+            const int rp = work / p.pairs_per_row;
             if (rp != cur_rp) {
                 __syncwarp();
                 const RowPlan row = p.rows[rp];
                 nstrips = row.strip_end - row.strip_begin;
                 int w_last = 0;
                 w_first = 0;
-                if (nstrips > 0) { w_first = __ldg(&p.strips[row.strip_begin].win_begin); w_last = __ldg(&p.strips[row.strip_end - 1].win_end); }
+                if (nstrips > 0) { w_first = __ldg(&p.strips[row.strip_begin].win_begin); w_last = __ldg(&p.strips[row.strip_begin + nstrips - 1].win_end); }
                 for (int e = lane; e < nstrips; e += 32)
                     s_strip[e] = make_int2(__ldg(&p.strips[row.strip_begin + e].win_begin), __ldg(&p.strips[row.strip_begin + e].win_end));
                 for (int e = lane; e < w_last - w_first; e += 32) s_tile[e] = __ldg(&p.wins[w_first + e].wtile0) * p.wmul;
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) strip_conv_kernel(const StripPa
                             const uint32_t dst = smem_u32(b_ring + ws * b_stage);
                             const uint8_t *src = base + (size_t)wt * tile_bytes;
                             mbar_arrive_expect_tx(bfull0 + 8 * ws, (uint32_t)b_stage);
-                            if (tile == (int)blockIdx.x && cc == 0 && si == 0 && wi == wr.x) strip_stamp(p.flags, 7);   // first weight tile requested
+                            if (work == (int)blockIdx.x && cc == 0 && si == 0 && wi == wr.x) strip_stamp(p.flags, 7);   // first weight tile requested
                             bulk_g2s(dst, src, (uint32_t)b_plane, bfull0 + 8 * ws);
                             if (SPLIT3) bulk_g2s(dst + b_plane, src + tile_plane, (uint32_t)b_plane, bfull0 + 8 * ws);
                             if (++ws == (uint32_t)p.NWB) { ws = 0; wphase ^= 1; }
@@ -703,28 +707,48 @@ static int launch_strip(const StripLaunch &a, const StripPlan &pl)
     // fits (3xTF32 keeps a second plane of both operands) the filters are sliced further.
     const int budget = 227 * 1024;
     int best_nsb = 0, best_nwb = 0, best_g = 0;
-    for (;; nsub *= 2) {
+    // two tiles of one row class per CTA step (M = 256 through two accumulators) when there is more than a wave of tile pairs: every
+    // weight tile is fetched once per pair and every barrier round trip of the issuing warp covers 8 MMAs.  Measured (B = 64, 64x256):
+    // 7x7 32->32 1.18 -> 0.91 ms (N = 32 MMAs are issue-bound), 128->128 k3 unchanged (269 vs 264 TFLOP/s: producer-bound, and the
+    // ring holds half as many stages) -> only for narrow layers
+    const int tiles_per_row = p.tiles_x * p.tiles_b;
+    p.pair = 1;
+    if (!SPLIT3 && nsub == 1 && nimages == 1 && Fp <= SC_PAIR_MAX_N && tiles_per_row >= 2 && (long)pl.nrows * ((tiles_per_row + 1) / 2) >= 2L * num_sms_cached() &&
+        !(a.flags & SKY_EPI_NO_PAIR) && !getenv("SKY_STRIP_NO_PAIR"))
+        p.pair = 2;
+    for (;;) {
         p.nsub = nsub; p.Fs = Fp / nsub;
         p.tmem_cols = 32;
-        while ((int)p.tmem_cols < 2 * p.Fs) p.tmem_cols <<= 1;
+        while ((int)p.tmem_cols < 2 * p.pair * p.Fs) p.tmem_cols <<= 1;
         const int gs[3] = { 4, 2, 1 };
         for (int gi = 0; gi < 3 && !best_nsb && p.tmem_cols <= 512; ++gi) {
             const int G = gs[gi];
             for (int nsb = 2 * G; nsb >= G && nsb >= 2 && !best_nsb; nsb -= G)
                 for (int nwb = 6; nwb >= 3; --nwb)
-                    if (L::total_bytes(p.PS, p.Fs, nsb, nwb) <= budget) { best_nsb = nsb; best_nwb = nwb; best_g = G; break; }
+                    if (L::total_bytes(p.PS, p.Fs, nsb, nwb, p.pair) <= budget) { best_nsb = nsb; best_nwb = nwb; best_g = G; break; }
         }
         if (best_nsb) break;
+        if (p.pair == 2) { p.pair = 1; continue; }           // pairs do not fit: single tiles
         if (Fp % (32 * nsub) != 0) return SKY_ERR_UNSUPPORTED;
+        nsub *= 2;                                            // nothing fits: slice the filters further
     }
     const int nslices = nimages * nsub;
+    p.pairs_per_row = (tiles_per_row + p.pair - 1) / p.pair;
+    p.nwork = pl.nrows * p.pairs_per_row;
     p.NSB = best_nsb; p.NWB = best_nwb; p.G = best_g; p.group_threads = SC_PROD_THREADS / best_g;
-    const int smem = L::total_bytes(p.PS, p.Fs, p.NSB, p.NWB);
-    SKY_ENSURE_DYN_SMEM((strip_conv_kernel<SPLIT3>), 227 * 1024);
+    const int smem = L::total_bytes(p.PS, p.Fs, p.NSB, p.NWB, p.pair);
     int gx = num_sms_cached() / nslices;
     if (gx < 1) gx = 1;
-    if (gx > p.ntiles) gx = p.ntiles;
-    strip_conv_kernel<SPLIT3><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);
+    if (gx > p.nwork) gx = p.nwork;
+    if (p.pair == 2) {
+        if constexpr (!SPLIT3) {
+            SKY_ENSURE_DYN_SMEM((strip_conv_kernel<false, 2>), 227 * 1024);
+            strip_conv_kernel<false, 2><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);
+        }
+    } else {
+        SKY_ENSURE_DYN_SMEM((strip_conv_kernel<SPLIT3, 1>), 227 * 1024);
+        strip_conv_kernel<SPLIT3, 1><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);
+    }
     SKY_CHECK_LAUNCH();
     return SKY_OK;
 }
@@ -857,7 +881,7 @@ extern "C" int sky_da_conv2d_bwd_data_strip(const float *dy, const float *offset
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension (B=%d h=%d w=%d C=%d F=%d)", B, h, w, C, F);
     SKY_REQUIRE(k % 2 == 1 && k >= 3 && k <= 15, SKY_ERR_UNSUPPORTED, "kernel_size %d outside the supported odd range 3..15", k);
     SKY_REQUIRE(F % BLOCK_K == 0 && C <= 256, SKY_ERR_UNSUPPORTED, "the strip data gradient needs F %% 32 == 0 and C <= 256 (C=%d F=%d)", C, F);
-    SKY_REQUIRE(!(epilogue_flags & ~SKY_EPI_MASK), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK only");
+    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_MASK | SKY_EPI_NO_PAIR)), SKY_ERR_INVALID, "the data gradient takes SKY_EPI_MASK only");
     SKY_REQUIRE(!(epilogue_flags & SKY_EPI_MASK) || (aux && !accumulate), SKY_ERR_INVALID, "SKY_EPI_MASK needs its mask source and excludes accumulate");
     SKY_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)packed_t & 15) == 0, SKY_ERR_INVALID, "dy, dx and packed must be 16-byte aligned");
     SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
@@ -869,7 +893,7 @@ extern "C" int sky_da_conv2d_bwd_data_strip(const float *dy, const float *offset
     s.x = dy; s.packed = packed_t; s.bias = nullptr; s.y = dx; s.stats = nullptr;
     s.residual = accumulate ? dx : aux;                      // accumulate: each output element is read and rewritten by the one thread that owns it
     s.B = B; s.H = h; s.W = w; s.C = F; s.OH = h; s.OW = w; s.F = C; s.ldF = C; s.nimages = 1; s.image_stride = 0;
-    s.k = k; s.flags = accumulate ? SKY_EPI_RESIDUAL : epilogue_flags; s.math_mode = math_mode; s.da = 2; s.slope = slope;
+    s.k = k; s.flags = (accumulate ? SKY_EPI_RESIDUAL : (epilogue_flags & SKY_EPI_MASK)) | (epilogue_flags & SKY_EPI_NO_PAIR); s.math_mode = math_mode; s.da = 2; s.slope = slope;
     s.stream = (cudaStream_t)stream;
     int pht, pwt;
     pad_axis(h, k, &s.ph0, &pht);

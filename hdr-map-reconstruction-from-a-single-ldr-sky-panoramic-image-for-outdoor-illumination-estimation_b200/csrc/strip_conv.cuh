@@ -47,6 +47,19 @@ struct WeffTerm {
     float coef;
 };
 
+// Weight gradient over a forward plan (strip_wgrad.cu).  One MMA group = one tcgen05.mma chain whose A operand starts at strip row
+// `start_row`; its 128 accumulator lanes are either the (up to) 128 channels of window win[0] (layers with C >= 64) or the 32 channels
+// of the four windows win[0..3] at consecutive column shifts (C == 32: a shift of one column is exactly one MN atom of the operand).
+struct WgGroup {
+    int start_row;
+    int win[4];                    // window index per 32-lane quarter, -1: the quarter is not stored
+};
+// One accumulation unit: the groups of one strip that share TMEM (the strip and the dy tile are produced once per pixel tile for all of them).
+struct WgUnit {
+    int row, strip;
+    int group_begin, group_end;
+};
+
 struct StripPlan {                 // host view of a cached plan; the arrays live on the device
     const RowPlan *rows = nullptr;
     const StripDesc *strips = nullptr;
@@ -58,6 +71,9 @@ struct StripPlan {                 // host view of a cached plan; the arrays liv
     int TW = 0, NB = 0, SR = 0;           // tile width (columns), panoramas per tile, strip rows (multiple of 8)
     int max_strips_row = 0, max_wins_row = 0, exact_strips = 0;
     int weff = 0;                         // 1: weight tiles are per-window effective weights (tile = window * CC + cc)
+    const WgUnit *wg_units = nullptr;     // weight-gradient plans only
+    const WgGroup *wg_groups = nullptr;
+    int n_wg_units = 0, n_wg_groups = 0, max_groups_unit = 0, span_max = 0;
 };
 
 // plans are built once per layer geometry and cached for the life of the process (host tables + device copies)
@@ -67,8 +83,32 @@ int get_plan_da(const float *offsets_host, int h, int w, int k, const StripPlan 
 int get_plan_plain(int h, int w, int k, int stride, int transposed, int out_h, int out_w, int tp_ph0, int tp_pw0, const StripPlan **out,
                    bool device = true);
 
+// weight-gradient flavour of the forward plans: tiles of 8 columns x 8 panoramas (a column shift = 8 strip rows = two K atoms of the
+// MN-major operand), `wpg` windows per MMA group (1, or 4 for 32-channel layers), at most `gmax` groups per unit
+int get_plan_da_wgrad(const float *offsets_host, int h, int w, int k, int wpg, int gmax, const StripPlan **out, bool device = true);
+int get_plan_plain_wgrad(int h, int w, int k, int stride, int out_h, int out_w, int wpg, int gmax, const StripPlan **out, bool device = true);
+
 // strip kernel behind sky_conv2d_fwd / the data gradients (plain SAME conv, C % 32 == 0); SKY_ERR_UNSUPPORTED (no error text) when it
 // does not apply
 int launch_fwd_strip_plain(const FwdArgs &a);
+
+// weight gradient on the strip formulation (strip_wgrad.cu); offsets_host != NULL: distortion-aware layer, else plain SAME conv of
+// `stride`.  dw [k*k*C, F] is ADDED to (the caller zeroes it).  SKY_ERR_UNSUPPORTED (no error text) when it does not apply.
+int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_host, float *dw, int B, int h, int w, int C, int F, int k,
+                       int stride, cudaStream_t stream);
+
+#ifdef __CUDACC__
+// The reference's treatment of a column index (distortion_aware_ops.py:76-77 on the float coordinate, :90-91 on the integer corners),
+// restated on the integer part: `q` is a column in the PADDED frame before any wrap.  Returns the unpadded column, or -1 for a zero.
+__device__ __forceinline__ int da_map_col(int q, int in_w, int pw0, int W)
+{
+    if (q < 0) q += in_w;                 // :76 (x < 0 -> x + in_w; the result is <= in_w - 1, so :77 does not fire after it)
+    else if (q > in_w - 1) q -= in_w;     // :77
+    if (q < 0) q += in_w;                 // :90
+    if (q > in_w - 1) q -= in_w;          // :91
+    const int c = q - pw0;
+    return (c >= 0 && c < W) ? c : -1;
+}
+#endif
 
 }  // namespace sky

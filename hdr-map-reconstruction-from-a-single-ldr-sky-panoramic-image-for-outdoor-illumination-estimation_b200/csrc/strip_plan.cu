@@ -71,6 +71,8 @@ struct HostPlan {
     std::vector<WinDesc> wins;
     std::vector<int> term_begin;
     std::vector<WeffTerm> terms;
+    std::vector<WgUnit> wg_units;
+    std::vector<WgGroup> wg_groups;
     StripPlan dev;
     bool uploaded = false;
 };
@@ -132,6 +134,7 @@ int finish_plan(HostPlan &hp, int TW, int NB, int span_max, int ncols, int ocs, 
     StripPlan &d = hp.dev;
     d.nrows = (int)hp.rows.size(); d.nstrips = (int)hp.strips.size(); d.nwins = (int)hp.wins.size(); d.nterms = (int)hp.terms.size();
     d.ncols = ncols; d.ocs = ocs; d.TW = TW; d.NB = NB; d.weff = weff;
+    d.span_max = span_max;
     d.SR = round_up((TW + span_max) * NB, 8);
     if (d.SR < BLOCK_M) d.SR = BLOCK_M;
     for (const RowPlan &r : hp.rows) {
@@ -158,8 +161,48 @@ int ensure_device(HostPlan &hp)
         if ((rc = upload(hp.term_begin, &d.term_begin)) != SKY_OK) return rc;
         if ((rc = upload(hp.terms, &d.terms)) != SKY_OK) return rc;
     }
+    if (!hp.wg_units.empty()) {
+        if ((rc = upload(hp.wg_units, &d.wg_units)) != SKY_OK) return rc;
+        if ((rc = upload(hp.wg_groups, &d.wg_groups)) != SKY_OK) return rc;
+    }
     hp.uploaded = true;
     return SKY_OK;
+}
+
+// Weight-gradient units over a finished forward plan: the windows of a strip become MMA groups (one window each, or up to four windows
+// at consecutive shifts for 32-channel layers), at most gmax groups (accumulators in TMEM) per unit.
+void build_wgrad_units(HostPlan &hp, int NB, int wpg, int gmax)
+{
+    for (int r = 0; r < (int)hp.rows.size(); ++r)
+        for (int si = hp.rows[r].strip_begin; si < hp.rows[r].strip_end; ++si) {
+            const StripDesc &sd = hp.strips[si];
+            std::vector<WgGroup> groups;
+            for (int wi = sd.win_begin; wi < sd.win_end;) {
+                WgGroup g;
+                g.start_row = hp.wins[wi].start_row;
+                g.win[0] = wi; g.win[1] = g.win[2] = g.win[3] = -1;
+                int nx = wi + 1;
+                if (wpg == 4)
+                    for (; nx < sd.win_end; ++nx) {                 // windows are sorted by shift, shifts are distinct
+                        const int q = (hp.wins[nx].start_row - g.start_row) / NB;
+                        if (q > 3) break;
+                        g.win[q] = nx;
+                    }
+                groups.push_back(g);
+                wi = nx;
+            }
+            for (size_t g0 = 0; g0 < groups.size(); g0 += gmax) {
+                WgUnit u;
+                u.row = r; u.strip = si;
+                u.group_begin = (int)hp.wg_groups.size();
+                for (size_t g = g0; g < groups.size() && g < g0 + gmax; ++g) hp.wg_groups.push_back(groups[g]);
+                u.group_end = (int)hp.wg_groups.size();
+                hp.wg_units.push_back(u);
+                hp.dev.max_groups_unit = std::max(hp.dev.max_groups_unit, u.group_end - u.group_begin);
+            }
+        }
+    hp.dev.n_wg_units = (int)hp.wg_units.size();
+    hp.dev.n_wg_groups = (int)hp.wg_groups.size();
 }
 
 // One kernel row of one output row: the vertical geometry (shared by its k taps) and the horizontal terms by column shift.
@@ -230,13 +273,14 @@ int analyse_kernel_row(const float *off, int h, int w, int k, int i, int a, bool
     return SKY_OK;
 }
 
-int build_da(const float *off, int h, int w, int k, HostPlan &hp)
+// force_tw > 0: tile geometry and strip span of the weight-gradient plans instead of the forward kernel's
+int build_da(const float *off, int h, int w, int k, HostPlan &hp, int force_tw = 0, int force_nb = 0, int force_cap = 0)
 {
     const int k2 = k * k;
     int ph0, pht;
     pad_axis(h, k, &ph0, &pht);
-    const int TW = pow2_floor(std::min(w, BLOCK_M)), NB = BLOCK_M / TW;
-    const int cap = (SR_MAX - BLOCK_M) / NB;
+    const int TW = force_tw > 0 ? force_tw : pow2_floor(std::min(w, BLOCK_M)), NB = force_tw > 0 ? force_nb : BLOCK_M / TW;
+    const int cap = force_tw > 0 ? force_cap : (SR_MAX - BLOCK_M) / NB;
     int span_max = 0;
     for (int i = 0; i < h; ++i) {
         RowPlan rp;
@@ -326,7 +370,8 @@ int build_da_transposed(const float *off, int h, int w, int k, HostPlan &hp)
 // plain SAME convolution (tf.nn.conv2d, ops.py:41) of stride 1 / 2, or — transposed != 0 — the data gradient of one run as a forward
 // pass over dy (same tap convention as the direct kernel: output pixel (i, j) reads tap (a, b) at ((i + a - ph0) / s, (j + b - pw0) / s)
 // when both divisions are exact)
-int build_plain(int h, int w, int k, int stride, int transposed, int OH, int OW, int tp_ph0, int tp_pw0, HostPlan &hp)
+int build_plain(int h, int w, int k, int stride, int transposed, int OH, int OW, int tp_ph0, int tp_pw0, HostPlan &hp, int force_tw = 0,
+                int force_nb = 0, int force_cap = 0)
 {
     int ph0 = tp_ph0, pw0 = tp_pw0;
     if (!transposed) {
@@ -336,8 +381,8 @@ int build_plain(int h, int w, int k, int stride, int transposed, int OH, int OW,
     const int col_classes = (transposed && stride == 2) ? 2 : 1;
     if (col_classes == 2 && (OW & 1)) return SKY_ERR_UNSUPPORTED;
     const int ncols = OW / col_classes;
-    const int TW = pow2_floor(std::min(ncols, BLOCK_M)), NB = BLOCK_M / TW;
-    const int cap = (SR_MAX - BLOCK_M) / NB;
+    const int TW = force_tw > 0 ? force_tw : pow2_floor(std::min(ncols, BLOCK_M)), NB = force_tw > 0 ? force_nb : BLOCK_M / TW;
+    const int cap = force_tw > 0 ? force_cap : (SR_MAX - BLOCK_M) / NB;
     int span_max = 0;
     for (int io = 0; io < OH; ++io)
         for (int pj = 0; pj < col_classes; ++pj) {
@@ -441,6 +486,52 @@ int get_plan_plain(int h, int w, int k, int stride, int transposed, int out_h, i
         HostPlan *hp = new HostPlan();
         const int rc = build_plain(h, w, k, stride, transposed, out_h, out_w, tp_ph0, tp_pw0, *hp);
         if (rc != SKY_OK) { delete hp; return rc; }
+        it = g_plain.emplace(key, hp).first;
+    }
+    if (device) {
+        const int rc = ensure_device(*it->second);
+        if (rc != SKY_OK) return rc;
+    }
+    *out = &it->second->dev;
+    return SKY_OK;
+}
+
+// weight-gradient plans share the caches: the `transposed` slot of the key carries 100 + 1000 * wpg + gmax
+constexpr int WG_TW = 8, WG_NB = 8;
+static int wg_cap(int wpg) { return wpg == 4 ? 8 : 4; }
+
+int get_plan_da_wgrad(const float *offsets_host, int h, int w, int k, int wpg, int gmax, const StripPlan **out, bool device)
+{
+    if (h <= 0 || w <= 0 || k < 3 || !(k & 1) || gmax < 1) return SKY_ERR_UNSUPPORTED;
+    const auto key = std::make_tuple(h, w, k, 100 + 1000 * wpg + gmax, fnv1a(offsets_host, (size_t)h * k * k * 2 * sizeof(float)));
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_da.find(key);
+    if (it == g_da.end()) {
+        HostPlan *hp = new HostPlan();
+        const int rc = build_da(offsets_host, h, w, k, *hp, WG_TW, WG_NB, wg_cap(wpg));
+        if (rc != SKY_OK) { delete hp; return rc; }
+        build_wgrad_units(*hp, WG_NB, wpg, gmax);
+        it = g_da.emplace(key, hp).first;
+    }
+    if (device) {
+        const int rc = ensure_device(*it->second);
+        if (rc != SKY_OK) return rc;
+    }
+    *out = &it->second->dev;
+    return SKY_OK;
+}
+
+int get_plan_plain_wgrad(int h, int w, int k, int stride, int out_h, int out_w, int wpg, int gmax, const StripPlan **out, bool device)
+{
+    if (gmax < 1) return SKY_ERR_UNSUPPORTED;
+    const auto key = std::make_tuple(h, w, k, stride, 100 + 1000 * wpg + gmax, out_h, out_w, 0, 0);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_plain.find(key);
+    if (it == g_plain.end()) {
+        HostPlan *hp = new HostPlan();
+        const int rc = build_plain(h, w, k, stride, 0, out_h, out_w, 0, 0, *hp, WG_TW, WG_NB, wg_cap(wpg));
+        if (rc != SKY_OK) { delete hp; return rc; }
+        build_wgrad_units(*hp, WG_NB, wpg, gmax);
         it = g_plain.emplace(key, hp).first;
     }
     if (device) {

@@ -35,6 +35,24 @@ int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, in
     return SKY_OK;
 }
 
+// dy [B, OH, OW, F] as the B operand of the strip weight gradient: dimensions ordered (f, panorama, column, row) so that a box of
+// (32 filters, 8 panoramas, 8 columns, 1 row) lands in shared memory as rows = column * 8 + panorama of 128 bytes, in the 32-byte-atom
+// 128-byte swizzle the MN-major TF32 operand descriptor expects (SWIZZLE_128B_BASE32B); out-of-range panoramas / columns / filters are zero.
+int encode_dy_wgrad_tensor_map(CUtensorMap *out, const float *base, int B, int OH, int OW, int F, int box_cols)
+{
+    EncodeTiledFn enc = get_encoder();
+    SKY_REQUIRE(enc != nullptr, SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = { (cuuint64_t)F, (cuuint64_t)B, (cuuint64_t)OW, (cuuint64_t)OH };
+    cuuint64_t strides[3] = { (cuuint64_t)OH * OW * F * 4, (cuuint64_t)F * 4, (cuuint64_t)OW * F * 4 };
+    cuuint32_t box[4] = { 32, 8, (cuuint32_t)box_cols, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKY_REQUIRE(r == CUDA_SUCCESS, SKY_ERR_CUDA, "cuTensorMapEncodeTiled (dy, weight gradient) failed with CUresult %d (B=%d OH=%d OW=%d F=%d)", (int)r,
+                B, OH, OW, F);
+    return SKY_OK;
+}
+
 int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows)
 {
     EncodeTiledFn enc = get_encoder();

@@ -203,3 +203,21 @@ def test_full_size_properties(pkg, ops):
     rhs = 0.5 * (y[:4] - layer.bias) + (layer(x2) - layer.bias)
     r = (torch.linalg.norm((lhs - rhs).double()) / torch.linalg.norm(rhs.double())).item()
     assert r <= 2 * TOL_TF32, r
+
+
+def test_tile_pairs_equal_single_tiles(pkg):
+    """Large launches process two tiles of a row class per weight tile (M = 256 through two accumulators).  Per tile the MMA sequence is
+    the same as without pairing, so the results are bit-identical — also when a row class has an odd number of tiles (the last pair's
+    second accumulator is never stored)."""
+    torch.manual_seed(1)
+    for (B, h, w, C, F) in ((3, 150, 128, 32, 32), (32, 32, 128, 64, 24)):
+        x = torch.randn(B, h, w, C, device="cuda")
+        layer = pkg.conv2d(F, kernel_size=3, math_mode="tf32")
+        layer.build(tuple(x.shape))
+        layer.bias.normal_()
+        stats_a = torch.zeros(B, F, 2, dtype=torch.float64, device="cuda")
+        stats_b = torch.zeros_like(stats_a)
+        paired = layer(x, stats=stats_a)
+        single = layer(x, stats=stats_b, extra_flags=pkg._lib.EPI_NO_PAIR)
+        assert torch.equal(paired, single)
+        assert torch.allclose(stats_a, stats_b, rtol=1e-12, atol=1e-9)
