@@ -86,6 +86,7 @@ SIGNATURES = {
     "sky_vgg_preprocess": (_i, [_vp, _vp, ctypes.c_long, _f, _f, _f, _vp]),
     "sky_sun_radiance": (_i, [_vp] * 5 + [_i, _i, _f, _vp]),
     "sky_conv2d_transpose_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sky_conv2d_pack_weights_t": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "sky_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 8 + [_f, _i, _vp]),
     "sky_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 9 + [_vp]),
     "sky_bn_train_stats": (_i, [_vp] * 5 + [_i, _i, _i, _i, _f, _vp]),

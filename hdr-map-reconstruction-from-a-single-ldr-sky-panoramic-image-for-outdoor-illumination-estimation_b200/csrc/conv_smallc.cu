@@ -14,8 +14,10 @@ constexpr int SC_FMAX = 32;
 // bias, optional LeakyReLU, coalesced stores, per-(sample, filter) moments for the instance norm that follows
 __device__ __forceinline__ void smallc_epilogue(float (&acc)[SC_FMAX], const float *__restrict__ bias, float *__restrict__ y,
                                                 double *__restrict__ stats, float *red, int b, int i, int j, int h, int w, int F,
-                                                int flags, float slope)
+                                                int flags, float slope, int ldF = 0)
 {
+    // F = filters of this launch (<= 32); ldF = filters of the layer when the launch covers a slice of them (bias, y, stats pre-offset)
+    if (ldF == 0) ldF = F;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ok = j < w;
 #pragma unroll
@@ -25,8 +27,8 @@ __device__ __forceinline__ void smallc_epilogue(float (&acc)[SC_FMAX], const flo
         acc[f] = v;
     }
     if (ok) {
-        float *dst = y + (((size_t)b * h + i) * w + j) * F;
-        if (F == SC_FMAX) {
+        float *dst = y + (((size_t)b * h + i) * w + j) * ldF;
+        if (F == SC_FMAX && (ldF & 3) == 0) {
 #pragma unroll
             for (int f4 = 0; f4 < SC_FMAX / 4; ++f4)
                 reinterpret_cast<float4 *>(dst)[f4] = make_float4(acc[4 * f4], acc[4 * f4 + 1], acc[4 * f4 + 2], acc[4 * f4 + 3]);
@@ -52,15 +54,16 @@ __device__ __forceinline__ void smallc_epilogue(float (&acc)[SC_FMAX], const flo
             const int f = tid >> 1, which = tid & 1;
             double s = 0.0;
             for (int wq = 0; wq < SC_THREADS / 32; ++wq) s += (double)red[(wq * SC_FMAX + f) * 2 + which];
-            atomicAdd(stats + ((size_t)b * F + f) * 2 + which, s);
+            atomicAdd(stats + ((size_t)b * ldF + f) * 2 + which, s);
         }
     }
 }
 
+// blockIdx.x = column tile * nslices + filter slice (slices of 32 filters: VGG conv1_1 has 64)
 template <int C>
 __global__ void __launch_bounds__(SC_THREADS)
 conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kernel, const float *__restrict__ bias,
-                     float *__restrict__ y, double *__restrict__ stats, int h, int w, int F, int k, int flags, float slope)
+                     float *__restrict__ y, double *__restrict__ stats, int h, int w, int Ftot, int nslices, int k, int flags, float slope)
 {
     extern __shared__ float sm[];
     const int r = k / 2, pw = SC_THREADS + k - 1;
@@ -68,11 +71,12 @@ conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kern
     float *patch = sm + k * k * C * SC_FMAX;  // [k][pw][C]
     float *red = patch + k * pw * C;          // [4 warps][SC_FMAX][2]
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * SC_THREADS, i = blockIdx.y, b = blockIdx.z;
+    const int slice = blockIdx.x % nslices, f0 = slice * SC_FMAX, F = min(SC_FMAX, Ftot - f0);
+    const int x0 = (blockIdx.x / nslices) * SC_THREADS, i = blockIdx.y, b = blockIdx.z;
 
     for (int e = tid; e < k * k * C * SC_FMAX; e += SC_THREADS) {
         const int f = e % SC_FMAX, row = e / SC_FMAX;
-        wts[e] = f < F ? kernel[(size_t)row * F + f] : 0.f;
+        wts[e] = f < F ? kernel[(size_t)row * Ftot + f0 + f] : 0.f;
     }
     for (int e = tid; e < k * pw * C; e += SC_THREADS) {
         const int c = e % C, px = (e / C) % pw, a = e / (C * pw);
@@ -101,7 +105,7 @@ conv2d_smallc_kernel(const float *__restrict__ x, const float *__restrict__ kern
                 }
             }
         }
-    smallc_epilogue(acc, bias, y, stats, red, b, i, x0 + tid, h, w, F, flags, slope);
+    smallc_epilogue(acc, bias ? bias + f0 : nullptr, y + f0, stats ? stats + 2 * f0 : nullptr, red, b, i, x0 + tid, h, w, F, flags, slope, Ftot);
 }
 
 
@@ -329,19 +333,22 @@ extern "C" int sky_conv2d_smallc_fwd(const float *x, const float *kernel, const 
 {
     SKY_REQUIRE(x && kernel && y, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0, SKY_ERR_INVALID, "non-positive dimension");
-    SKY_REQUIRE(C >= 1 && C <= 4 && F >= 1 && F <= SC_FMAX && k % 2 == 1 && k <= 11, SKY_ERR_UNSUPPORTED,
-                "small-C conv covers C <= 4, F <= 32, odd k <= 11 (got C=%d F=%d k=%d)", C, F, k);
-    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_LEAKY_RELU)), SKY_ERR_UNSUPPORTED, "small-C conv supports only the LeakyReLU epilogue");
-    SKY_REQUIRE(F != SC_FMAX || ((uintptr_t)y & 15) == 0, SKY_ERR_INVALID, "y must be 16-byte aligned");
+    SKY_REQUIRE(C >= 1 && C <= 4 && F >= 1 && F <= 256 && k % 2 == 1 && k <= 11, SKY_ERR_UNSUPPORTED,
+                "small-C conv covers C <= 4, F <= 256, odd k <= 11 (got C=%d F=%d k=%d)", C, F, k);
+    SKY_REQUIRE(!(epilogue_flags & ~(SKY_EPI_LEAKY_RELU | SKY_EPI_RELU)) && (epilogue_flags & (SKY_EPI_LEAKY_RELU | SKY_EPI_RELU)) != (SKY_EPI_LEAKY_RELU | SKY_EPI_RELU),
+                SKY_ERR_UNSUPPORTED, "small-C conv supports the LeakyReLU or the ReLU epilogue");
+    SKY_REQUIRE(((uintptr_t)y & 15) == 0, SKY_ERR_INVALID, "y must be 16-byte aligned");
+    if (epilogue_flags & SKY_EPI_RELU) { epilogue_flags = SKY_EPI_LEAKY_RELU; slope = 0.f; }      // ReLU = LeakyReLU of slope 0
     const int pw = SC_THREADS + k - 1;
+    const int nslices = (F + SC_FMAX - 1) / SC_FMAX;
     const size_t smem = ((size_t)k * k * C * SC_FMAX + (size_t)k * pw * C + 4 * SC_FMAX * 2) * sizeof(float);
-    dim3 grid((w + SC_THREADS - 1) / SC_THREADS, h, B);
+    dim3 grid(((w + SC_THREADS - 1) / SC_THREADS) * nslices, h, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define SKY_LAUNCH_SC(CC)                                                                                                     \
     do {                                                                                                                      \
         SKY_ENSURE_DYN_SMEM(conv2d_smallc_kernel<CC>, 200 * 1024);                    \
                                                                                                                              \
-        conv2d_smallc_kernel<CC><<<grid, SC_THREADS, smem, st>>>(x, kernel, bias, y, stats, h, w, F, k, epilogue_flags, slope); \
+        conv2d_smallc_kernel<CC><<<grid, SC_THREADS, smem, st>>>(x, kernel, bias, y, stats, h, w, F, nslices, k, epilogue_flags, slope); \
     } while (0)
     switch (C) {
         case 1: SKY_LAUNCH_SC(1); break;

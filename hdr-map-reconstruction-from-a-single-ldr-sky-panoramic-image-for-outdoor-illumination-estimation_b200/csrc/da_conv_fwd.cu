@@ -23,29 +23,76 @@ constexpr int NUM_THREADS = NUM_PRODUCER_THREADS + 64;   // + MMA warp + weight-
 // k-block order: for C % 32 == 0 the tiles are stored chunk-major, kb = cc * k2 + tap (the order the conv kernels walk K:
 // all taps of one 32-channel chunk, then the next chunk), so consecutive taps of a chunk are contiguous; otherwise
 // k-block kb simply covers kernel rows [32 kb, 32 kb + 32).
-__global__ void da_pack_weights_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int K, int F, int Fp,
-                                       int KB, int planes, int C, int k2, int ldk)
+// One block per (k-block, 32 filters) sub-tile: the variable is read along its filters (128-byte rows, coalesced), the tile is written
+// along its k values (128-byte rows, 16 bytes per thread): the transpose goes through shared memory.
+__global__ void __launch_bounds__(256) da_pack_weights_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int K, int F, int Fp,
+                                                             int KB, int planes, int C, int k2, int ldk)
 {
-    const long total = (long)KB * Fp * BLOCK_K;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int kk = (int)(e % BLOCK_K);
-        const int n = (int)((e / BLOCK_K) % Fp);
-        const int kb = (int)(e / ((long)BLOCK_K * Fp));
-        int kidx = kb * BLOCK_K + kk;
+    __shared__ float wsm[BLOCK_K][33];
+    const int nsub = (Fp + 31) / 32;
+    const size_t tile_floats = (size_t)Fp * BLOCK_K;
+    for (int work = blockIdx.x; work < KB * nsub; work += gridDim.x) {
+        const int kb = work / nsub, n0 = (work - kb * nsub) * 32;
+        int kbase = kb * BLOCK_K;
         if (C % BLOCK_K == 0) {
             const int cc = kb / k2, t = kb % k2;
-            kidx = t * C + cc * BLOCK_K + kk;
+            kbase = t * C + cc * BLOCK_K;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < BLOCK_K * 32; e += 256) {
+            const int kk = e >> 5, n = n0 + (e & 31);
+            float v = 0.f;
+            if (kbase + kk < K && n < F) v = __ldg(kernel + (size_t)(kbase + kk) * ldk + n);
+            wsm[kk][e & 31] = v;
+        }
+        __syncthreads();
+        uint8_t *tile = reinterpret_cast<uint8_t *>(packed + (size_t)kb * planes * tile_floats);
+        {
+            const int chunk = threadIdx.x & 7, nl = threadIdx.x >> 3, n = n0 + nl;
+            if (n < Fp) {
+                const float v0 = wsm[4 * chunk][nl], v1 = wsm[4 * chunk + 1][nl], v2 = wsm[4 * chunk + 2][nl], v3 = wsm[4 * chunk + 3][nl];
+                uint4 hi;
+                hi.x = f32_to_tf32_rna(v0); hi.y = f32_to_tf32_rna(v1); hi.z = f32_to_tf32_rna(v2); hi.w = f32_to_tf32_rna(v3);
+                const uint32_t o = sw128_offset((uint32_t)n, (uint32_t)chunk);
+                *reinterpret_cast<uint4 *>(tile + o) = hi;
+                if (planes == 2) {
+                    uint4 lo;
+                    lo.x = f32_to_tf32_rna(v0 - __uint_as_float(hi.x)); lo.y = f32_to_tf32_rna(v1 - __uint_as_float(hi.y));
+                    lo.z = f32_to_tf32_rna(v2 - __uint_as_float(hi.z)); lo.w = f32_to_tf32_rna(v3 - __uint_as_float(hi.w));
+                    *reinterpret_cast<uint4 *>(tile + tile_floats * 4 + o) = lo;
+                }
+            }
+        }
+    }
+}
+
+// The same image for the FLIPPED, TRANSPOSED kernel of a plain conv (the data gradient run as a forward pass over dy, conv_bwd.cu),
+// straight from the layer variable: the virtual kernel is kernelT[(t' * F + f) * C + c] = kernel[((k2 - 1 - t') * C + c) * F + f], its
+// "input channels" are the layer's F filters and its "filters" the C channels (rows n of a tile; c0 = first channel of the slice).
+// A tile row holds 32 consecutive f of one (t', c): the reads are contiguous along kk, no transposed copy in global memory.
+__global__ void da_pack_weights_t_kernel(const float *__restrict__ kernel, float *__restrict__ packed, int Kt, int Cs, int Np, int KB,
+                                         int planes, int C, int F, int k2, int c0)
+{
+    const long total = (long)KB * Np * BLOCK_K;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % BLOCK_K);
+        const int n = (int)((e / BLOCK_K) % Np);
+        const int kb = (int)(e / ((long)BLOCK_K * Np));
+        int kidx = kb * BLOCK_K + kk;
+        if (F % BLOCK_K == 0) {
+            const int cc = kb / k2, t = kb % k2;
+            kidx = t * F + cc * BLOCK_K + kk;
         }
         float v = 0.f;
-        if (kidx < K && n < F) v = kernel[(size_t)kidx * ldk + n];
+        if (kidx < Kt && n < Cs) {
+            const int tp = kidx / F, f = kidx - tp * F;
+            v = __ldg(kernel + ((size_t)(k2 - 1 - tp) * C + c0 + n) * F + f);
+        }
         const uint32_t hi = f32_to_tf32_rna(v);
-        const size_t tile_floats = (size_t)Fp * BLOCK_K;
+        const size_t tile_floats = (size_t)Np * BLOCK_K;
         const size_t o = (sw128_offset((uint32_t)n, (uint32_t)(kk >> 2)) >> 2) + (kk & 3);
         packed[((size_t)kb * planes + 0) * tile_floats + o] = __uint_as_float(hi);
-        if (planes == 2) {
-            const float lo = v - __uint_as_float(hi);
-            packed[((size_t)kb * planes + 1) * tile_floats + o] = __uint_as_float(f32_to_tf32_rna(lo));
-        }
+        if (planes == 2) packed[((size_t)kb * planes + 1) * tile_floats + o] = __uint_as_float(f32_to_tf32_rna(v - __uint_as_float(hi)));
     }
 }
 
@@ -578,12 +625,32 @@ extern "C" int sky_da_pack_weights(const float *kernel, void *packed, int C, int
     uint8_t *dst = (uint8_t *)packed;
     for (int s = 0; s < slice_count(F); ++s) {
         const int Fs = slice_filters(F, s), Fp = f_pad_of(Fs);
-        const long total = (long)KB * Fp * BLOCK_K;
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        const int work = KB * ((Fp + 31) / 32), blocks = work < 148 * 8 ? work : 148 * 8;
         da_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel + 256 * s, (float *)dst, K, Fs, Fp, KB, planes, C, k * k, F);
         SKY_CHECK_LAUNCH();
         dst += slice_bytes(C, Fs, k, math_mode);
+    }
+    return SKY_OK;
+}
+
+// Packed image of the flipped, transposed kernel of a plain conv layer [k*k*C, F]: byte for byte what sky_conv2d_transpose_weights
+// (flip = 1) followed by sky_da_pack_weights(F, C, k) produces (sky_da_packed_weight_bytes(F, C, k, math_mode) bytes), in one pass.
+extern "C" int sky_conv2d_pack_weights_t(const float *kernel, void *packed, int C, int F, int k, int math_mode, void *stream)
+{
+    SKY_REQUIRE(kernel && packed, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(C > 0 && F > 0 && k > 0, SKY_ERR_INVALID, "non-positive dimension");
+    SKY_REQUIRE(math_mode == SKY_MATH_TF32 || math_mode == SKY_MATH_3XTF32, SKY_ERR_INVALID, "unknown math_mode %d", math_mode);
+    const int Kt = k * k * F, KB = (Kt + BLOCK_K - 1) / BLOCK_K;
+    const int planes = math_mode == SKY_MATH_3XTF32 ? 2 : 1;
+    uint8_t *dst = (uint8_t *)packed;
+    for (int s = 0; s < slice_count(C); ++s) {
+        const int Cs = slice_filters(C, s), Np = f_pad_of(Cs);
+        const long total = (long)KB * Np * BLOCK_K;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        da_pack_weights_t_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kernel, (float *)dst, Kt, Cs, Np, KB, planes, C, F, k * k, 256 * s);
+        SKY_CHECK_LAUNCH();
+        dst += slice_bytes(F, Cs, k, math_mode);
     }
     return SKY_OK;
 }

@@ -3,6 +3,9 @@
 //     (generator.py:30) that precedes it in the backward pass and with the residual gradient add (generator.py:35),
 //   the synthetic L2 objective used by the trunk train bench, and Keras RMSprop (train.py:201-202).
 // All HBM-bound: each distinct tensor is read or written once per kernel.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "sky_common.cuh"
 
 namespace sky {
@@ -119,6 +122,118 @@ instnorm_bwd_apply_kernel(const float *__restrict__ x, const double *__restrict_
     }
 }
 
+// One-launch version: the CTAs that share a sample form a thread-block cluster; each reduces its pixel chunk, the per-CTA partial sums
+// meet through distributed shared memory (no global atomics, no memset, no second launch), then every CTA applies the gradient to its
+// chunk — from registers when the chunk is small enough to have been kept there (the 8x32 trunk planes), else re-read (L2).
+// grid (CL, B), cluster (CL, 1, 1); CL * pix_per_cta >= hw.
+constexpr int IN_CACHE = 4;             // pixel iterations per thread kept in registers
+template <bool CACHE>
+__global__ void __launch_bounds__(TR_THREADS)
+instnorm_bwd_cluster_kernel(const float *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
+                            const float *__restrict__ dy, const float *__restrict__ act, const float *__restrict__ extra,
+                            float *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int hw, int F, float eps,
+                            float slope, int pix_per_cta)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float sm[];       // mean[F], rstd[F], k1[F], m1[F], m2[F], csum[2F] (this CTA's partial sums), part[TR_THREADS][8]
+    float *mean = sm, *rstd = sm + F, *k1 = sm + 2 * F, *m1 = sm + 3 * F, *m2 = sm + 4 * F, *csum = sm + 5 * F, *part = sm + 7 * F;
+    const int b = blockIdx.y, rank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
+    for (int f = threadIdx.x; f < F; f += TR_THREADS) {
+        in_scale_shift(stats, b, f, F, hw, eps, &mean[f], &rstd[f]);
+        k1[f] = gamma[f] * rstd[f];
+    }
+    __syncthreads();
+    const int f4n = F / 4;
+    const int npix = max(0, min(pix_per_cta, hw - rank * pix_per_cta));
+    const size_t base = ((size_t)b * hw + (size_t)rank * pix_per_cta) * F;
+    const int c4 = threadIdx.x % f4n, prow = threadIdx.x / f4n, pstep = TR_THREADS / f4n;
+    float a1[4] = { 0.f, 0.f, 0.f, 0.f }, a2[4] = { 0.f, 0.f, 0.f, 0.f };
+    float4 xc[CACHE ? IN_CACHE : 1], gc[CACHE ? IN_CACHE : 1];
+    auto load = [&](int p, float4 &xv, float4 &g) {
+        const size_t o = base + (size_t)p * F + 4 * c4;
+        xv = __ldg(reinterpret_cast<const float4 *>(x + o));
+        g = __ldg(reinterpret_cast<const float4 *>(dy + o));
+        if (act) {
+            const float4 av = __ldg(reinterpret_cast<const float4 *>(act + o));
+            g.x *= av.x > 0.f ? 1.f : slope; g.y *= av.y > 0.f ? 1.f : slope;
+            g.z *= av.z > 0.f ? 1.f : slope; g.w *= av.w > 0.f ? 1.f : slope;
+        }
+    };
+    auto accumulate = [&](const float4 &xv, const float4 &g) {
+        const float xs[4] = { xv.x, xv.y, xv.z, xv.w }, gs[4] = { g.x, g.y, g.z, g.w };
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xs[u] - mean[4 * c4 + u]) * rstd[4 * c4 + u];
+            a1[u] += gs[u];
+            a2[u] = fmaf(gs[u], xh, a2[u]);
+        }
+    };
+    if (CACHE) {
+#pragma unroll
+        for (int it = 0; it < IN_CACHE; ++it) {
+            const int p = prow + it * pstep;
+            xc[it] = make_float4(0.f, 0.f, 0.f, 0.f); gc[it] = xc[it];
+            if (p < npix) load(p, xc[it], gc[it]);
+        }
+#pragma unroll
+        for (int it = 0; it < IN_CACHE; ++it)
+            if (prow + it * pstep < npix) accumulate(xc[it], gc[it]);
+    } else {
+        for (int p = prow; p < npix; p += pstep) {
+            float4 xv, g;
+            load(p, xv, g);
+            accumulate(xv, g);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { part[threadIdx.x * 8 + u] = a1[u]; part[threadIdx.x * 8 + 4 + u] = a2[u]; }
+    __syncthreads();
+    if (threadIdx.x < 2 * F) {
+        const int f = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const int cc4 = f >> 2, u = f & 3;
+        float s = 0.f;
+        for (int r = 0; r < pstep; ++r) s += part[(r * f4n + cc4) * 8 + which * 4 + u];
+        csum[threadIdx.x] = s;                                   // [f][which]
+    }
+    cluster.sync();
+    if (threadIdx.x < 2 * F) {
+        double s = 0.0;
+        for (int r = 0; r < CL; ++r) s += (double)cluster.map_shared_rank(csum, r)[threadIdx.x];
+        const int f = threadIdx.x >> 1, which = threadIdx.x & 1;
+        (which ? m2 : m1)[f] = (float)(s / hw);
+        if (rank == 0) atomicAdd((which ? dgamma : dbeta) + f, (float)s);
+    }
+    cluster.sync();                                              // remote reads are done before any CTA of the cluster may exit
+    auto apply = [&](int p, const float4 &xv, const float4 &g) {
+        const int f = 4 * c4;
+        const float xs[4] = { xv.x, xv.y, xv.z, xv.w }, gs[4] = { g.x, g.y, g.z, g.w };
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xh = (xs[u] - mean[f + u]) * rstd[f + u];
+            o[u] = k1[f + u] * (gs[u] - m1[f + u] - xh * m2[f + u]);
+        }
+        const size_t off = base + (size_t)p * F + f;
+        if (extra) {
+            const float4 ev = __ldg(reinterpret_cast<const float4 *>(extra + off));
+            o[0] += ev.x; o[1] += ev.y; o[2] += ev.z; o[3] += ev.w;
+        }
+        *reinterpret_cast<float4 *>(dx + off) = make_float4(o[0], o[1], o[2], o[3]);
+    };
+    if (CACHE) {
+#pragma unroll
+        for (int it = 0; it < IN_CACHE; ++it)
+            if (prow + it * pstep < npix) apply(prow + it * pstep, xc[it], gc[it]);
+    } else {
+        for (int p = prow; p < npix; p += pstep) {
+            float4 xv, g;
+            load(p, xv, g);
+            apply(p, xv, g);
+        }
+    }
+}
+
 // loss = mean((y - target)^2); dy = 2 (y - target) / n.  loss (fp64) must be zeroed by the caller.
 __global__ void mse_loss_kernel(const float *__restrict__ y, const float *__restrict__ target, float *__restrict__ dy,
                                 double *__restrict__ loss, long n4, float inv_n)
@@ -171,6 +286,29 @@ extern "C" int sky_instnorm_bwd(const float *x, const double *stats, const float
                 "instance-norm backward needs filters in {4, 8, 16, 32, 64, 128} (got %d)", F);
     cudaStream_t st = (cudaStream_t)stream;
     const int hw = h * w;
+    if (!getenv("SKY_INSTNORM_BWD_TWO_PASS")) {
+        // one launch: a cluster of up to 8 CTAs per sample, partial sums through distributed shared memory (`sums` is not used)
+        const int pstep = TR_THREADS / (F / 4);
+        int CL = 8;
+        while (CL > 1 && hw < CL * pstep) CL >>= 1;
+        const int pix = (hw + CL - 1) / CL;
+        const bool cache = pix <= IN_CACHE * pstep;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(TR_THREADS); cfg.stream = st;
+        cfg.dynamicSmemBytes = (7 * F + TR_THREADS * 8) * sizeof(float);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cache)
+            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<true>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
+                                              eps, slope, pix));
+        else
+            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<false>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
+                                              eps, slope, pix));
+        SKY_CHECK_LAUNCH();
+        return SKY_OK;
+    }
     int chunks, pix;
     in_grid(B, hw, &chunks, &pix);
     SKY_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * F * 2 * sizeof(double), st));

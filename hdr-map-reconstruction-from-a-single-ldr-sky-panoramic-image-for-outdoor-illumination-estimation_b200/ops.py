@@ -47,8 +47,9 @@ class TransposedPack:
     def get(self, w):
         key = (w.data_ptr(), w._version)
         if self.key != key:
-            check(LIB.sky_conv2d_transpose_weights(w.data_ptr(), self.scratch.data_ptr(), self.C, self.F, self.k, 1, _stream()))
-            check(LIB.sky_da_pack_weights(self.scratch.data_ptr(), self.packed.data_ptr(), self.F, self.C, self.k, self.mode, _stream()))
+            if self.F <= 4:      # 3-filter layers also run on the unpacked transposed kernel (small-C kernel of conv_backward_data)
+                check(LIB.sky_conv2d_transpose_weights(w.data_ptr(), self.scratch.data_ptr(), self.C, self.F, self.k, 1, _stream()))
+            check(LIB.sky_conv2d_pack_weights_t(w.data_ptr(), self.packed.data_ptr(), self.C, self.F, self.k, self.mode, _stream()))
             self.key = key
         return self.packed
 
@@ -179,8 +180,9 @@ class _PlainConvCore:
             check(LIB.sky_conv2d_fwd_blend(x.data_ptr(), self._packed_weights().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
                                            _ptr(residual), sky_gamma.data_ptr(), float(threshold), B, h, w, C, k, flags, slope,
                                            mode, _stream()))
-        elif (s == 1 and k % 2 == 1 and k <= 11 and C <= 4 and F <= 32 and residual is None and not relu and not log_decompress):
-            # image-like input (conv1_d): fp32 CUDA-core kernel, the unpacked variable is read directly
+        elif (s == 1 and k % 2 == 1 and k <= 11 and C <= 4 and F <= 256 and residual is None and not log_decompress
+              and not (relu and leaky_slope is not None)):
+            # image-like input (conv1_d; VGG conv1_1 with its ReLU): fp32 CUDA-core kernel, the unpacked variable is read directly
             check(LIB.sky_conv2d_smallc_fwd(x.data_ptr(), self._weight().data_ptr(), self._bias().data_ptr(), y.data_ptr(),
                                             _ptr(stats), B, h, w, C, F, k, flags, slope, _stream()))
         else:

@@ -103,6 +103,42 @@ def test_plain_conv_backward(pkg, case):
         assert rel(dk6.cpu().numpy(), wt.grad.numpy()[:, :, :6, :].reshape(k * k * 6, F)) < 2e-3
 
 
+def test_weight_packing_kernels(pkg):
+    """The packed tensor-core images: the tiled forward pack against a numpy restatement of its layout, and the one-pass pack of the
+    flipped, transposed kernel (data gradients) byte for byte against transpose-then-pack."""
+    LIB, check = pkg._lib.LIB, pkg._lib.check
+    rng = np.random.default_rng(5)
+    for (C, F, k) in ((32, 64, 3), (64, 128, 4), (256, 512, 4), (512, 1, 4), (32, 3, 7), (128, 256, 3), (8, 64, 4), (4, 64, 3), (96, 48, 3)):
+        w = T(rng.standard_normal((k * k * C, F)).astype(np.float32)).cuda()
+        for mode in (pkg._lib.MATH_TF32, pkg._lib.MATH_3XTF32):
+            scratch = torch.empty(k * k * F * C, device="cuda")
+            nb = LIB.sky_da_packed_weight_bytes(F, C, k, mode)
+            a = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+            b = torch.ones(nb, dtype=torch.uint8, device="cuda")
+            check(LIB.sky_conv2d_transpose_weights(w.data_ptr(), scratch.data_ptr(), C, F, k, 1, st()))
+            check(LIB.sky_da_pack_weights(scratch.data_ptr(), a.data_ptr(), F, C, k, mode, st()))
+            check(LIB.sky_conv2d_pack_weights_t(w.data_ptr(), b.data_ptr(), C, F, k, mode, st()))
+            assert torch.equal(a, b), (C, F, k, mode)
+        # forward pack, TF32 plane of the first slice: tile kb, row n, 16-byte chunk ch (XOR-swizzled with n & 7) holds kernel rows
+        # kbase + 4 ch .. + 3 of filter n, kbase = t * C + cc * 32 for kb = cc * k*k + t when C % 32 == 0, else 32 kb
+        nb = LIB.sky_da_packed_weight_bytes(C, F, k, pkg._lib.MATH_TF32)
+        pk_ = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        check(LIB.sky_da_pack_weights(w.data_ptr(), pk_.data_ptr(), C, F, k, pkg._lib.MATH_TF32, st()))
+        Fs = min(F, 256)
+        Fp = max(16, (Fs + 15) // 16 * 16)
+        K = k * k * C
+        KB = (K + 31) // 32
+        img = pk_.cpu().numpy().view(np.float32)[:KB * Fp * 32].reshape(KB, Fp, 8, 4)
+        wn = w.cpu().numpy()
+        for kb in (0, KB // 2, KB - 1):
+            kbase = (kb % (k * k)) * C + (kb // (k * k)) * 32 if C % 32 == 0 else 32 * kb
+            for n in (0, Fs - 1):
+                for ch in (0, 3, 7):
+                    want = np.array([wn[kbase + 4 * ch + u, n] if kbase + 4 * ch + u < K else 0.0 for u in range(4)], np.float32)
+                    got = img[kb, n, ch ^ (n & 7)]
+                    assert np.allclose(got, want, rtol=1e-3, atol=1e-6), (C, F, k, kb, n, ch)
+
+
 @pytest.mark.parametrize("B,h,w,C,F,k", [(2, 8, 32, 128, 128, 3), (2, 16, 64, 64, 64, 3), (2, 32, 128, 32, 32, 7), (3, 8, 32, 64, 128, 3)])
 def test_da_weight_gradient_pipelined(pkg, B, h, w, C, F, k):
     """The pipelined weight-gradient kernel with the distortion-aware sampler vs autograd through the materialised oracle."""
@@ -575,6 +611,6 @@ def test_train_step_batch_8_losses(pkg):
     step2._dis.set_weights(wd)
     outs2 = step2.train_step([T(hdr_t).cuda(), T(ldr).cuda()], T(gt).cuda())
     torch.cuda.synchronize()
-    assert rel(outs2[0].cpu().numpy(), outs[0].cpu().numpy()) <= 1e-6
+    assert rel(outs2[0].cpu().numpy(), outs[0].cpu().numpy()) <= 5e-6
     assert rel(step2.fv_gen.flat_g.cpu().numpy(), step.fv_gen.flat_g.cpu().numpy()) <= 2e-3
     assert rel(step2.fv_dis.flat_g.cpu().numpy(), step.fv_dis.flat_g.cpu().numpy()) <= 2e-3
