@@ -385,17 +385,6 @@ static int launch_wgrad_smallf(const float *x, const float *dy, float *dw, int B
     return SKY_OK;
 }
 
-// db[f] (+)= sum_m dy[m*ldF + f]
-__global__ void col_sum_ld_kernel(const float *__restrict__ dy, float *__restrict__ db, int M, int F, int ldF)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const int rows_per = (M + gridDim.y - 1) / gridDim.y;
-    const int lo = blockIdx.y * rows_per, hi = min(M, lo + rows_per);
-    float s = 0.f;
-    for (int m = lo; m < hi; ++m) s += dy[(size_t)m * ldF + f];
-    if (hi > lo) atomicAdd(db + f, s);
-}
 
 static int launch_wgrad(WgParams p, cudaStream_t st)
 {
@@ -522,10 +511,8 @@ extern "C" int sky_conv2d_bwd_filter(const float *x, const float *dy, const floa
     }
     if (dbias) {
         if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)F * sizeof(float), st));
-        int ysplit = (p.M + 63) / 64;
-        if (ysplit > 4 * 148) ysplit = 4 * 148;
-        col_sum_ld_kernel<<<dim3((F + 127) / 128, ysplit), 128, 0, st>>>(dy, dbias, p.M, F, F);
-        SKY_CHECK_LAUNCH();
+        const int rc = launch_col_sum(dy, dbias, p.M, F, st);
+        if (rc != SKY_OK) return rc;
     }
     return SKY_OK;
 }

@@ -97,6 +97,9 @@ int launch_fwd_strip_plain(const FwdArgs &a);
 int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_host, float *dw, int B, int h, int w, int C, int F, int k,
                        int stride, cudaStream_t stream);
 
+// db[f] += column sums of the dense matrix dy [M][F] (bias gradients; db zeroed by the caller)
+int launch_col_sum(const float *dy, float *db, int M, int F, cudaStream_t st);
+
 #ifdef __CUDACC__
 // The reference's treatment of a column index (distortion_aware_ops.py:76-77 on the float coordinate, :90-91 on the integer corners),
 // restated on the integer part: `q` is a column in the PADDED frame before any wrap.  Returns the unpadded column, or -1 for a zero.

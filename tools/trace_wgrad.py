@@ -21,3 +21,4 @@ print("kernel", rel(buf[103]), "us; first drain", rel(buf[100]), "->", rel(buf[1
 for i in range(12):
     print("item %2d  mma: wait %8.2f got %8.2f issued %8.2f | producer: stage free %8.2f strip done %8.2f dy done %8.2f" %
           (i, rel(buf[4 * i]), rel(buf[4 * i + 1]), rel(buf[4 * i + 2]), rel(buf[48 + 4 * i]), rel(buf[49 + 4 * i]), rel(buf[50 + 4 * i])))
+print("every 32nd item issued at (us):", [round(rel(buf[104 + i]), 1) for i in range(24) if buf[104 + i]])
