@@ -63,6 +63,7 @@ SIGNATURES = {
     "sky_blend_split": (_i, [_vp, _vp, _f] + [_vp] * 5 + [ctypes.c_long, _vp]),
     "sky_transpose": (_i, [_vp, _vp, _i, _i, _vp]),
     "sky_dense_bwd_data": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
+    "sky_dense_bwd_data_nt": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
     "sky_maxpool2x2_bwd": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "sky_gradcam": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
     "sky_sunrad_input": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),

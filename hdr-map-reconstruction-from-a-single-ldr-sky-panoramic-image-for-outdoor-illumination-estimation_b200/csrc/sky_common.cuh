@@ -278,5 +278,6 @@ int encode_nhwc_tensor_map(CUtensorMap *out, const float *base, int B, int h, in
 int encode_dy_wgrad_tensor_map(CUtensorMap *out, const float *base, int B, int OH, int OW, int F, int box_cols);
 // Host: encode a row-major fp32 matrix [rows][cols] with box (box_cols, box_rows), no swizzle (cols % 4 == 0, 16-byte aligned base).
 int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows);
+int encode_2d_tensor_map_sw(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows, int swizzle128);
 }  // namespace sky
 #endif

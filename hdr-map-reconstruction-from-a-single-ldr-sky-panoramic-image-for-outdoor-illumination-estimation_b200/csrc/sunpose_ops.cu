@@ -158,6 +158,86 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     }
 }
 
+// The data gradient of the same layers without a transposed copy of W: dx [B, K] = dy [B, N] . W^T with W read in its own [K, N]
+// layout.  Same ring and the same FMA structure with the roles exchanged — a thread owns two k-ROWS of the [256 k][32 n] weight tile
+// (TMA, 128-byte swizzle: the 128-bit reads of 32 threads on 32 different rows spread over all banks), the dy tile [32 b][32 n] is
+// broadcast; the contraction runs over n (split over blockIdx.y).
+constexpr int DT_BKR = 256, DT_BN = 32;
+constexpr int DT_W_STAGE = DT_BKR * DT_BN * 4, DT_X_STAGE = DN_BM * DT_BN * 4;
+constexpr int DT_SMEM = DS_STAGES * (DT_W_STAGE + DT_X_STAGE) + 2 * DS_STAGES * 8 + 1024;
+
+__global__ void __launch_bounds__(DS_THREADS, 1)
+dense_stream_t_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_dy, float *__restrict__ dx, int B,
+                      int K, int N, int n_per)
+{
+    extern __shared__ uint8_t ds_raw[];
+    uint8_t *ds_smem = ds_raw + ((1024u - (smem_u32(ds_raw) & 1023u)) & 1023u);
+    uint8_t *Ws = ds_smem;                                                            // [STAGES][256 k][32 n], swizzled
+    float *xs = reinterpret_cast<float *>(ds_smem + DS_STAGES * DT_W_STAGE);          // [STAGES][32 b][32 n]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ds_smem + DS_STAGES * (DT_W_STAGE + DT_X_STAGE));
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + DS_STAGES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.x * DT_BKR, b0 = blockIdx.z * DN_BM;
+    const int n_lo = blockIdx.y * n_per, n_hi = min(N, n_lo + n_per);
+    const int nsteps = (n_hi - n_lo + DT_BN - 1) / DT_BN;
+    if (tid == 0) {
+        for (int s = 0; s < DS_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, DS_CONSUMERS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == DS_CONSUMERS / 32) {
+        if (lane == 0) {
+            prefetch_tmap(&tmap_w);
+            prefetch_tmap(&tmap_dy);
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % DS_STAGES, n0 = n_lo + it * DT_BN;
+                mbar_wait(empty0 + 8 * s, ((it / DS_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(DT_W_STAGE + DT_X_STAGE));
+                tma_load_2d(smem_u32(Ws + s * DT_W_STAGE), &tmap_w, n0, k0, full0 + 8 * s);
+                tma_load_2d(smem_u32(xs + s * DN_BM * DT_BN), &tmap_dy, n0, b0, full0 + 8 * s);
+            }
+        }
+    } else {
+        // consumers: k-rows k0 + ct and k0 + 128 + ct, n-columns [16 * nhalf, 16 * nhalf + 16) of every stage
+        const int ct = tid & 127, nhalf = tid >> 7;
+        float acc0[DN_BM], acc1[DN_BM];
+#pragma unroll
+        for (int b = 0; b < DN_BM; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+        for (int it = 0; it < nsteps; ++it) {
+            const int s = it % DS_STAGES;
+            mbar_wait(full0 + 8 * s, (it / DS_STAGES) & 1);
+            const uint8_t *wt = Ws + s * DT_W_STAGE;
+            const float *xt = xs + s * DN_BM * DT_BN;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const int c = 4 * nhalf + q;                                          // 16-byte chunk of the 128-byte tile rows
+                const float4 w0 = *reinterpret_cast<const float4 *>(wt + ct * 128 + ((c ^ (ct & 7)) << 4));
+                const float4 w1 = *reinterpret_cast<const float4 *>(wt + (ct + 128) * 128 + ((c ^ (ct & 7)) << 4));
+#pragma unroll
+                for (int b = 0; b < DN_BM; ++b) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xt + b * DT_BN + 4 * c);
+                    acc0[b] = fmaf(xv.x, w0.x, acc0[b]); acc1[b] = fmaf(xv.x, w1.x, acc1[b]);
+                    acc0[b] = fmaf(xv.y, w0.y, acc0[b]); acc1[b] = fmaf(xv.y, w1.y, acc1[b]);
+                    acc0[b] = fmaf(xv.z, w0.z, acc0[b]); acc1[b] = fmaf(xv.z, w1.z, acc1[b]);
+                    acc0[b] = fmaf(xv.w, w0.w, acc0[b]); acc1[b] = fmaf(xv.w, w1.w, acc1[b]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+        const int ka = k0 + ct, kb = k0 + 128 + ct;
+#pragma unroll
+        for (int b = 0; b < DN_BM; ++b)
+            if (b0 + b < B) {
+                if (ka < K) atomicAdd(dx + (size_t)(b0 + b) * K + ka, acc0[b]);
+                if (kb < K) atomicAdd(dx + (size_t)(b0 + b) * K + kb, acc1[b]);
+            }
+    }
+}
+
 // y = act(y + bias)
 __global__ void dense_finalize_kernel(float *__restrict__ y, const float *__restrict__ bias, long total, int N, int relu)
 {
@@ -253,6 +333,49 @@ extern "C" int sky_dense_fwd(const float *x, const float *W, const float *bias, 
     dense_splitk_kernel<<<dim3(ncta, ksplit, bcta), DN_THREADS, 0, st>>>(x, W, y, B, K, N, k_per);
     SKY_CHECK_LAUNCH();
     return dense_finish(y, bias, B, N, relu, st);
+}
+
+namespace sky {
+// dx = 0 where the ReLU output that fed the layer is not positive
+__global__ void dense_relu_mask_kernel(float *__restrict__ dx, const float *__restrict__ act, long total)
+{
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+        if (!(act[e] > 0.f)) dx[e] = 0.f;
+}
+}  // namespace sky
+
+// dx [B, K] = dy [B, N] . W^T from W in its own [K, N] layout (Keras Dense kernel): no transposed copy.  dx is overwritten and zeroed
+// where `act` (the ReLU output that fed the layer, may be NULL) is not positive.
+// Needs N % 4 == 0 and K >= 256; SKY_ERR_UNSUPPORTED otherwise (the caller then streams a transposed copy through sky_dense_bwd_data).
+extern "C" int sky_dense_bwd_data_nt(const float *dy, const float *W, const float *act, float *dx, int B, int K, int N, void *stream)
+{
+    SKY_REQUIRE(dy && W && dx && B > 0 && K > 0 && N > 0, SKY_ERR_INVALID, "bad arguments");
+    SKY_REQUIRE(N % 4 == 0 && K >= DT_BKR && ((uintptr_t)W & 15) == 0 && ((uintptr_t)dy & 15) == 0, SKY_ERR_UNSUPPORTED,
+                "the transposed weight-streaming kernel needs N %% 4 == 0, K >= 256 and 16-byte aligned operands (K=%d N=%d)", K, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    SKY_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * K * sizeof(float), st));
+    SKY_ENSURE_DYN_SMEM(dense_stream_t_kernel, DT_SMEM);
+    CUtensorMap tmap_w, tmap_dy;
+    int rc = encode_2d_tensor_map_sw(&tmap_w, W, K, N, DT_BN, DT_BKR, 1);
+    if (rc != SKY_OK) return rc;
+    rc = encode_2d_tensor_map(&tmap_dy, dy, B, N, DT_BN, DN_BM);
+    if (rc != SKY_OK) return rc;
+    const int kcta = (K + DT_BKR - 1) / DT_BKR, bcta = (B + DN_BM - 1) / DN_BM;
+    int nsplit = 148 / (kcta * bcta);                                   // one wave of CTAs, one per SM
+    if (nsplit < 1) nsplit = 1;
+    int n_per = (N + nsplit - 1) / nsplit;
+    n_per = (n_per + DT_BN - 1) / DT_BN * DT_BN;
+    nsplit = (N + n_per - 1) / n_per;
+    dense_stream_t_kernel<<<dim3(kcta, nsplit, bcta), DS_THREADS, DT_SMEM, st>>>(tmap_w, tmap_dy, dx, B, K, N, n_per);
+    SKY_CHECK_LAUNCH();
+    if (act) {
+        const long total = (long)B * K;
+        long blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dense_relu_mask_kernel<<<(int)blocks, 256, 0, st>>>(dx, act, total);
+        SKY_CHECK_LAUNCH();
+    }
+    return SKY_OK;
 }
 
 extern "C" int sky_softmax_rows(const float *x, float *y, int rows, int N, void *stream)

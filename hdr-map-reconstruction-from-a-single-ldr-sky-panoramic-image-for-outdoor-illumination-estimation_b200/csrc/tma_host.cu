@@ -55,6 +55,12 @@ int encode_dy_wgrad_tensor_map(CUtensorMap *out, const float *base, int B, int O
 
 int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows)
 {
+    return encode_2d_tensor_map_sw(out, base, rows, cols, box_cols, box_rows, 0);
+}
+
+// swizzle128 != 0: box_cols must be 32 (128-byte rows); 16-byte chunk c of tile row r lands at chunk c ^ (r & 7)
+int encode_2d_tensor_map_sw(CUtensorMap *out, const float *base, long rows, long cols, int box_cols, int box_rows, int swizzle128)
+{
     EncodeTiledFn enc = get_encoder();
     SKY_REQUIRE(enc != nullptr, SKY_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = { (cuuint64_t)cols, (cuuint64_t)rows };
@@ -62,7 +68,8 @@ int encode_2d_tensor_map(CUtensorMap *out, const float *base, long rows, long co
     cuuint32_t box[2] = { (cuuint32_t)box_cols, (cuuint32_t)box_rows };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SKY_REQUIRE(r == CUDA_SUCCESS, SKY_ERR_CUDA, "cuTensorMapEncodeTiled (2-D) failed with CUresult %d (rows=%ld cols=%ld box=%dx%d)", (int)r,
                 rows, cols, box_rows, box_cols);
     return SKY_OK;

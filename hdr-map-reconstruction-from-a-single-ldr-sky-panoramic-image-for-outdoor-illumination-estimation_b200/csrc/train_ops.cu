@@ -125,10 +125,11 @@ instnorm_bwd_apply_kernel(const float *__restrict__ x, const double *__restrict_
 // One-launch version: the CTAs that share a sample form a thread-block cluster; each reduces its pixel chunk, the per-CTA partial sums
 // meet through distributed shared memory (no global atomics, no memset, no second launch), then every CTA applies the gradient to its
 // chunk — from registers when the chunk is small enough to have been kept there (the 8x32 trunk planes), else re-read (L2).
-// grid (CL, B), cluster (CL, 1, 1); CL * pix_per_cta >= hw.
+// grid (CL, B), cluster (CL, 1, 1); CL * pix_per_cta >= hw.  Small chunks: 256 threads with the chunk in registers; large chunks: 1024
+// threads streaming twice (the stage is bound by the loads in flight).
 constexpr int IN_CACHE = 4;             // pixel iterations per thread kept in registers
-template <bool CACHE>
-__global__ void __launch_bounds__(TR_THREADS)
+template <bool CACHE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 instnorm_bwd_cluster_kernel(const float *__restrict__ x, const double *__restrict__ stats, const float *__restrict__ gamma,
                             const float *__restrict__ dy, const float *__restrict__ act, const float *__restrict__ extra,
                             float *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta, int hw, int F, float eps,
@@ -136,10 +137,10 @@ instnorm_bwd_cluster_kernel(const float *__restrict__ x, const double *__restric
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ float sm[];       // mean[F], rstd[F], k1[F], m1[F], m2[F], csum[2F] (this CTA's partial sums), part[TR_THREADS][8]
+    extern __shared__ float sm[];       // mean[F], rstd[F], k1[F], m1[F], m2[F], csum[2F] (this CTA's partial sums), part[THREADS][8]
     float *mean = sm, *rstd = sm + F, *k1 = sm + 2 * F, *m1 = sm + 3 * F, *m2 = sm + 4 * F, *csum = sm + 5 * F, *part = sm + 7 * F;
     const int b = blockIdx.y, rank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
-    for (int f = threadIdx.x; f < F; f += TR_THREADS) {
+    for (int f = threadIdx.x; f < F; f += THREADS) {
         in_scale_shift(stats, b, f, F, hw, eps, &mean[f], &rstd[f]);
         k1[f] = gamma[f] * rstd[f];
     }
@@ -147,7 +148,7 @@ instnorm_bwd_cluster_kernel(const float *__restrict__ x, const double *__restric
     const int f4n = F / 4;
     const int npix = max(0, min(pix_per_cta, hw - rank * pix_per_cta));
     const size_t base = ((size_t)b * hw + (size_t)rank * pix_per_cta) * F;
-    const int c4 = threadIdx.x % f4n, prow = threadIdx.x / f4n, pstep = TR_THREADS / f4n;
+    const int c4 = threadIdx.x % f4n, prow = threadIdx.x / f4n, pstep = THREADS / f4n;
     float a1[4] = { 0.f, 0.f, 0.f, 0.f }, a2[4] = { 0.f, 0.f, 0.f, 0.f };
     float4 xc[CACHE ? IN_CACHE : 1], gc[CACHE ? IN_CACHE : 1];
     auto load = [&](int p, float4 &xv, float4 &g) {
@@ -308,18 +309,19 @@ extern "C" int sky_instnorm_bwd(const float *x, const double *stats, const float
         while (CL > 1 && hw < CL * pstep) CL >>= 1;
         const int pix = (hw + CL - 1) / CL;
         const bool cache = pix <= IN_CACHE * pstep;
+        const int threads = cache ? TR_THREADS : 1024;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(TR_THREADS); cfg.stream = st;
-        cfg.dynamicSmemBytes = (7 * F + TR_THREADS * 8) * sizeof(float);
+        cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(threads); cfg.stream = st;
+        cfg.dynamicSmemBytes = (7 * F + threads * 8) * sizeof(float);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (cache)
-            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<true>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
+            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<true, TR_THREADS>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
                                               eps, slope, pix));
         else
-            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<false>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
+            SKY_CHECK_CUDA(cudaLaunchKernelEx(&cfg, instnorm_bwd_cluster_kernel<false, 1024>, x, stats, gamma, dy, act, extra, dx, dgamma, dbeta, hw, F,
                                               eps, slope, pix));
         SKY_CHECK_LAUNCH();
         return SKY_OK;

@@ -7,6 +7,7 @@ north-star path; `distortion_aware=False` gives the plain ``ops.conv2d`` wiring 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -23,6 +24,9 @@ def maxpool2d(x):
     y = torch.empty((B, (h + 1) // 2, (w + 1) // 2, C), dtype=torch.float32, device=x.device)
     check(LIB.sky_maxpool2x2_fwd(x.data_ptr(), y.data_ptr(), B, h, w, C, _stream()))
     return y
+
+
+DENSE_BWD_KERNEL = os.environ.get("SKY_DENSE_BWD_KERNEL", "nt")      # "t": transposed copy + the forward kernel (round 1)
 
 
 class Dense:
@@ -61,8 +65,13 @@ class Dense:
         B, n = dy.shape
         k = self.kernel.shape[0]
         dx = torch.empty((B, k), dtype=torch.float32, device=dy.device)
-        check(LIB.sky_dense_bwd_data(dy.data_ptr(), self.kernel_transposed().data_ptr(), None if act is None else act.data_ptr(),
-                                     dx.data_ptr(), B, k, n, _stream()))
+        if DENSE_BWD_KERNEL == "nt" and n % 4 == 0 and k >= 256:
+            # W streamed in its own [in, units] layout: no transposed copy per step
+            check(LIB.sky_dense_bwd_data_nt(dy.data_ptr(), self.kernel.data_ptr(), None if act is None else act.data_ptr(), dx.data_ptr(),
+                                            B, k, n, _stream()))
+        else:
+            check(LIB.sky_dense_bwd_data(dy.data_ptr(), self.kernel_transposed().data_ptr(), None if act is None else act.data_ptr(),
+                                         dx.data_ptr(), B, k, n, _stream()))
         return dx
 
     @property

@@ -52,6 +52,7 @@ class Step:
         self._dis.build(batch_size, im_height, im_width)
         self._acc = torch.zeros(16, dtype=torch.float64, device=device)
         self.lr, self.rho, self.eps = lr, rho, eps
+        self._marks = None
         self.fv_gen = self.fv_dis = None
         self._side = None
         self.last_losses = {}
@@ -169,6 +170,14 @@ class Step:
             self._side = (torch.cuda.Stream(), torch.cuda.Stream())
         s1, s2 = self._side if self.concurrent else (main, main)
 
+        marks = self._marks          # debug (tools/step_phases.py): events at the phase boundaries of every stream; None in production
+
+        def mark(name, stream=None):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream if stream is not None else torch.cuda.current_stream())
+                marks.append((name, ev))
+
         def fork(side):
             if side is not main:
                 side.wait_stream(main)
@@ -180,24 +189,30 @@ class Step:
         # ================================ generator_in_step(training=True), forward (:239-331) ================================
         both = torch.empty((2 * B, H, W, 3), dtype=torch.float32, device=dev)                    # [y_final_gamma; hdr_t_gamma]: VGG16's batch
         y_gamma = both[:B]
+        mark("start")
         fork(s1)
         with torch.cuda.stream(s1):
             sm, acts = sun.sunposeEstimation(ldr, training=True)                                 # :253
+            mark("s1: sunpose forward done")
             sun.fc1.kernel_transposed()
             sun.fc2.kernel_transposed()
             y_c = sun.class_score(sm, gt)                                                        # :263-265 (outside the tape)
             cams = [grad_cam.layer(y_c, a) for a in acts]                                        # :267-269
+            mark("s1: grad-cam done")
             sun_rad_gamma, _, _ = gen.sun_rad_estimation(ldr, cams[0], cams[1], cams[2], sm, training=True, log_compress=True)   # :286-287
             check(LIB.sky_kl_divergence(gt.data_ptr(), sm.data_ptr(), gt.numel(), acc[0:1].data_ptr(), _stream()))              # :303
             g_sm = torch.empty_like(sm)
             check(LIB.sky_kl_divergence_bwd(gt.data_ptr(), sm.data_ptr(), g_sm.data_ptr(), sm.numel(), 1.0 / Bg, 0, _stream()))
+            mark("s1: sun branch forward done")
         check(LIB.sky_hdr_log_codec(hdr_t.data_ptr(), both[B:].data_ptr(), hdr_t.numel(), 0, st))                 # :246
         res_out = gen.encode(ldr, training=True, save=True)                                      # :249
+        mark("main: encoder + trunk forward done")
         c_sky, sky_in = gen.decode_train(res_out, gen._dec, gen.conv1_f)                         # :250 up to conv1_f's raw output
         c_sun, sun_in = gen.decode_train(res_out, gen._dec_u, gen.conv1_u)                       # :288 up to conv1_u's raw output
         y_lin = torch.empty_like(c_sky)
         sky_lin, sun_lin = torch.empty_like(c_sky), torch.empty_like(c_sky)
         alpha = torch.empty((B, H, W, 1), dtype=torch.float32, device=dev)
+        mark("main: decoders forward done")
         join(s1)
         check(LIB.sky_train_tail_fwd(c_sky.data_ptr(), c_sun.data_ptr(), ldr.data_ptr(), sun_rad_gamma.data_ptr(), hdr_t.data_ptr(), THRESHOLD,
                                      0.1, y_gamma.data_ptr(), y_lin.data_ptr(), sky_lin.data_ptr(), sun_lin.data_ptr(), alpha.data_ptr(),
@@ -217,6 +232,7 @@ class Step:
                                      1000.0 / (base_y.numel() // B * Bg), _stream()))
             g_dog = torch.empty_like(y_lin)
             check(LIB.sky_dog_base_bwd(dbase.data_ptr(), g_dog.data_ptr(), B, H, W, 3, 0, _stream()))
+            mark("s1: DoG done")
         with torch.cuda.stream(s2):
             # adversarial (:300, 327): the discriminator in inference mode on [ldr, y_final_lin], LSGAN gen_loss, data gradient back to y_final_lin
             cat16 = torch.empty((2 * B, H, W, 8), dtype=torch.float32, device=dev)
@@ -231,6 +247,7 @@ class Step:
             g_dis8 = dis.infer_backward_data(g_same)
             adv_done = torch.cuda.Event()
             adv_done.record(torch.cuda.current_stream())
+            mark("s2: adversarial term done")
             # ============================ discriminator_in_step(training=True) + disc_tape.gradient (:351-380, 405) ============================
             # needs nothing of the generator's backward pass: it stays on this stream until the optimizers
             d_both = dis.train_forward(cat16, groups=2)                                          # :360-361, batch statistics per call
@@ -241,9 +258,11 @@ class Step:
                                     0.5 / (n_d // B * Bg), _stream()))                           # generated_loss (:237)
             zero_(fvd.flat_g)
             dis.train_backward(g_both, fvd)
+            mark("s2: discriminator step done")
         # perceptual (:306-312): VGG16 features of [prediction; target] in one batch, data gradient for the prediction half
         self.vgg.forward_saved(both)
         g_vgg4 = self.vgg.perceptual_backward(B, 0.01 * B / Bg, acc[1:4])
+        mark("main: VGG forward + backward done")
         join(s1)
         if s2 is not main:
             main.wait_event(adv_done)
@@ -260,15 +279,20 @@ class Step:
             # sun radiance -> sun-position softmax (the max-normalisation of generator.py:160 included), joined with the KL adjoint
             gen.sun.train_backward(d_srg, self._sun_grads(), g_sm, accumulate_dsm=True)
             sunpose_backward(sun, g_sm, fv.grad, on_dense_done=lambda: work.append(self._start_tail_allreduce()))
+            mark("s1: sun branch backward done")
+        mark("main: tail backward done")
         dres = torch.empty_like(res_out)
         gen.decode_backward(dc_sun, gen._dec_u, gen.conv1_u, sun_in, fv, dres, False)            # sun decoder (generator.py:127-156)
         gen.decode_backward(dc_sky, gen._dec, gen.conv1_f, sky_in, fv, dres, True)               # sky decoder (:110-125)
+        mark("main: decoders backward done")
         gen.encode_backward(dres, fv)                                                            # trunk + encoder (:92-108)
+        mark("main: trunk + encoder backward done")
         join(s1)
         join(s2)
         # ================================ optimizers (:403, 406) ================================
         self._finish_allreduce(work[0])
         self.apply_gradients()
+        mark("main: optimizers done")
         kl = acc[0:1] / B
         perceptual = acc[1] / self.vgg._saved[3][:B].numel() + acc[2] / self.vgg._saved[6][:B].numel() + acc[3] / self.vgg._saved[10][:B].numel()
         dog = acc[4:8].sum() / base_y.numel()

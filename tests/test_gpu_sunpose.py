@@ -91,3 +91,27 @@ def test_dense_streaming_kernel(pkg, B, K, N):
     want = x.astype(np.float64) @ W.astype(np.float64) + b
     assert rel_l2(d(torch.from_numpy(x).cuda()).cpu().numpy(), want) < 1e-5
     assert rel_l2(d(torch.from_numpy(x).cuda(), relu=True).cpu().numpy(), np.maximum(want, 0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,K,N", [(32, 1000, 1028), (5, 256, 96), (40, 4096, 512), (32, 8192, 4096)])
+def test_dense_data_gradient_without_transposed_copy(pkg, B, K, N):
+    """dx = dy . W^T streamed from W in its own [K, N] layout (128-byte-swizzled TMA tiles, a thread owns two k-rows) against fp64 and
+    against the round-1 path (transposed copy + the forward kernel): ragged K / N tails, B < 32 and B > 32, the ReLU mask."""
+    import unittest.mock as mock
+    sp = pkg.sunpose_net
+    rng = np.random.default_rng(B + K + N)
+    dy = rng.standard_normal((B, N)).astype(np.float32)
+    W = rng.standard_normal((K, N)).astype(np.float32)
+    act = rng.standard_normal((B, K)).astype(np.float32)
+    d = sp.Dense(N)
+    d.build((B, K))
+    d.kernel.copy_(torch.from_numpy(W))
+    want = dy.astype(np.float64) @ W.astype(np.float64).T
+    assert sp.DENSE_BWD_KERNEL == "nt"
+    got = d.backward_data(torch.from_numpy(dy).cuda())
+    assert rel_l2(got.cpu().numpy(), want) < 1e-5, rel_l2(got.cpu().numpy(), want)
+    got_m = d.backward_data(torch.from_numpy(dy).cuda(), act=torch.from_numpy(act).cuda())
+    assert rel_l2(got_m.cpu().numpy(), want * (act > 0)) < 1e-5
+    with mock.patch.object(sp, "DENSE_BWD_KERNEL", "t"):
+        old = d.backward_data(torch.from_numpy(dy).cuda())
+    assert rel_l2(got.cpu().numpy(), old.cpu().numpy()) < 1e-5
