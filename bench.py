@@ -586,8 +586,9 @@ def run_sweep(pkg, args):
                 fns["dgrad"] = lambda: pkg.distortion_aware_ops.conv2d_backward(layer, x, dy, need_dw=False, dx_out=dx)     # row-strip kernel over the transposed plan
                 fns["dgrad (scatter kernel)"] = lambda: check(lib.sky_da_conv2d_bwd_data(dy.data_ptr(), layer.offset_table.data_ptr(), layer.kernel.data_ptr(),
                                                                                          dx.data_ptr(), B, H, W, Ci, F, k, 0, st()))
-                fns["wgrad"] = lambda: check(lib.sky_conv2d_bwd_filter(x.data_ptr(), dy.data_ptr(), layer.offset_table.data_ptr(), dk.data_ptr(), db.data_ptr(),
-                                                                       B, H, W, Ci, Ci, F, k, 1, 0, st()))
+                fns["wgrad"] = lambda: pkg.distortion_aware_ops.conv2d_backward(layer, x, dy, need_dx=False, dk_out=dk, db_out=db)   # strip formulation (strip_wgrad.cu)
+                fns["wgrad (gather kernel)"] = lambda: check(lib.sky_conv2d_bwd_filter(x.data_ptr(), dy.data_ptr(), layer.offset_table.data_ptr(), dk.data_ptr(),
+                                                                                        db.data_ptr(), B, H, W, Ci, Ci, F, k, 1, 0, st()))
             flops, nbytes = 2.0 * M * k * k * Ci * F, 4.0 * M * (Ci + F)
             tensor_bound = flops / nbytes >= tf32_peak * 1e12 / (hbm * 1e9)
             for name, fn in fns.items():

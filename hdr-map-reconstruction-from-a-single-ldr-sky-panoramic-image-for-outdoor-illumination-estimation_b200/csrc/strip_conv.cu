@@ -713,7 +713,7 @@ static int launch_strip(const StripLaunch &a, const StripPlan &pl)
     // ring holds half as many stages) -> only for narrow layers
     const int tiles_per_row = p.tiles_x * p.tiles_b;
     p.pair = 1;
-    if (!SPLIT3 && nsub == 1 && nimages == 1 && Fp <= SC_PAIR_MAX_N && tiles_per_row >= 2 && (long)pl.nrows * ((tiles_per_row + 1) / 2) >= 2L * num_sms_cached() &&
+    if ((!SPLIT3 || getenv("SKY_STRIP_PAIR3")) && nsub == 1 && nimages == 1 && Fp <= SC_PAIR_MAX_N && tiles_per_row >= 2 && (long)pl.nrows * ((tiles_per_row + 1) / 2) >= 2L * num_sms_cached() &&
         !(a.flags & SKY_EPI_NO_PAIR) && !getenv("SKY_STRIP_NO_PAIR"))
         p.pair = 2;
     for (;;) {
@@ -741,10 +741,8 @@ static int launch_strip(const StripLaunch &a, const StripPlan &pl)
     if (gx < 1) gx = 1;
     if (gx > p.nwork) gx = p.nwork;
     if (p.pair == 2) {
-        if constexpr (!SPLIT3) {
-            SKY_ENSURE_DYN_SMEM((strip_conv_kernel<false, 2>), 227 * 1024);
-            strip_conv_kernel<false, 2><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);
-        }
+        SKY_ENSURE_DYN_SMEM((strip_conv_kernel<SPLIT3, 2>), 227 * 1024);
+        strip_conv_kernel<SPLIT3, 2><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);
     } else {
         SKY_ENSURE_DYN_SMEM((strip_conv_kernel<SPLIT3, 1>), 227 * 1024);
         strip_conv_kernel<SPLIT3, 1><<<dim3(gx, nslices), SC_THREADS, smem, a.stream>>>(p);

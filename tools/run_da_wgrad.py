@@ -23,7 +23,7 @@ for _ in range(reps):
     e.record()
     torch.cuda.synchronize()
     ms.append(s.elapsed_time(e))
-print("wgrad", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:]) / 1e9))
+print("wgrad", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:] or ms) / 1e9))
 # the pipelined kernel of csrc/conv_bwd.cu through sky_conv2d_bwd_filter (offsets != NULL)
 lib, check = pkg._lib.LIB, pkg._lib.check
 dk, db = torch.empty_like(layer.kernel), torch.empty_like(layer.bias)
@@ -37,4 +37,4 @@ for _ in range(reps):
     e.record()
     torch.cuda.synchronize()
     ms.append(s.elapsed_time(e))
-print("wgrad (pipelined kernel, sky_conv2d_bwd_filter)", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:]) / 1e9))
+print("wgrad (pipelined kernel, sky_conv2d_bwd_filter)", (B, h, w, C, F, k), "ms", [round(m, 4) for m in ms], "TFLOP/s best %.1f" % (fl / min(ms[1:] or ms) / 1e9))
