@@ -732,6 +732,14 @@ static int launch_strip(const StripLaunch &a, const StripPlan &pl)
         if (Fp % (32 * nsub) != 0) return SKY_ERR_UNSUPPORTED;
         nsub *= 2;                                            // nothing fits: slice the filters further
     }
+    if (const char *ring = getenv("SKY_STRIP_RING")) {        // tuning: "G,NSB,NWB" replaces the choice above when it fits
+        int g = 0, nsb = 0, nwb = 0;
+        if (sscanf(ring, "%d,%d,%d", &g, &nsb, &nwb) == 3 && (g == 1 || g == 2 || g == 4) && nsb >= 2 && nsb % g == 0 && nwb >= 2 && nwb <= 16 &&
+            L::total_bytes(p.PS, p.Fs, nsb, nwb, p.pair) <= budget) { best_g = g; best_nsb = nsb; best_nwb = nwb; }
+    }
+    if (getenv("SKY_STRIP_VERBOSE"))
+        fprintf(stderr, "strip launch: C=%d F=%d Fs=%d nsub=%d pair=%d PS=%d strip_bytes=%d b_stage=%d G=%d NSB=%d NWB=%d smem=%d nrows=%d tiles/row=%d\n", a.C, a.F, p.Fs, nsub,
+                p.pair, p.PS, L::strip_bytes(p.PS), L::b_stage(p.Fs), best_g, best_nsb, best_nwb, L::total_bytes(p.PS, p.Fs, best_nsb, best_nwb, p.pair), pl.nrows, tiles_per_row);
     const int nslices = nimages * nsub;
     p.pairs_per_row = (tiles_per_row + p.pair - 1) / p.pair;
     p.nwork = pl.nrows * p.pairs_per_row;
