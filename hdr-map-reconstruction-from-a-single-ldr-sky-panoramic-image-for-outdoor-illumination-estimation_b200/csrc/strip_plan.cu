@@ -577,6 +577,40 @@ extern "C" int sky_da_strip_plan_export(const float *offsets_host, int h, int w,
     return SKY_ERR_INVALID;
 }
 
+// Weight-gradient plans (strip_wgrad.cu): the forward plan with tiles of 8 columns x 8 panoramas, plus its accumulation units / MMA
+// groups.  info: out12 = rows, strips, windows, terms, exact-tap strips, tile width, panoramas per tile, largest window shift of a strip,
+// units, groups, most groups of a unit, 0.  export: the tables of sky_da_strip_plan_export + units {row, strip, group_begin, group_end}
+// and groups {start_row, win[4]} (int32).
+extern "C" int sky_da_strip_wgrad_plan_info(const float *offsets_host, int h, int w, int k, int wpg, int gmax, int *out12)
+{
+    SKY_REQUIRE(offsets_host && out12, SKY_ERR_INVALID, "NULL pointer");
+    SKY_REQUIRE(wpg == 1 || wpg == 4, SKY_ERR_INVALID, "wpg must be 1 or 4");
+    const StripPlan *pl = nullptr;
+    int rc = get_plan_da_wgrad(offsets_host, h, w, k, wpg, gmax, &pl, false);
+    SKY_REQUIRE(rc == SKY_OK, rc, "no weight-gradient plan for h=%d w=%d k=%d", h, w, k);
+    plan_info(*pl, out12);
+    out12[7] = pl->span_max; out12[8] = pl->n_wg_units; out12[9] = pl->n_wg_groups; out12[10] = pl->max_groups_unit; out12[11] = 0;
+    return SKY_OK;
+}
+
+extern "C" int sky_da_strip_wgrad_plan_export(const float *offsets_host, int h, int w, int k, int wpg, int gmax, void *rows, void *strips,
+                                              void *wins, int *term_begin, void *terms, void *units, void *groups)
+{
+    SKY_REQUIRE(offsets_host, SKY_ERR_INVALID, "NULL pointer");
+    const StripPlan *pl = nullptr;
+    int rc = get_plan_da_wgrad(offsets_host, h, w, k, wpg, gmax, &pl, false);
+    SKY_REQUIRE(rc == SKY_OK, rc, "no weight-gradient plan for h=%d w=%d k=%d", h, w, k);
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : g_da)
+        if (&kv.second->dev == pl) {
+            const HostPlan &hp = *kv.second;
+            if (units) memcpy(units, hp.wg_units.data(), hp.wg_units.size() * sizeof(WgUnit));
+            if (groups) memcpy(groups, hp.wg_groups.data(), hp.wg_groups.size() * sizeof(WgGroup));
+            return export_plan(hp, rows, strips, wins, term_begin, terms);
+        }
+    return SKY_ERR_INVALID;
+}
+
 extern "C" int sky_conv_strip_plan_info(int h, int w, int k, int stride, int transposed, int out_h, int out_w, int ph0, int pw0, int *out8)
 {
     SKY_REQUIRE(out8, SKY_ERR_INVALID, "NULL pointer");

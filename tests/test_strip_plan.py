@@ -248,3 +248,97 @@ def test_da_strip_plan_data_gradient(pkg, h, w, k):
     assert int(wins["start_row"].max()) + 128 <= int(info[7])
     print("transposed plan", (h, w, k), "windows per row", [int(sum(s["we"] - s["wb"] for s in strips[r["sb"]:r["se"]])) for r in rows][:12],
           "strips per row", [int(r["se"] - r["sb"]) for r in rows][:12], "SR", int(info[7]))
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# weight-gradient plans (csrc/strip_wgrad.cu): units / MMA groups over the forward plan with tiles of 8 columns x 8 panoramas
+# --------------------------------------------------------------------------------------------------------------------------------
+UNIT = np.dtype([("row", "i4"), ("strip", "i4"), ("gb", "i4"), ("ge", "i4")])
+GROUP = np.dtype([("start_row", "i4"), ("win", "i4", (4,))])
+
+
+def da_wgrad_plan(pkg, off, h, w, k, wpg, gmax):
+    lib, chk = pkg._lib.LIB, pkg._lib.check
+    info = np.zeros(12, np.int32)
+    chk(lib.sky_da_strip_wgrad_plan_info(_vp(off), h, w, k, wpg, gmax, _vp(info)))
+    nr, ns, nw, nt = (int(v) for v in info[:4])
+    rows, strips, wins = np.zeros(nr, ROW), np.zeros(ns, STRIP), np.zeros(nw, WIN)
+    tb, terms = np.zeros(nw + 1, np.int32), np.zeros(max(nt, 1), TERM)
+    units, groups = np.zeros(int(info[8]), UNIT), np.zeros(int(info[9]), GROUP)
+    chk(lib.sky_da_strip_wgrad_plan_export(_vp(off), h, w, k, wpg, gmax, _vp(rows), _vp(strips), _vp(wins), _vp(tb), _vp(terms), _vp(units), _vp(groups)))
+    return info, rows, strips, wins, tb, terms, units, groups
+
+
+def emulate_da_wgrad(x, dy, off, k, plan):
+    """What strip_wgrad_kernel computes, from the exported plan, in fp64: per unit and MMA group the accumulators
+    G[c, f] = sum over panoramas, columns of strip[column + shift, c] * dy[column, f] (one per window of the group), added to the taps of the
+    window with their coefficients."""
+    info, rows, strips, wins, tb, terms, units, groups = plan
+    B, h, w, C = x.shape
+    F = dy.shape[-1]
+    NB = int(info[6])
+    (ph0, _), pw = O.pad_amounts(h, k), O.pad_amounts(w, k)
+    pw0, in_w = pw[0], w + sum(pw)
+    samp = O.sample(h, w, k, off)
+    dk = np.zeros((k * k, C, F))
+    x64, dy64 = x.astype(np.float64), dy.astype(np.float64)
+    jj = np.arange(w)
+    for u in units:
+        rp, sd = rows[u["row"]], strips[u["strip"]]
+        i = int(rp["out_row"])
+        for g in groups[u["gb"]:u["ge"]]:
+            for q, wi in enumerate(g["win"]):
+                if wi < 0:
+                    continue
+                assert sd["wb"] <= wi < sd["we"]
+                assert wins[wi]["start_row"] == g["start_row"] + q * NB          # quarter q of the MMA = the window one column shift further
+                if sd["kind"] == 1:
+                    t = int(sd["r0"])
+                    pix = np.zeros((B, w, C))
+                    for (yn, xn, wn) in (("y0", "x0", "w0"), ("y0", "x1", "w1"), ("y1", "x0", "w2"), ("y1", "x1", "w3")):
+                        r, c = samp[yn][i, :, t] - ph0, samp[xn][i, :, t] - pw0
+                        ok = (r >= 0) & (r < h) & (c >= 0) & (c < w)
+                        pix[:, ok] += samp[wn][i, ok, t][None, :, None].astype(np.float64) * x64[:, r[ok], c[ok]]
+                    G = np.einsum("bjc,bjf->cf", pix, dy64[:, i])
+                else:
+                    v0 = x64[:, sd["r0"]] if sd["r0"] >= 0 else np.zeros((B, w, C))
+                    v1 = x64[:, sd["r1"]] if sd["r1"] >= 0 else np.zeros((B, w, C))
+                    v = float(sd["wy0"]) * v0 + float(sd["wy1"]) * v1
+                    shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // NB
+                    cols = np.array([map_col(int(sd["cm"]) * (j + shift) + int(sd["c0"]) + pw0, in_w, pw0, w) for j in jj])
+                    ok = cols >= 0
+                    G = np.einsum("bjc,bjf->cf", v[:, cols[ok]], dy64[:, i, ok])
+                for t in terms[tb[wi]:tb[wi + 1]]:
+                    dk[int(t["tap"])] += float(t["coef"]) * G
+    return dk.reshape(k * k * C, F)
+
+
+@pytest.mark.parametrize("h,w,k,wpg,gmax", [(8, 32, 3, 1, 4), (16, 64, 3, 1, 8), (32, 128, 7, 4, 16), (16, 64, 5, 4, 5), (4, 16, 3, 4, 16)])
+def test_da_wgrad_plan_reproduces_the_weight_gradient(pkg, h, w, k, wpg, gmax):
+    rng = np.random.default_rng(h + w + k + wpg)
+    B, C, F = 3, 4, 5
+    off = O.offsets(h, w, k)
+    x = rng.standard_normal((B, h, w, C)).astype(np.float32)
+    dy = rng.standard_normal((B, h, w, F)).astype(np.float32)
+    kern = rng.standard_normal((k * k * C, F)).astype(np.float32)
+    plan = da_wgrad_plan(pkg, off, h, w, k, wpg, gmax)
+    info, rows, strips, wins, tb, terms, units, groups = plan
+    # structure: tiles of 8 columns x 8 panoramas, every window in exactly one group, at most gmax accumulators per unit, window starts
+    # on whole column shifts (8 strip rows = two K atoms of the MN-major operand), spans within the strip the kernel allocates
+    assert int(info[5]) == 8 and int(info[6]) == 8
+    seen = np.zeros(len(wins), np.int32)
+    for u in units:
+        assert 1 <= u["ge"] - u["gb"] <= gmax
+        for g in groups[u["gb"]:u["ge"]]:
+            assert g["start_row"] % 8 == 0 and g["win"][0] >= 0
+            for wi in g["win"]:
+                if wi >= 0:
+                    seen[wi] += 1
+            if wpg == 1:
+                assert (g["win"][1:] < 0).all()
+    assert (seen == 1).all()
+    assert int(wins["start_row"].max()) // 8 <= int(info[7]) <= (8 if wpg == 4 else 4)
+    want = O.conv2d_backward(x, kern, np.zeros(F, np.float32), dy, k, acc_dtype=torch.float64)[1].numpy()
+    got = emulate_da_wgrad(x, dy, off, k, plan)
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel <= 3e-5, (rel, info)
