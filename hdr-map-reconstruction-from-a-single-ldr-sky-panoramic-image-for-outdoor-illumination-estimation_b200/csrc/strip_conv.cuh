@@ -48,8 +48,9 @@ struct WeffTerm {
 };
 
 // Weight gradient over a forward plan (strip_wgrad.cu).  One MMA group = one tcgen05.mma chain whose A operand starts at strip row
-// `start_row`; its 128 accumulator lanes are either the (up to) 128 channels of window win[0] (layers with C >= 64) or the 32 channels
-// of the four windows win[0..3] at consecutive column shifts (C == 32: a shift of one column is exactly one MN atom of the operand).
+// `start_row`; its 128 accumulator lanes are either the (up to) 128 channels of window win[0], or the channels of the wpg windows
+// win[0 .. wpg-1] at consecutive column shifts (C == 64: two windows, C == 32: four — the operand is laid out so that the MN atoms of
+// neighbouring column shifts follow each other).
 struct WgGroup {
     int start_row;
     int win[4];                    // window index per 32-lane quarter, -1: the quarter is not stored

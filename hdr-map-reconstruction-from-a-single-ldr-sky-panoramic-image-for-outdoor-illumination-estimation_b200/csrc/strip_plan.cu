@@ -182,10 +182,10 @@ void build_wgrad_units(HostPlan &hp, int NB, int wpg, int gmax)
                 g.start_row = hp.wins[wi].start_row;
                 g.win[0] = wi; g.win[1] = g.win[2] = g.win[3] = -1;
                 int nx = wi + 1;
-                if (wpg == 4)
+                if (wpg > 1)
                     for (; nx < sd.win_end; ++nx) {                 // windows are sorted by shift, shifts are distinct
                         const int q = (hp.wins[nx].start_row - g.start_row) / NB;
-                        if (q > 3) break;
+                        if (q > wpg - 1) break;
                         g.win[q] = nx;
                     }
                 groups.push_back(g);
@@ -584,7 +584,7 @@ extern "C" int sky_da_strip_plan_export(const float *offsets_host, int h, int w,
 extern "C" int sky_da_strip_wgrad_plan_info(const float *offsets_host, int h, int w, int k, int wpg, int gmax, int *out12)
 {
     SKY_REQUIRE(offsets_host && out12, SKY_ERR_INVALID, "NULL pointer");
-    SKY_REQUIRE(wpg == 1 || wpg == 4, SKY_ERR_INVALID, "wpg must be 1 or 4");
+    SKY_REQUIRE(wpg == 1 || wpg == 2 || wpg == 4, SKY_ERR_INVALID, "wpg must be 1, 2 or 4");
     const StripPlan *pl = nullptr;
     int rc = get_plan_da_wgrad(offsets_host, h, w, k, wpg, gmax, &pl, false);
     SKY_REQUIRE(rc == SKY_OK, rc, "no weight-gradient plan for h=%d w=%d k=%d", h, w, k);

@@ -44,8 +44,11 @@ struct SwParams {
     int B, H, W, C, OH, OW, F;
     int weff, da, in_h, in_w, ph0, pw0, k;
     int ncols, ocs;
-    int SR, nreg, wpg;                 // strip rows; 32-channel regions of the A tile that are written; windows per MMA group
-    int a_lbo;                         // bytes between the MN atoms of A: one region (SR * 128) or one column shift (wpg == 4)
+    int SR, nreg, wpg;                 // strip rows (column * 8 + panorama); 32-channel chunks of the A tile that are written; windows per MMA group
+    int nch;                           // A layout: 0 = one region of SR rows per 32-channel chunk (C >= 96); 1 / 2 = rows interleaved as
+                                       // (column * nch + chunk) * 8 + panorama (C = 32 / 64), so that the MN atoms of an MMA are the chunks
+                                       // of wpg = 4 / nch windows at consecutive column shifts, 1024 bytes apart
+    int a_lbo, a_kstep;                // bytes between the MN atoms of A; 16-byte units between the K = 8 steps of a window
     int NF, ncc, nfc;                  // filters per MMA (N), channel chunks of 128, filter chunks of NF
     int TW, KT;                        // columns / pixels of a tile
     int tiles_x, tiles_b, ntiles;      // pixel tiles of one output row
@@ -65,6 +68,13 @@ __device__ __forceinline__ void sw_red_add_v4(float *addr, float a, float b, flo
 __device__ __forceinline__ uint32_t sw_offset(uint32_t row, uint32_t chunk16)
 {
     return row * 128u + ((((chunk16 >> 1) ^ (row & 3u)) << 5) | ((chunk16 & 1u) << 4));
+}
+// byte offset of (strip row rho = column * 8 + panorama, 32-channel chunk r, 16-byte chunk c16) in the A tile
+template <class P>
+__device__ __forceinline__ uint32_t sw_a_off(const P &p, int rho, int r, int c16)
+{
+    if (p.nch) return sw_offset((uint32_t)((((rho >> 3) * p.nch + r) << 3) | (rho & 7)), (uint32_t)c16);
+    return (uint32_t)(r * (p.SR * 128)) + sw_offset((uint32_t)rho, (uint32_t)c16);
 }
 __device__ __forceinline__ uint4 sw_tf32x4(float4 v)
 {
@@ -123,7 +133,6 @@ __device__ __forceinline__ void sw_fill_strip(const SwParams &p, const StripDesc
     const float *x1 = p.x + (size_t)(sd.r1 >= 0 ? sd.r1 : 0) * p.W * p.C + ch0;
     const int ubase = j0 + sd.u0, img_elems = p.H * p.W;
     int off[NPASS];
-    uint32_t so[NPASS];
 #pragma unroll
     for (int ps = 0; ps < NPASS; ++ps) {
         const int rho = rr + ps * SW_RP;
@@ -132,7 +141,6 @@ __device__ __forceinline__ void sw_fill_strip(const SwParams &p, const StripDesc
         if (p.da) col = da_map_col(col + p.pw0, p.in_w, p.pw0, p.W);
         const bool ok = (unsigned)col < (unsigned)p.W && bimg < p.B;
         off[ps] = ok ? (bimg * img_elems + col) * p.C : -1;
-        so[ps] = sw_offset((uint32_t)rho, (uint32_t)c16);
     }
     if (has1) {
 #pragma unroll
@@ -140,7 +148,7 @@ __device__ __forceinline__ void sw_fill_strip(const SwParams &p, const StripDesc
             if (rr + ps * SW_RP < p.SR) {
 #pragma unroll
                 for (int r = 0; r < NREG; ++r)
-                    cp_async16(smem_u32(a_tile + r * (p.SR * 128) + so[ps]), x1 + (off[ps] >= 0 ? off[ps] : 0) + r * 32, off[ps] >= 0);
+                    cp_async16(smem_u32(a_tile + sw_a_off(p, rr + ps * SW_RP, r, c16)), x1 + (off[ps] >= 0 ? off[ps] : 0) + r * 32, off[ps] >= 0);
             }
     }
     float4 v0[NPASS][NREG];
@@ -157,7 +165,7 @@ __device__ __forceinline__ void sw_fill_strip(const SwParams &p, const StripDesc
         if (rr + ps * SW_RP < p.SR) {
 #pragma unroll
             for (int r = 0; r < NREG; ++r) {
-                uint4 *ptr = reinterpret_cast<uint4 *>(a_tile + r * (p.SR * 128) + so[ps]);
+                uint4 *ptr = reinterpret_cast<uint4 *>(a_tile + sw_a_off(p, rr + ps * SW_RP, r, c16));
                 float4 v;
                 v.x = sd.wy0 * v0[ps][r].x; v.y = sd.wy0 * v0[ps][r].y; v.z = sd.wy0 * v0[ps][r].z; v.w = sd.wy0 * v0[ps][r].w;
                 if (has1) {
@@ -254,7 +262,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) strip_wgrad_kernel(const SwPara
                         const Sample sm = da_sample(row.out_row, j, ta, tb, sd.wy0, sd.wy1, p.in_h, p.in_w);
                         cr = da_corners(sm, bimg, p.H, p.W, p.C, p.ph0, p.pw0);
                     }
-                    const uint32_t so = sw_offset((uint32_t)rho, (uint32_t)c16);
                     for (int r = 0; r < nreg; ++r) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (ok) {
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) strip_wgrad_kernel(const SwPara
                                 v.z = fmaf(cr.w[u], pv.z, v.z); v.w = fmaf(cr.w[u], pv.w, v.w);
                             }
                         }
-                        *reinterpret_cast<uint4 *>(a_tile + r * (p.SR * 128) + so) = sw_tf32x4(v);
+                        *reinterpret_cast<uint4 *>(a_tile + sw_a_off(p, rho, r, c16)) = sw_tf32x4(v);
                     }
                 }
             }
@@ -321,9 +328,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) strip_wgrad_kernel(const SwPara
             mbar_wait_sleep(acc_full, n & 1);
             tc_fence_after();
             if (tid == 0 && n == 0) sw_stamp(p.trace, 100);
-            const int c = p.wpg == 4 ? lane : q.cc * 128 + warp * 32 + lane;
+            const int cpw = 128 / p.wpg, wq = (warp * 32) / cpw;          // accumulator lanes per window; this warp's window of a group
+            const int c = q.cc * 128 + (warp * 32) % cpw + lane;
             for (int g = u.group_begin; g < u.group_end; ++g) {
-                const int win = __ldg(&p.groups[g].win[p.wpg == 4 ? warp : 0]);
+                const int win = __ldg(&p.groups[g].win[wq]);
                 int t_lo = 0, t_hi = 1, tap1 = 0;
                 if (win >= 0) {
                     if (p.weff) { t_lo = __ldg(p.term_begin + win); t_hi = __ldg(p.term_begin + win + 1); }
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) strip_wgrad_kernel(const SwPara
         const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)p.NF) | (1u << 15) | (1u << 16);       // both operands MN-major
         const uint32_t a_hi = (512u >> 4) | (1u << 14) | (1u << 29);                                   // sbo, descriptor version, SWIZZLE_128B_BASE32B
         const uint32_t a_lbo = (((uint32_t)p.a_lbo >> 4) & 0x3FFFu) << 16, b_lbo = (((uint32_t)(p.KT * 128) >> 4) & 0x3FFFu) << 16;
+        const uint32_t a_kstep = (uint32_t)p.a_kstep, a_rowu = 8u * (uint32_t)(p.nch > 1 ? p.nch : 1);
         uint32_t s = 0, phase = 0;
         int cur_uidx = -1, ng = 0, n = 0, ti = -1;
         for (int ls = 0; ls < nseq; ++ls) {
@@ -391,11 +400,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) strip_wgrad_kernel(const SwPara
             const uint32_t a0 = (smem_u32(smem + s * p.stage_bytes) & 0x3FFFFu) >> 4, b0 = a0 + ((uint32_t)p.a_bytes >> 4);
             if (elect_one()) {                   // one lane issues everything up to the commits (tcgen05.commit tracks the issuing thread's MMAs)
                 for (int g = 0; g < ng; ++g) {
-                    const uint32_t a_g = a0 + (uint32_t)s_grow[g] * 8u;                    // start row * 128 B, in 16-byte units
+                    const uint32_t a_g = a0 + (uint32_t)s_grow[g] * a_rowu;                // start row (x chunks per column) * 128 B, in 16-byte units
                     const uint32_t d_g = tmem_base + (uint32_t)(g * p.NF);
 #pragma unroll 8
                     for (int k8 = 0; k8 < p.TW; ++k8) {
-                        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)((a_g + k8 * 64u) | a_lbo);
+                        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)((a_g + k8 * a_kstep) | a_lbo);
                         const uint64_t db = ((uint64_t)a_hi << 32) | (uint64_t)((b0 + k8 * 64u) | b_lbo);
                         umma_tf32(d_g, da, db, idesc, (first_tile && k8 == 0) ? 0u : 1u);
                     }
@@ -490,7 +499,8 @@ int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_hos
     const int Fp = round_up(F, 32);
     p.NF = Fp < 128 ? Fp : 128;
     p.nfc = (Fp + p.NF - 1) / p.NF;
-    p.wpg = C == 32 ? 4 : 1;
+    p.wpg = C == 32 ? 4 : (C == 64 ? 2 : 1);
+    p.nch = C == 32 ? 1 : (C == 64 ? 2 : 0);
     p.ncc = (C + 127) / 128;
     const int gmax = (512 / p.NF) < SW_MAX_GROUPS ? (512 / p.NF) : SW_MAX_GROUPS;
     const StripPlan *pl = nullptr;
@@ -514,17 +524,18 @@ int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_hos
     p.weff = pl->weff; p.ncols = pl->ncols; p.ocs = pl->ocs;
     // tile width: 8 columns where the strip is 128 channels wide; 32-channel layers take 32 columns per tile (a stage costs a round trip
     // to L2 whatever it holds, and their tiles are small)
-    p.nreg = p.wpg == 4 ? 1 : (C >= 128 ? 4 : C / 32);
+    p.nreg = C >= 128 ? 4 : C / 32;
     const int budget = 227 * 1024 - 2048;
     // (12 columns where the rows are long enough for the ragged last tile not to matter: a third less halo per strip, measured +5 %)
-    for (p.TW = getenv("SKY_WGRAD_TW") ? atoi(getenv("SKY_WGRAD_TW")) : (p.wpg == 4 ? 32 : (pl->ncols >= 96 ? 12 : 8));; p.TW -= (p.TW == 12 ? 4 : 8)) {
+    for (p.TW = getenv("SKY_WGRAD_TW") ? atoi(getenv("SKY_WGRAD_TW")) : (p.wpg == 4 ? 32 : (p.wpg == 2 ? 16 : (pl->ncols >= 96 ? 12 : 8)));; p.TW -= (p.TW == 12 ? 4 : 8)) {
         if (p.TW > round_up(pl->ncols, 8)) p.TW = round_up(pl->ncols, 8);
         if (p.TW < 8) p.TW = 8;
         p.KT = p.TW * SW_NB;
-        p.SR = (p.TW + pl->span_max + (p.wpg == 4 ? 3 : 0)) * SW_NB;
-        p.a_lbo = p.wpg == 4 ? SW_NB * 128 : p.SR * 128;
+        p.SR = (p.TW + pl->span_max + p.wpg - 1) * SW_NB;
+        p.a_lbo = p.nch ? SW_NB * 128 : p.SR * 128;
+        p.a_kstep = 64 * (p.nch > 1 ? p.nch : 1);
         // the A tile is sized for the four MN atoms an M = 128 MMA reads (64-channel layers leave two of them unwritten: their lanes are not stored)
-        p.a_bytes = p.wpg == 4 ? p.SR * 128 : 4 * p.SR * 128;
+        p.a_bytes = p.nch ? p.nch * p.SR * 128 : 4 * p.SR * 128;
         p.stage_bytes = p.a_bytes + (p.NF / 32) * p.KT * 128;
         p.stages = budget / p.stage_bytes;
         if (p.stages >= 2 || p.TW <= 8) break;

@@ -313,7 +313,7 @@ def emulate_da_wgrad(x, dy, off, k, plan):
     return dk.reshape(k * k * C, F)
 
 
-@pytest.mark.parametrize("h,w,k,wpg,gmax", [(8, 32, 3, 1, 4), (16, 64, 3, 1, 8), (32, 128, 7, 4, 16), (16, 64, 5, 4, 5), (4, 16, 3, 4, 16)])
+@pytest.mark.parametrize("h,w,k,wpg,gmax", [(8, 32, 3, 1, 4), (16, 64, 3, 1, 8), (32, 128, 7, 4, 16), (16, 64, 5, 4, 5), (4, 16, 3, 4, 16), (16, 64, 3, 2, 8), (8, 32, 5, 2, 4)])
 def test_da_wgrad_plan_reproduces_the_weight_gradient(pkg, h, w, k, wpg, gmax):
     rng = np.random.default_rng(h + w + k + wpg)
     B, C, F = 3, 4, 5
@@ -338,6 +338,8 @@ def test_da_wgrad_plan_reproduces_the_weight_gradient(pkg, h, w, k, wpg, gmax):
                 assert (g["win"][1:] < 0).all()
     assert (seen == 1).all()
     assert int(wins["start_row"].max()) // 8 <= int(info[7]) <= (8 if wpg == 4 else 4)
+    if wpg > 1:
+        assert all((g["win"][wpg:] < 0).all() for g in groups)
     want = O.conv2d_backward(x, kern, np.zeros(F, np.float32), dy, k, acc_dtype=torch.float64)[1].numpy()
     got = emulate_da_wgrad(x, dy, off, k, plan)
     rel = np.linalg.norm(got - want) / np.linalg.norm(want)
