@@ -46,7 +46,7 @@ SIGNATURES = {
     "sky_da_conv2d_fwd_simt": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sky_da_conv2d_bwd_data": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
-    "sky_da_conv2d_bwd_filter_strip": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
+    "sky_da_conv2d_bwd_filter_strip": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
     "sky_debug_wgrad_trace": (_i, [_vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
     "sky_instnorm_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp]),

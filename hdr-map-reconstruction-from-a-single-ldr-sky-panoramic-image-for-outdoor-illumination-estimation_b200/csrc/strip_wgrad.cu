@@ -593,8 +593,9 @@ using namespace sky;
 
 // Weight gradient of the distortion-aware layer on the strip formulation (same contract as sky_da_conv2d_bwd_filter, with the HOST copy
 // of the offset table the strip plans are built from).
+// accumulate != 0: dkernel / dbias are added to (the caller zeroed them, e.g. one memset of a flat gradient buffer per step).
 extern "C" int sky_da_conv2d_bwd_filter_strip(const float *x, const float *dy, const float *offsets_host, float *dkernel, float *dbias, int B,
-                                              int h, int w, int C, int F, int k, void *stream)
+                                              int h, int w, int C, int F, int k, int accumulate, void *stream)
 {
     SKY_REQUIRE(x && dy && offsets_host && dkernel, SKY_ERR_INVALID, "NULL pointer");
     SKY_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && F > 0, SKY_ERR_INVALID, "non-positive dimension");
@@ -603,12 +604,12 @@ extern "C" int sky_da_conv2d_bwd_filter_strip(const float *x, const float *dy, c
     SKY_REQUIRE(C % 32 == 0, SKY_ERR_UNSUPPORTED, "the strip weight gradient needs C %% 32 == 0 (got %d)", C);
     SKY_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dkernel & 15) == 0, SKY_ERR_INVALID, "x, dy and dkernel must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    SKY_CHECK_CUDA(cudaMemsetAsync(dkernel, 0, (size_t)k * k * C * F * sizeof(float), st));
+    if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dkernel, 0, (size_t)k * k * C * F * sizeof(float), st));
     const int rc = launch_wgrad_strip(x, dy, offsets_host, dkernel, B, h, w, C, F, k, 1, st);
     SKY_REQUIRE(rc == SKY_OK, rc, "no strip weight-gradient plan for B=%d h=%d w=%d C=%d F=%d k=%d", B, h, w, C, F, k);
     if (dbias) {
         const int M = B * h * w;
-        SKY_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)F * sizeof(float), st));
+        if (!accumulate) SKY_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)F * sizeof(float), st));
         return launch_col_sum(dy, dbias, M, F, st);
     }
     return SKY_OK;

@@ -50,12 +50,16 @@ def conv_backward(conv, x, dy, fv, need_dx=True, residual=None):
     """Weight / bias gradients into the flat buffer and (optionally) the data gradient (+ residual) of either conv flavour."""
     kname, bname = _kernel_attr(conv)
     dk, db = fv.grad(conv, kname), fv.grad(conv, bname)
+    # fv.zeroed_each_step (set by train.Step, which zeroes the flat gradient buffer once before the backward pass): the weight-gradient
+    # kernels add to the views instead of zeroing them first — two memset nodes less per conv in the step's graph
+    acc = bool(getattr(fv, "zeroed_each_step", False))
     if isinstance(conv, da_conv2d):
         dx = None
         if need_dx and residual is not None:
             dx = residual.clone()
-        return conv2d_backward(conv, x, dy, need_dx=need_dx, dx_out=dx, dk_out=dk, db_out=db, accumulate_dx=residual is not None)[0]
-    conv.backward_filter(x, dy, dk, db)
+        return conv2d_backward(conv, x, dy, need_dx=need_dx, dx_out=dx, dk_out=dk, db_out=db, accumulate_dx=residual is not None,
+                               accumulate_dw=acc)[0]
+    conv.backward_filter(x, dy, dk, db, accumulate=acc and x.shape[-1] > 4)
     return conv.backward_data(x, dy, residual=residual) if need_dx else None
 
 

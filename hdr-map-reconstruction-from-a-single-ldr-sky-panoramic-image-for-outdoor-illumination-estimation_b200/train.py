@@ -137,6 +137,7 @@ class Step:
         self.fv_gen = FlatVars(self._gen.owner_list() + conv_owners + fc_owners, dev)          # the Dense variables last: one early bucket
         self._fc_offset = self.fv_gen.offset(self._sun.fc1, "kernel")
         self.fv_dis = FlatVars(self._dis.owner_list(), dev)
+        self.fv_gen.zeroed_each_step = True      # train_step zeroes flat_g[:fc_offset] before the backward pass: conv gradients accumulate
         self.ms_gen = torch.zeros_like(self.fv_gen.flat_w)
         self.ms_dis = torch.zeros_like(self.fv_dis.flat_w)
 
