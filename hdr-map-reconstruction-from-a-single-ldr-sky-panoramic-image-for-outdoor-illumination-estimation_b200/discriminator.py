@@ -142,13 +142,14 @@ class model:
     def train_backward(self, g_same, fv):
         """g_same [2B,hh,ww,1]: gradient of total_disc_loss w.r.t. the SAME map.  Variable gradients go to fv."""
         a4 = self._saved
-        conv_backward_filter(a4, g_same, 4, 1, fv.grad(self, "out_kernel").view(-1, 1), fv.grad(self, "out_bias"))
+        acc = bool(getattr(fv, "zeroed_each_step", False))       # the caller zeroed fv.flat_g: the conv weight gradients add to it
+        conv_backward_filter(a4, g_same, 4, 1, fv.grad(self, "out_kernel").view(-1, 1), fv.grad(self, "out_bias"), acc)
         # the BN backward applies the LeakyReLU mask itself: the out conv's data gradient must arrive unmasked
         if self._tp_out is None:
             self._tp_out = TransposedPack(4, 512, 1, self.math_mode, self.device)
         g = conv_backward_data(self._tp_out, self.out_kernel, tuple(a4.shape), g_same, 1)
         grads = lambda d: {k: fv.grad(d, k) for k in (("kernel", "gamma", "beta") if d.apply_norm else ("kernel",))}
-        g = self.d4.train_backward(g, grads(self.d4))
-        g = self.d3.train_backward(g, grads(self.d3))
-        g = self.d2.train_backward(g, grads(self.d2), dx_mask_src=self.d1._saved["a"])
-        self.d1.train_backward(g, grads(self.d1), need_dx=False)
+        g = self.d4.train_backward(g, grads(self.d4), accumulate=acc)
+        g = self.d3.train_backward(g, grads(self.d3), accumulate=acc)
+        g = self.d2.train_backward(g, grads(self.d2), dx_mask_src=self.d1._saved["a"], accumulate=acc)
+        self.d1.train_backward(g, grads(self.d1), need_dx=False, accumulate=acc)

@@ -271,7 +271,7 @@ class sunRadNet:
 
     __call__ = call
 
-    def train_backward(self, d_out3, grads, dsm, accumulate_dsm=True):
+    def train_backward(self, d_out3, grads, dsm, accumulate_dsm=True, accumulate_dw=False):
         """Backward of the training-mode call whose first output was hdr_logCompression(tile(sun_rad, 3)): d_out3 [B,H,W,3] is the
         gradient w.r.t. that tensor.  grads: dict d1..d4 -> {kernel (, gamma, beta)}, gb_kernel, gb_bias -> gradient views.  The
         gradient w.r.t. the (un-normalised) sun-position map, max-normalisation of generator.py:160 included, is added to dsm."""
@@ -290,7 +290,8 @@ class sunRadNet:
         check(LIB.sky_sunrad_heads_bwd(flat.data_ptr(), self.gb_kernel.data_ptr(), dgb64.data_ptr(), grads["gb_kernel"].data_ptr(),
                                        grads["gb_bias"].data_ptr(), dflat.data_ptr(), B, flat.shape[1], _stream()))
         g = dflat.view(sv["d4_shape"])
-        g = self.d4.train_backward(g, grads["d4"])
-        g = self.d3.train_backward(g, grads["d3"])
-        g = self.d2.train_backward(g, grads["d2"], dx_mask_src=self.d1._saved["a"])      # d1 has no norm: its LeakyReLU mask rides here
-        self.d1.train_backward(g, grads["d1"], need_dx=False)
+        # accumulate_dw: the kernel gradient views were zeroed by the caller (the flat buffer, once per step)
+        g = self.d4.train_backward(g, grads["d4"], accumulate=accumulate_dw)
+        g = self.d3.train_backward(g, grads["d3"], accumulate=accumulate_dw)
+        g = self.d2.train_backward(g, grads["d2"], dx_mask_src=self.d1._saved["a"], accumulate=accumulate_dw)      # d1 has no norm: its LeakyReLU mask rides here
+        self.d1.train_backward(g, grads["d1"], need_dx=False, accumulate=accumulate_dw)

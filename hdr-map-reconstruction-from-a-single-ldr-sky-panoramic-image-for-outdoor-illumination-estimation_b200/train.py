@@ -138,6 +138,7 @@ class Step:
         self._fc_offset = self.fv_gen.offset(self._sun.fc1, "kernel")
         self.fv_dis = FlatVars(self._dis.owner_list(), dev)
         self.fv_gen.zeroed_each_step = True      # train_step zeroes flat_g[:fc_offset] before the backward pass: conv gradients accumulate
+        self.fv_dis.zeroed_each_step = True      # and fv_dis.flat_g before the discriminator's
         self.ms_gen = torch.zeros_like(self.fv_gen.flat_w)
         self.ms_dis = torch.zeros_like(self.fv_dis.flat_w)
 
@@ -278,8 +279,8 @@ class Step:
         fork(s1)
         with torch.cuda.stream(s1):
             # sun radiance -> sun-position softmax (the max-normalisation of generator.py:160 included), joined with the KL adjoint
-            gen.sun.train_backward(d_srg, self._sun_grads(), g_sm, accumulate_dsm=True)
-            sunpose_backward(sun, g_sm, fv.grad, on_dense_done=lambda: work.append(self._start_tail_allreduce()))
+            gen.sun.train_backward(d_srg, self._sun_grads(), g_sm, accumulate_dsm=True, accumulate_dw=True)
+            sunpose_backward(sun, g_sm, fv.grad, on_dense_done=lambda: work.append(self._start_tail_allreduce()), accumulate=True)
             mark("s1: sun branch backward done")
         mark("main: tail backward done")
         dres = torch.empty_like(res_out)

@@ -51,11 +51,12 @@ def sunpose_owner_list(net):
     return owners, [(net.fc1, "kernel"), (net.fc1, "bias"), (net.fc2, "kernel"), (net.fc2, "bias")]
 
 
-def sunpose_backward(net, g_sm, grad_of, on_dense_done=None):
+def sunpose_backward(net, g_sm, grad_of, on_dense_done=None, accumulate=False):
     """Backward of sunposeEstimation (sunpose_net.py:54-72) from the gradient w.r.t. its softmax output: softmax backward (+ ReLU mask),
     Dense weight / data gradients, max-pool gradients, per sunposeLayer the instance-norm backward fused with the ReLU mask and the conv
     weight / data gradients (either wiring; the 3-channel first layer on the small-C kernels).  grad_of(obj, attr) -> gradient view.
-    on_dense_done() is called as soon as the Dense gradients are complete (start of their all-reduce bucket)."""
+    on_dense_done() is called as soon as the Dense gradients are complete (start of their all-reduce bucket).  accumulate: the conv
+    gradient views were zeroed by the caller (one memset of the flat buffer per step): the conv weight gradients add to them."""
     sm, actv1_s, actv2_s, pool_shape, acts = net._saved
     flat = net._saved_flat
     B, n_fc = sm.shape
@@ -91,8 +92,8 @@ def sunpose_backward(net, g_sm, grad_of, on_dense_done=None):
                     check(LIB.sky_da_conv2d_smallc_bwd_filter(xin.data_ptr(), dy.data_ptr(), conv.offset_table.data_ptr(), dk.data_ptr(),
                                                               db.data_ptr(), Bq, h, w, C, conv.filters, conv.kernel_size, _stream()))
                     return None
-                return conv2d_backward(conv, xin, dy, need_dx=need_dx, dk_out=dk, db_out=db)[0]
-            conv.backward_filter(xin, dy, grad_of(conv, "w"), grad_of(conv, "biases"))          # plain wiring (sunpose_net.py:10,15)
+                return conv2d_backward(conv, xin, dy, need_dx=need_dx, dk_out=dk, db_out=db, accumulate_dw=accumulate)[0]
+            conv.backward_filter(xin, dy, grad_of(conv, "w"), grad_of(conv, "biases"), accumulate=accumulate and C > 4)   # plain wiring (sunpose_net.py:10,15)
             return conv.backward_data(xin, dy) if (need_dx and C > 4) else None
 
         g_ = norm_bwd(layer.norm2, conv2, layer._stats[1], g_out, actv2)          # relu (:28) + IN (:26)
@@ -181,7 +182,7 @@ class SunTrainer:
         # data-parallel: the Dense gradients (201 MB at 32x128) are complete before any conv gradient — their all-reduce is started
         # from the callback and runs on NCCL's stream under the rest of the backward pass
         work = []
-        sunpose_backward(net, g_sm, self._g, on_dense_done=lambda: work.append(start_tail_allreduce(self.flat_g, self._fc_offset)))
+        sunpose_backward(net, g_sm, self._g, on_dense_done=lambda: work.append(start_tail_allreduce(self.flat_g, self._fc_offset)), accumulate=True)
         # ---- optimizer (:258) ----
         finish_allreduce(self.flat_g, self._fc_offset, work[0])                   # conv / norm gradients (1 MB), then join
         main.wait_stream(self._side)                                              # Grad-CAM done before Adam invalidates W^T / the packed kernels
