@@ -11,8 +11,11 @@
 // (the im2col producer of conv2d_wgrad_kernel re-gathers it per tap); B = the dy tile [pixel][filter].  Strip row = column * 8 +
 // panorama: a column shift is 8 rows = 1024 bytes, i.e. a window is the same A tile at another (swizzle-aligned) start address.
 // Accumulators (one [C x F] block per window) stay in TMEM over all the pixel tiles a CTA owns of a unit and are added to dW with the
-// tap coefficients by vector atomics.  32-channel layers put four windows at consecutive shifts into the four 32-lane quarters of one
-// MMA (MN-atom stride = one column shift).
+// tap coefficients by vector atomics.  32- / 64-channel layers interleave the operand rows as (column * chunks + 32-channel chunk) * 8 +
+// panorama, so that the four MN atoms of one MMA are the chunks of four / two windows at consecutive column shifts (atom stride 1024 B).
+// dy arrives by TMA through a tensor map with dimensions (filter, panorama, column, row) and CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B — the
+// box lands as rows = column * 8 + panorama in exactly the MN-major operand layout.  Work: every accumulation unit (strip x windows that
+// fit in TMEM) is split over P CTAs of TP pixel tiles, U units run at a time (launch_wgrad_strip's cost model), one drain per wave.
 //
 // Persistent, warp-specialised: two producer groups of 7 warps that take alternate pixel tiles (second input row by cp.async straight
 // into the operand, first row by vector loads, blend in place; dy tile by TMA + in-place TF32 rounding), one MMA warp (elect-issued), 4 drain warps.
