@@ -48,6 +48,7 @@ SIGNATURES = {
     "sky_da_conv2d_bwd_filter": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "sky_da_conv2d_bwd_filter_strip": (_i, [_vp] * 5 + [_i] * 7 + [_vp]),
     "sky_debug_wgrad_trace": (_i, [_vp]),
+    "sky_wgrad_schedule_info": (_i, [_i, _i, _i, _i, _i, _vp]),
     "sky_instnorm_apply": (_i, [_vp] * 6 + [_i, _i, _i, _i, _f, _i, _f, _vp]),
     "sky_instnorm_bwd": (_i, [_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp]),
     "sky_mse_loss": (_i, [_vp] * 4 + [ctypes.c_long, _vp]),
@@ -131,7 +132,7 @@ def load():
 LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2, "sky_da_conv2d_bwd_filter_strip": 2,
                      "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_da_strip_weight_bytes": 0, "sky_da_strip_weight_bytes_t": 0, "sky_da_strip_plan_info": 0, "sky_da_strip_plan_export": 0, "sky_da_strip_wgrad_plan_info": 0, "sky_da_strip_wgrad_plan_export": 0,
                      "sky_conv_strip_plan_info": 0, "sky_conv_strip_plan_export": 0, "sky_last_error": 0, "sky_version": 0,
-                     "sky_debug_band_trace": 0, "sky_debug_strip_trace": 0, "sky_debug_wgrad_trace": 0}
+                     "sky_debug_band_trace": 0, "sky_debug_strip_trace": 0, "sky_debug_wgrad_trace": 0, "sky_wgrad_schedule_info": 0}
 
 
 _UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host", "sky_da_strip_weight_bytes", "sky_da_strip_weight_bytes_t",

@@ -98,6 +98,8 @@ int launch_fwd_strip_plain(const FwdArgs &a);
 int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_host, float *dw, int B, int h, int w, int C, int F, int k,
                        int stride, cudaStream_t stream);
 
+// schedule of the strip weight gradient (strip_wgrad.cu): parts per accumulation, tiles per part, accumulations per wave, waves
+void wgrad_schedule(int nuidx, int ntiles, int sms, bool big, int ucap, int *P_out, int *TP_out, int *U_out, int *nwaves_out);
 // db[f] += column sums of the dense matrix dy [M][F] (bias gradients; db zeroed by the caller)
 int launch_col_sum(const float *dy, float *db, int M, int F, cudaStream_t st);
 

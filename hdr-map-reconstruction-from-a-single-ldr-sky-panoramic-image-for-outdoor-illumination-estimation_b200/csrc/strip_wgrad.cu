@@ -473,6 +473,28 @@ int num_sms()
 
 }  // namespace
 
+// Schedule of the strip weight gradient: every accumulation (unit x channel chunk x filter chunk; nuidx of them) is split over P CTAs of
+// TP pixel tiles each (P * TP >= ntiles), U = SMs / P accumulations run at a time (a wave), and a CTA drains its accumulators once per
+// wave.  P is chosen by a cost model in microseconds (about 1.5 per tile, 3.5 per drain); `big` (the tensors do not fit in L2): U is capped
+// at ucap so that the rows a wave touches do.
+void wgrad_schedule(int nuidx, int ntiles, int sms, bool big, int ucap, int *P_out, int *TP_out, int *U_out, int *nwaves_out)
+{
+    double best = 1e30;
+    int bP = 1, bTP = ntiles, bU = sms < nuidx ? sms : nuidx;
+    for (int P = 1; P <= ntiles && P <= sms; ++P) {
+        const int TP = (ntiles + P - 1) / P, Pe = (ntiles + TP - 1) / TP;
+        int U = sms / Pe;
+        if (U > nuidx) U = nuidx;
+        if (U < 1) continue;
+        if (big && U > ucap && Pe < ntiles) continue;
+        const int waves = (nuidx + U - 1) / U;
+        const double cost = waves * (TP * 1.5 + 3.5);
+        if (cost < best) { best = cost; bP = Pe; bTP = TP; bU = U; }
+    }
+    if (bU < 1) bU = 1;
+    *P_out = bP; *TP_out = bTP; *U_out = bU; *nwaves_out = (nuidx + bU - 1) / bU;
+}
+
 // db[f] (+)= column sums of the dense matrix dy [M][F] (db zeroed by the caller)
 int launch_col_sum(const float *dy, float *db, int M, int F, cudaStream_t st)
 {
@@ -548,26 +570,10 @@ int launch_wgrad_strip(const float *x, const float *dy, const float *offsets_hos
     p.tiles_x = (pl->ncols + p.TW - 1) / p.TW; p.tiles_b = (B + SW_NB - 1) / SW_NB; p.ntiles = p.tiles_x * p.tiles_b;
     p.nuidx = pl->n_wg_units * p.ncc * p.nfc;
     if ((long)p.nuidx * p.ntiles >= (1L << 30)) return SKY_ERR_UNSUPPORTED;
-    // Schedule: every accumulation (unit x channel chunk x filter chunk) is split over P CTAs of TP tiles each, U = SMs / P accumulations
-    // run at a time (a wave), and a CTA drains its accumulators once per wave.  P is chosen by a cost model in units of microseconds
-    // (about 1.5 per tile, 3.5 per drain); when the tensors do not fit in L2, U is capped so that the rows a wave touches do.
     {
-        const int sms = num_sms();
         const bool big = ((double)B * h * w * C + (double)B * p.OH * p.OW * F) * 4.0 > 80e6;
         const int ucap = getenv("SKY_WGRAD_UCAP") ? atoi(getenv("SKY_WGRAD_UCAP")) : 16;
-        double best = 1e30;
-        p.P = 1; p.TP = p.ntiles; p.U = sms < p.nuidx ? sms : p.nuidx;
-        for (int P = 1; P <= p.ntiles && P <= sms; ++P) {
-            const int TP = (p.ntiles + P - 1) / P, Pe = (p.ntiles + TP - 1) / TP;
-            int U = sms / Pe;
-            if (U > p.nuidx) U = p.nuidx;
-            if (U < 1) continue;
-            if (big && U > ucap && Pe < p.ntiles) continue;
-            const int waves = (p.nuidx + U - 1) / U;
-            const double cost = waves * (TP * 1.5 + 3.5);
-            if (cost < best) { best = cost; p.P = Pe; p.TP = TP; p.U = U; }
-        }
-        p.nwaves = (p.nuidx + p.U - 1) / p.U;
+        wgrad_schedule(p.nuidx, p.ntiles, num_sms(), big, ucap, &p.P, &p.TP, &p.U, &p.nwaves);
     }
     const int grid = p.U * p.P;
     p.tmem_cols = 32;
@@ -623,5 +629,13 @@ extern "C" int sky_debug_wgrad_trace(unsigned long long *host_out128)
 {
     SKY_REQUIRE(host_out128, SKY_ERR_INVALID, "NULL pointer");
     SKY_CHECK_CUDA(cudaMemcpyFromSymbol(host_out128, g_wgrad_trace, sizeof(unsigned long long) * 128));
+    return SKY_OK;
+}
+
+/* debug / tests (host only): the schedule launch_wgrad_strip picks — out4 = P, TP, U, waves */
+extern "C" int sky_wgrad_schedule_info(int nuidx, int ntiles, int sms, int big, int ucap, int *out4)
+{
+    SKY_REQUIRE(out4 && nuidx > 0 && ntiles > 0 && sms > 0 && ucap > 0, SKY_ERR_INVALID, "bad arguments");
+    wgrad_schedule(nuidx, ntiles, sms, big != 0, ucap, out4, out4 + 1, out4 + 2, out4 + 3);
     return SKY_OK;
 }

@@ -344,3 +344,27 @@ def test_da_wgrad_plan_reproduces_the_weight_gradient(pkg, h, w, k, wpg, gmax):
     got = emulate_da_wgrad(x, dy, off, k, plan)
     rel = np.linalg.norm(got - want) / np.linalg.norm(want)
     assert rel <= 3e-5, (rel, info)
+
+
+def test_wgrad_schedule_covers_every_tile_once(pkg):
+    """The work split of the strip weight gradient (host logic of launch_wgrad_strip): CTA (ub, pb) of wave w owns tiles
+    [pb * TP, pb * TP + TP) of accumulation w * U + ub — every (accumulation, tile) exactly once, never more CTAs than SMs, and the L2 cap."""
+    lib, chk = pkg._lib.LIB, pkg._lib.check
+    for (nuidx, ntiles, sms, big, ucap) in ((40, 16, 148, 0, 16), (340, 256, 148, 1, 16), (340, 256, 148, 1, 4), (1, 1, 148, 0, 16), (7, 3, 148, 0, 16),
+                                            (500, 2, 148, 0, 16), (3, 1000, 148, 1, 16), (224, 64, 132, 0, 16)):
+        out = np.zeros(4, np.int32)
+        chk(lib.sky_wgrad_schedule_info(nuidx, ntiles, sms, big, ucap, _vp(out)))
+        P, TP, U, waves = (int(v) for v in out)
+        assert P >= 1 and TP >= 1 and U >= 1 and U * P <= sms
+        assert P * TP >= ntiles and (P - 1) * TP < ntiles          # no empty part
+        assert waves == -(-nuidx // U)
+        if big and P < ntiles:
+            assert U <= ucap
+        seen = np.zeros((nuidx, ntiles), np.int32)
+        for w in range(waves):
+            for b in range(U * P):
+                ub, pb = divmod(b, P)
+                u = w * U + ub
+                if u < nuidx:
+                    seen[u, pb * TP:min(ntiles, pb * TP + TP)] += 1
+        assert (seen == 1).all(), (nuidx, ntiles, P, TP, U)
