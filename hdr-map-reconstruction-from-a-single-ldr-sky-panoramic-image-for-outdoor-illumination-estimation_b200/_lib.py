@@ -33,6 +33,8 @@ SIGNATURES = {
     "sky_da_conv2d_fwd_strip": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "sky_da_strip_plan_info": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "sky_da_strip_wgrad_plan_info": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
+    "sky_conv_strip_wgrad_plan_info": (_i, [_i, _i, _i, _i, _i, _i, _vp]),
+    "sky_conv_strip_wgrad_plan_export": (_i, [_i, _i, _i, _i, _i, _i] + [_vp] * 5),
     "sky_da_strip_wgrad_plan_export": (_i, [_vp, _i, _i, _i, _i, _i] + [_vp] * 7),
     "sky_da_strip_plan_export": (_i, [_vp, _i, _i, _i, _i] + [_vp] * 5),
     "sky_da_strip_weight_bytes_t": (_sz, [_vp, _i, _i, _i, _i, _i, _i]),
@@ -130,13 +132,13 @@ def load():
 # kernel launches behind one call of each entry point (memsets not counted); bench.py's gpu_launches is derived from the calls a step
 # makes.  Entry points not listed launch one kernel.
 LAUNCHES_PER_CALL = {"sky_bn_train_stats": 2, "sky_bn_train_bwd": 2, "sky_conv2d_bwd_filter": 2, "sky_dense_fwd": 2, "sky_dense_bwd_data": 1, "sky_instnorm_bwd": 2, "sky_gradcam": 2, "sky_da_conv2d_bwd_filter": 2, "sky_da_conv2d_bwd_filter_strip": 2,
-                     "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_da_strip_weight_bytes": 0, "sky_da_strip_weight_bytes_t": 0, "sky_da_strip_plan_info": 0, "sky_da_strip_plan_export": 0, "sky_da_strip_wgrad_plan_info": 0, "sky_da_strip_wgrad_plan_export": 0,
+                     "sky_da_offsets_host": 0, "sky_zero": 0, "sky_da_packed_weight_bytes": 0, "sky_da_strip_weight_bytes": 0, "sky_da_strip_weight_bytes_t": 0, "sky_da_strip_plan_info": 0, "sky_da_strip_plan_export": 0, "sky_da_strip_wgrad_plan_info": 0, "sky_da_strip_wgrad_plan_export": 0, "sky_conv_strip_wgrad_plan_info": 0, "sky_conv_strip_wgrad_plan_export": 0,
                      "sky_conv_strip_plan_info": 0, "sky_conv_strip_plan_export": 0, "sky_last_error": 0, "sky_version": 0,
                      "sky_debug_band_trace": 0, "sky_debug_strip_trace": 0, "sky_debug_wgrad_trace": 0, "sky_wgrad_schedule_info": 0}
 
 
 _UNTRACED = ("sky_launch_count", "sky_last_error", "sky_version", "sky_da_packed_weight_bytes", "sky_da_offsets_host", "sky_da_strip_weight_bytes", "sky_da_strip_weight_bytes_t",
-             "sky_da_strip_plan_info", "sky_da_strip_plan_export", "sky_da_strip_wgrad_plan_info", "sky_da_strip_wgrad_plan_export", "sky_conv_strip_plan_info", "sky_conv_strip_plan_export")
+             "sky_da_strip_plan_info", "sky_da_strip_plan_export", "sky_da_strip_wgrad_plan_info", "sky_da_strip_wgrad_plan_export", "sky_conv_strip_wgrad_plan_info", "sky_conv_strip_wgrad_plan_export", "sky_conv_strip_plan_info", "sky_conv_strip_plan_export")
 
 
 class _Lib:

@@ -611,6 +611,35 @@ extern "C" int sky_da_strip_wgrad_plan_export(const float *offsets_host, int h, 
     return SKY_ERR_INVALID;
 }
 
+// the same for a plain SAME convolution (stride 1 / 2): out12 as above; export without terms (a window's tap is its wtile0)
+extern "C" int sky_conv_strip_wgrad_plan_info(int h, int w, int k, int stride, int wpg, int gmax, int *out12)
+{
+    SKY_REQUIRE(out12 && (wpg == 1 || wpg == 2 || wpg == 4), SKY_ERR_INVALID, "bad arguments");
+    const StripPlan *pl = nullptr;
+    int rc = get_plan_plain_wgrad(h, w, k, stride, (h + stride - 1) / stride, (w + stride - 1) / stride, wpg, gmax, &pl, false);
+    SKY_REQUIRE(rc == SKY_OK, rc, "no weight-gradient plan for this convolution");
+    plan_info(*pl, out12);
+    out12[7] = pl->span_max; out12[8] = pl->n_wg_units; out12[9] = pl->n_wg_groups; out12[10] = pl->max_groups_unit; out12[11] = 0;
+    return SKY_OK;
+}
+
+extern "C" int sky_conv_strip_wgrad_plan_export(int h, int w, int k, int stride, int wpg, int gmax, void *rows, void *strips, void *wins,
+                                                void *units, void *groups)
+{
+    const StripPlan *pl = nullptr;
+    int rc = get_plan_plain_wgrad(h, w, k, stride, (h + stride - 1) / stride, (w + stride - 1) / stride, wpg, gmax, &pl, false);
+    SKY_REQUIRE(rc == SKY_OK, rc, "no weight-gradient plan for this convolution");
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : g_plain)
+        if (&kv.second->dev == pl) {
+            const HostPlan &hp = *kv.second;
+            if (units) memcpy(units, hp.wg_units.data(), hp.wg_units.size() * sizeof(WgUnit));
+            if (groups) memcpy(groups, hp.wg_groups.data(), hp.wg_groups.size() * sizeof(WgGroup));
+            return export_plan(hp, rows, strips, wins, nullptr, nullptr);
+        }
+    return SKY_ERR_INVALID;
+}
+
 extern "C" int sky_conv_strip_plan_info(int h, int w, int k, int stride, int transposed, int out_h, int out_w, int ph0, int pw0, int *out8)
 {
     SKY_REQUIRE(out8, SKY_ERR_INVALID, "NULL pointer");

@@ -368,3 +368,45 @@ def test_wgrad_schedule_covers_every_tile_once(pkg):
                 if u < nuidx:
                     seen[u, pb * TP:min(ntiles, pb * TP + TP)] += 1
         assert (seen == 1).all(), (nuidx, ntiles, P, TP, U)
+
+
+@pytest.mark.parametrize("h,w,k,stride,wpg,gmax", [(8, 32, 3, 1, 1, 4), (16, 16, 3, 2, 4, 16), (8, 32, 4, 2, 2, 8), (4, 16, 4, 1, 1, 4), (16, 64, 7, 1, 4, 16),
+                                                   (5, 12, 3, 2, 2, 8), (7, 9, 1, 1, 4, 16)])
+def test_plain_wgrad_plan_reproduces_the_weight_gradient(pkg, h, w, k, stride, wpg, gmax):
+    """Weight-gradient plan of a plain SAME convolution (tf.nn.conv2d, ops.py:41; stride 1 / 2, even kernels, 1x1) evaluated in numpy
+    against autograd through the oracle's conv."""
+    from oracle import model_oracle as M
+    lib, chk = pkg._lib.LIB, pkg._lib.check
+    info = np.zeros(12, np.int32)
+    chk(lib.sky_conv_strip_wgrad_plan_info(h, w, k, stride, wpg, gmax, _vp(info)))
+    rows, strips, wins = np.zeros(int(info[0]), ROW), np.zeros(int(info[1]), STRIP), np.zeros(int(info[2]), WIN)
+    units, groups = np.zeros(int(info[8]), UNIT), np.zeros(int(info[9]), GROUP)
+    chk(lib.sky_conv_strip_wgrad_plan_export(h, w, k, stride, wpg, gmax, _vp(rows), _vp(strips), _vp(wins), _vp(units), _vp(groups)))
+    assert int(info[5]) == 8 and int(info[6]) == 8
+    rng = np.random.default_rng(h * 100 + w + k + stride)
+    B, C, F = 3, 4, 5
+    x = rng.standard_normal((B, h, w, C))
+    wt = torch.from_numpy(rng.standard_normal((k, k, C, F))).requires_grad_(True)
+    y = M.conv2d_same(torch.from_numpy(x), wt, torch.zeros(F, dtype=torch.float64), stride=stride, acc_dtype=torch.float64)
+    dy = rng.standard_normal(tuple(y.shape))
+    y.backward(torch.from_numpy(dy))
+    want = wt.grad.numpy().reshape(k * k, C, F)
+    OW = dy.shape[2]
+    dk = np.zeros((k * k, C, F))
+    seen = np.zeros(len(wins), np.int32)
+    for u in units:
+        rp, sd = rows[u["row"]], strips[u["strip"]]
+        assert 1 <= u["ge"] - u["gb"] <= gmax and sd["kind"] == 0 and sd["r1"] < 0 and sd["wy0"] == 1.0
+        for g in groups[u["gb"]:u["ge"]]:
+            for q, wi in enumerate(g["win"]):
+                if wi < 0:
+                    continue
+                assert q < wpg and wins[wi]["start_row"] == g["start_row"] + 8 * q
+                seen[wi] += 1
+                shift = int(sd["u0"]) + int(wins[wi]["start_row"]) // 8
+                for j in range(OW):
+                    c = int(sd["cm"]) * (j + shift) + int(sd["c0"])
+                    if 0 <= c < w:
+                        dk[int(wins[wi]["wtile0"])] += np.einsum("bc,bf->cf", x[:, sd["r0"], c], dy[:, rp["out_row"], j])
+    assert (seen == 1).all()
+    assert np.linalg.norm(dk - want) / np.linalg.norm(want) < 1e-12
